@@ -1,0 +1,165 @@
+/* pt_b200.h -- C ABI of the B200-native wavefront path tracer (libpt_b200.so).
+ *
+ * Drop-in boundary for the hot path of CIS565-Fall-2014/Project3-Pathtracer.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference repo root).  Plain pointers and sizes only;
+ * all pointers are HOST pointers unless a name says `device`.  Every function returns 0 on success and a
+ * negative pt_status otherwise; pt_last_error() gives the message.  The library never calls exit() (the
+ * reference does: src/raytraceKernel.cu:19-25) and never throws across the boundary.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with PT_ERR_CUDA.
+ *
+ * A context is not thread-safe (the reference is single-threaded: src/main.cpp:63-82); use one per GPU.
+ */
+#ifndef PT_B200_H
+#define PT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PT_ABI_VERSION 1
+
+typedef enum {
+  PT_OK = 0,
+  PT_ERR_INVALID = -1, /* bad argument */
+  PT_ERR_CUDA = -2,    /* CUDA runtime error or no device */
+  PT_ERR_IO = -3,      /* file could not be read / written */
+  PT_ERR_PARSE = -4,   /* malformed scene file */
+  PT_ERR_STATE = -5    /* call order (e.g. render on a destroyed context) */
+} pt_status;
+
+/* ---- POD images of the reference's structs (byte-for-byte the same layout) ---- */
+
+/* staticGeom, src/sceneStructs.h:32-40 (172 bytes); cudaMat4 = 4 ROWS x,y,z,w, src/cudaMat4.h:18-23 */
+typedef struct {
+  int32_t type;       /* GEOMTYPE src/sceneStructs.h:14: 0 SPHERE, 1 CUBE, 2 MESH (never hit) */
+  int32_t materialid;
+  float translation[3];
+  float rotation[3];
+  float scale[3];
+  float transform[16];
+  float inverseTransform[16];
+} pt_static_geom;
+
+/* material, src/sceneStructs.h:63-74 (64 bytes) */
+typedef struct {
+  float color[3];
+  float specularExponent;
+  float specularColor[3];
+  float hasReflective;
+  float hasRefractive;
+  float indexOfRefraction;
+  float hasScatter;
+  float absorptionCoefficient[3];
+  float reducedScatterCoefficient;
+  float emittance;
+} pt_material;
+
+/* cameraData, src/sceneStructs.h:42-48 (52 bytes); fov = half-angles in degrees (src/scene.cpp:203-207) */
+typedef struct {
+  float resolution[2];
+  float position[3];
+  float view[3];
+  float up[3];
+  float fov[2];
+} pt_camera_data;
+
+/* Thin lens for depth of field.  The reference camera has no such field (src/sceneStructs.h:50-61); the scene
+ * loader reads it from a new top-level LENS block, which the reference's dispatcher ignores (src/scene.cpp:22-31). */
+typedef struct {
+  float aperture;       /* lens radius, 0 = pinhole */
+  float focal_distance; /* plane of focus, measured along the view axis */
+} pt_lens;
+
+typedef struct pt_context pt_context;
+
+/* ---- library ---- */
+int pt_abi_version(void);
+const char* pt_last_error(void);
+int pt_device_count(int* count);
+
+/* ---- context: replaces the per-call cudaMalloc/upload/free of cudaRaytraceCore (src/raytraceKernel.cu:118-138,
+ * 157-159).  Geometry (one frame, already flattened as in :123-134), materials (never uploaded by the reference,
+ * SURVEY.md D11) and the camera (:141-146) are uploaded once and stay resident in HBM. ---- */
+int pt_context_create(const pt_static_geom* geoms, int n_geoms, const pt_material* materials, int n_materials,
+                      const pt_camera_data* cam, const pt_lens* lens /* may be NULL */, int device,
+                      pt_context** out);
+int pt_context_destroy(pt_context* ctx);
+/* replace the scene of an existing context (next animation frame: src/main.cpp:147-157); keeps the image size */
+int pt_update_scene(pt_context* ctx, const pt_static_geom* geoms, int n_geoms, const pt_material* materials,
+                    int n_materials, const pt_camera_data* cam, const pt_lens* lens);
+/* upper bound on paths in flight per wavefront (rounded down to whole samples of the frame, at least one).
+ * Default: 16 Mi paths. Path state costs 96 bytes per path (two ping-pong buffers of 3 float4). */
+int pt_set_wavefront_paths(pt_context* ctx, uint64_t max_paths);
+/* run on a caller-owned cudaStream_t instead of the context's own stream (NULL restores it) */
+int pt_set_stream(pt_context* ctx, void* cuda_stream);
+
+/* ---- render: replaces the raytraceRay launch (src/raytraceKernel.cu:149) and its per-iteration host round trip.
+ * Traces samples [first_sample, first_sample + n_samples) of every pixel to at most max_depth segments and ADDS
+ * their radiance to the accumulation buffer in HBM.  Asynchronous; pt_sync / pt_download_* wait for it.
+ * The reference's `iterations` argument (1-based sample number, src/main.cpp:95) is first_sample + 1. ---- */
+int pt_render(pt_context* ctx, uint32_t first_sample, uint32_t n_samples, int max_depth, uint64_t seed);
+int pt_sync(pt_context* ctx);
+/* zero the accumulation buffer and the counters: clearImage (src/raytraceKernel.cu:48-55) */
+int pt_clear(pt_context* ctx);
+/* GPU time of the most recent pt_render call, CUDA events on the launching stream; waits for it */
+int pt_last_render_ms(pt_context* ctx, float* ms);
+
+/* ---- image out: replaces the D2H of renderCam->image (src/raytraceKernel.cu:154).  rgb = W*H*3 floats in the
+ * renderCam->image layout (index = x + y*W, src/main.cpp:122). ---- */
+int pt_download_sum(pt_context* ctx, float* rgb);
+int pt_download_mean(pt_context* ctx, float* rgb, uint32_t spp); /* sum / spp */
+/* overwrite the accumulation buffer (resume, or the running mean of the compat shim) */
+int pt_upload_sum(pt_context* ctx, const float* rgb);
+/* sendImageToPBO (src/raytraceKernel.cu:58-89): uchar4{r,g,b,0} = min(mean*255, 255), truncated.
+ * Either destination may be NULL.  device_rgba8 is a DEVICE pointer (the reference's mapped PBO, src/main.cpp:96). */
+int pt_resolve_rgba8(pt_context* ctx, uint32_t spp, uint8_t* host_rgba8, void* device_rgba8);
+/* the float4[W*H] accumulation buffer itself (DEVICE pointer), for the multi-GPU reduce done by the host plumbing */
+int pt_accum_device_ptr(pt_context* ctx, void** device_ptr, size_t* bytes);
+
+/* ---- counters: paths started, segments traced (= sum of live), live[d] = paths for which
+ * closest-hit ran at depth d; live must have room for 64 entries.  Waits for outstanding renders. ---- */
+int pt_counters(pt_context* ctx, uint64_t* paths, uint64_t* segments, uint64_t* live);
+/* number of this library's kernels launched for this context so far (render + resolve kernels) */
+int pt_launch_count(pt_context* ctx, uint64_t* launches);
+
+/* ---- stage entry points (same kernels' device functions; used by the parity tests and by callers that want one
+ * stage).  All buffers are host buffers of n elements (x3 floats for vectors). ---- */
+/* raycastFromCameraKernel (src/raytraceKernel.cu:40-45) + depth of field */
+int pt_raygen(pt_context* ctx, uint64_t seed, int n, const uint32_t* pixel, const uint32_t* sample, float* origin,
+              float* direction);
+/* closest hit over all geoms: sphereIntersectionTest / boxIntersectionTest (src/intersections.h:74-117);
+ * geom_id = -1 and t = -1 on a miss */
+int pt_intersect(pt_context* ctx, int n, const float* origin, const float* direction, int32_t* geom_id, float* t,
+                 float* point, float* normal);
+/* the stream-compaction primitive (README.md:63-70) on its own: keeps values[i] where flags[i] != 0, order
+ * preserved; out must have room for n entries */
+int pt_compact_u32(int device, const uint32_t* values, const uint8_t* flags, uint64_t n, uint32_t* out,
+                   uint64_t* n_out);
+
+/* ---- scene file and image file (host side; same formats as the reference) ---- */
+typedef struct pt_scene pt_scene;
+/* scene::scene(string), src/scene.cpp:11-35.  rotat_degrees = 0 reproduces the reference exactly (ROTAT is
+ * consumed as radians); 1 converts ROTAT from degrees. */
+int pt_scene_load(const char* path, int rotat_degrees, pt_scene** out);
+int pt_scene_free(pt_scene* s);
+int pt_scene_info(const pt_scene* s, int* n_geoms, int* n_materials, int* n_frames, int* width, int* height,
+                  int* iterations, char* image_name, int image_name_cap);
+/* flatten one frame the way cudaRaytraceCore does (src/raytraceKernel.cu:123-146); arrays sized by pt_scene_info */
+int pt_scene_frame(const pt_scene* s, int frame, pt_static_geom* geoms, pt_material* materials,
+                   pt_camera_data* cam, pt_lens* lens);
+/* the save path of runCuda (src/main.cpp:118-139) + image::saveImageRGB (src/image.cpp:46-88): mirror x, identity
+ * gamma, clamp(f*255,0,255) truncated, ".<frame>" spliced before .png/.bmp, BMP iff the name ends in "bmp".
+ * force_png = 1 rewrites a trailing .bmp to .png first (headless default).  out_name may be NULL. */
+int pt_save_image(const float* rgb, int width, int height, const char* image_name, int frame, int force_png,
+                  char* out_name, int out_name_cap);
+/* the 8-bit conversion alone: rgb8 = W*H*3 bytes, rows top-down, x mirrored (what the file holds) */
+int pt_image_to_rgb8(const float* rgb, int width, int height, uint8_t* rgb8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PT_B200_H */

@@ -1,0 +1,249 @@
+"""project3-pathtracer_b200 -- host-side mirror of the reference interface over libpt_b200.so.
+
+B200-native wavefront path tracer, drop-in for the hot path of CIS565-Fall-2014/Project3-Pathtracer
+(cudaRaytraceCore, reference src/raytraceKernel.cu:108-165).  Everything here is a thin ctypes layer over the C ABI
+declared in include/pt_b200.h; the compute lives in csrc/ (hand-written CUDA for sm_100a).
+
+There is NO CPU fallback: if the shared library is missing or no CUDA device is present, calls raise.
+
+The directory name contains a hyphen, so import it with importlib:
+
+    import importlib; pt = importlib.import_module("project3-pathtracer_b200")
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libpt_b200.so")
+
+# numpy images of the reference structs (src/sceneStructs.h:32-48,63-74)
+GEOM_DTYPE = np.dtype([("type", "<i4"), ("materialid", "<i4"), ("translation", "<f4", (3,)), ("rotation", "<f4", (3,)),
+                       ("scale", "<f4", (3,)), ("transform", "<f4", (16,)), ("inverseTransform", "<f4", (16,))])
+MATERIAL_DTYPE = np.dtype([("color", "<f4", (3,)), ("specularExponent", "<f4"), ("specularColor", "<f4", (3,)),
+                           ("hasReflective", "<f4"), ("hasRefractive", "<f4"), ("indexOfRefraction", "<f4"),
+                           ("hasScatter", "<f4"), ("absorptionCoefficient", "<f4", (3,)),
+                           ("reducedScatterCoefficient", "<f4"), ("emittance", "<f4")])
+CAMERA_DTYPE = np.dtype([("resolution", "<f4", (2,)), ("position", "<f4", (3,)), ("view", "<f4", (3,)),
+                         ("up", "<f4", (3,)), ("fov", "<f4", (2,))])
+LENS_DTYPE = np.dtype([("aperture", "<f4"), ("focal_distance", "<f4")])
+assert GEOM_DTYPE.itemsize == 172 and MATERIAL_DTYPE.itemsize == 64 and CAMERA_DTYPE.itemsize == 52
+
+SPHERE, CUBE, MESH = 0, 1, 2
+
+
+class PtError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libpt_b200.so (building it first if sources are newer).  Fails loudly; never falls back."""
+    global _lib
+    if _lib is None:
+        _build.build()
+        if not os.path.exists(LIB_PATH):
+            raise PtError("libpt_b200.so is missing: the CUDA extension is required (no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.pt_last_error.restype = C.c_char_p
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise PtError("pt_b200 error %d: %s" % (rc, lib().pt_last_error().decode(errors="replace")))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def device_count():
+    n = C.c_int()
+    _check(lib().pt_device_count(C.byref(n)))
+    return n.value
+
+
+class Context:
+    """Scene + path-state buffers + accumulation image resident on one GPU (pt_context_* in include/pt_b200.h)."""
+
+    def __init__(self, geoms, materials, camera, lens=None, device=0):
+        self._h = C.c_void_p()
+        g = _arr(geoms, GEOM_DTYPE)
+        m = _arr(materials, MATERIAL_DTYPE)
+        cam = _arr(camera, CAMERA_DTYPE).reshape(-1)[:1]
+        ln = None if lens is None else np.array([(lens[0], lens[1])], LENS_DTYPE)
+        _check(lib().pt_context_create(_p(g), C.c_int(g.shape[0]), _p(m), C.c_int(m.shape[0]), _p(cam),
+                                       _p(ln) if ln is not None else None, C.c_int(device), C.byref(self._h)))
+        self.width, self.height = int(cam["resolution"][0][0]), int(cam["resolution"][0][1])
+        self.npix = self.width * self.height
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().pt_context_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def update_scene(self, geoms, materials, camera, lens=None):
+        g, m = _arr(geoms, GEOM_DTYPE), _arr(materials, MATERIAL_DTYPE)
+        cam = _arr(camera, CAMERA_DTYPE).reshape(-1)[:1]
+        ln = None if lens is None else np.array([(lens[0], lens[1])], LENS_DTYPE)
+        _check(lib().pt_update_scene(self._h, _p(g), C.c_int(g.shape[0]), _p(m), C.c_int(m.shape[0]), _p(cam),
+                                     _p(ln) if ln is not None else None))
+
+    def set_wavefront_paths(self, max_paths):
+        _check(lib().pt_set_wavefront_paths(self._h, C.c_uint64(int(max_paths))))
+
+    def set_stream(self, cuda_stream):
+        _check(lib().pt_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def render(self, first_sample, n_samples, max_depth, seed=0):
+        _check(lib().pt_render(self._h, C.c_uint32(first_sample), C.c_uint32(n_samples), C.c_int(max_depth),
+                               C.c_uint64(seed)))
+
+    def sync(self):
+        _check(lib().pt_sync(self._h))
+
+    def clear(self):
+        _check(lib().pt_clear(self._h))
+
+    def last_render_ms(self):
+        ms = C.c_float()
+        _check(lib().pt_last_render_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def download_sum(self, out=None):
+        out = np.empty((self.npix, 3), np.float32) if out is None else out
+        _check(lib().pt_download_sum(self._h, _p(out)))
+        return out
+
+    def download_mean(self, spp, out=None):
+        out = np.empty((self.npix, 3), np.float32) if out is None else out
+        _check(lib().pt_download_mean(self._h, _p(out), C.c_uint32(spp)))
+        return out
+
+    def upload_sum(self, rgb):
+        rgb = _arr(rgb, np.float32)
+        assert rgb.size == self.npix * 3
+        _check(lib().pt_upload_sum(self._h, _p(rgb)))
+
+    def resolve_rgba8(self, spp, device_ptr=None):
+        out = np.empty((self.npix, 4), np.uint8)
+        _check(lib().pt_resolve_rgba8(self._h, C.c_uint32(spp), _p(out), C.c_void_p(device_ptr)))
+        return out
+
+    def accum_device_ptr(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(lib().pt_accum_device_ptr(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def counters(self):
+        paths, segs = C.c_uint64(), C.c_uint64()
+        live = np.zeros(64, np.uint64)
+        _check(lib().pt_counters(self._h, C.byref(paths), C.byref(segs), _p(live)))
+        return paths.value, segs.value, live
+
+    def launch_count(self):
+        n = C.c_uint64()
+        _check(lib().pt_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def raygen(self, seed, pixel, sample):
+        pixel, sample = _arr(pixel, np.uint32).ravel(), _arr(sample, np.uint32).ravel()
+        n = pixel.shape[0]
+        o, d = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+        _check(lib().pt_raygen(self._h, C.c_uint64(seed), C.c_int(n), _p(pixel), _p(sample), _p(o), _p(d)))
+        return o, d
+
+    def intersect(self, origin, direction):
+        o, d = _arr(origin, np.float32).reshape(-1, 3), _arr(direction, np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        gid, t = np.zeros(n, np.int32), np.zeros(n, np.float32)
+        p, nr = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+        _check(lib().pt_intersect(self._h, C.c_int(n), _p(o), _p(d), _p(gid), _p(t), _p(p), _p(nr)))
+        return gid, t, p, nr
+
+
+def compact_u32(values, flags, device=0):
+    """Stream compaction primitive on its own (pt_compact_u32): values[flags != 0], order preserved."""
+    v, f = _arr(values, np.uint32).ravel(), _arr(flags, np.uint8).ravel()
+    assert v.shape == f.shape
+    out = np.empty(max(v.shape[0], 1), np.uint32)
+    n_out = C.c_uint64()
+    _check(lib().pt_compact_u32(C.c_int(device), _p(v), _p(f), C.c_uint64(v.shape[0]), _p(out), C.byref(n_out)))
+    return out[: n_out.value].copy()
+
+
+class Scene:
+    """scene::scene(string) of the reference (src/scene.cpp:11-35) through pt_scene_load."""
+
+    def __init__(self, path, rotat_degrees=False):
+        self._h = C.c_void_p()
+        _check(lib().pt_scene_load(str(path).encode(), C.c_int(1 if rotat_degrees else 0), C.byref(self._h)))
+        ng, nm, nf, w, h, it = (C.c_int() for _ in range(6))
+        name = C.create_string_buffer(512)
+        _check(lib().pt_scene_info(self._h, C.byref(ng), C.byref(nm), C.byref(nf), C.byref(w), C.byref(h), C.byref(it),
+                                   name, C.c_int(512)))
+        self.n_geoms, self.n_materials, self.n_frames = ng.value, nm.value, nf.value
+        self.width, self.height, self.iterations = w.value, h.value, it.value
+        self.image_name = name.value.decode()
+
+    def frame(self, frame=0):
+        g = np.zeros(self.n_geoms, GEOM_DTYPE)
+        m = np.zeros(self.n_materials, MATERIAL_DTYPE)
+        cam = np.zeros(1, CAMERA_DTYPE)
+        lens = np.zeros(1, LENS_DTYPE)
+        _check(lib().pt_scene_frame(self._h, C.c_int(frame), _p(g), _p(m), _p(cam), _p(lens)))
+        return g, m, cam, (float(lens["aperture"][0]), float(lens["focal_distance"][0]))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().pt_scene_free(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+
+def save_image(rgb, width, height, image_name, frame=0, force_png=True):
+    """runCuda's save path (src/main.cpp:118-139) + image::saveImageRGB (src/image.cpp:46-88)."""
+    rgb = _arr(rgb, np.float32)
+    assert rgb.size == width * height * 3
+    out = C.create_string_buffer(1024)
+    _check(lib().pt_save_image(_p(rgb), C.c_int(width), C.c_int(height), str(image_name).encode(), C.c_int(frame),
+                               C.c_int(1 if force_png else 0), out, C.c_int(1024)))
+    return out.value.decode()
+
+
+def image_to_rgb8(rgb, width, height):
+    rgb = _arr(rgb, np.float32)
+    out = np.empty((height, width, 3), np.uint8)
+    _check(lib().pt_image_to_rgb8(_p(rgb), C.c_int(width), C.c_int(height), _p(out)))
+    return out
+
+
+def render_frame(geoms, materials, camera, spp, max_depth, seed=0, lens=None, device=0, wavefront_paths=None):
+    """Convenience: one whole render -> (mean image (H*W,3) float32, paths, segments, live, gpu_ms)."""
+    with Context(geoms, materials, camera, lens, device) as ctx:
+        if wavefront_paths:
+            ctx.set_wavefront_paths(wavefront_paths)
+        ctx.render(0, spp, max_depth, seed)
+        img = ctx.download_mean(spp)
+        paths, segs, live = ctx.counters()
+        return img, paths, segs, live, ctx.last_render_ms()

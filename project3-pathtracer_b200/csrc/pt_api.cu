@@ -1,0 +1,511 @@
+// pt_api.cu -- the C ABI (include/pt_b200.h) over the wavefront kernels.
+//
+// Replaces the body of cudaRaytraceCore (reference src/raytraceKernel.cu:108-165): instead of malloc / upload /
+// launch / download / free once per sample, a context keeps the scene, the path-state ping-pong buffers and the
+// accumulation image resident in HBM, and pt_render() traces any number of samples with no host round trip.
+//
+// Compiled with -fmad=false (see pt_device.cuh: the arithmetic contract).
+#include "../../include/pt_b200.h"
+#include "pt_kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ptd;
+
+// ---------------------------------------------------------------- errors
+static thread_local std::string g_err;
+extern "C" void pt_set_error_(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+extern "C" const char* pt_last_error(void) { return g_err.c_str(); }
+extern "C" int pt_abi_version(void) { return PT_ABI_VERSION; }
+
+#define CU(call)                                                                             \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      pt_set_error_("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return PT_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+extern "C" int pt_device_count(int* count) {
+  if (!count) { pt_set_error_("count is NULL"); return PT_ERR_INVALID; }
+  *count = 0;
+  CU(cudaGetDeviceCount(count));
+  return PT_OK;
+}
+
+// ---------------------------------------------------------------- context
+struct pt_context {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  // scene
+  int n_geoms = 0, n_mats = 0, geom_cap = 0;
+  float4* d_rows = nullptr;  // 6 arrays of n_geoms float4
+  int2* d_meta = nullptr;
+  float4* d_mats = nullptr;
+  GeomSoA g{};
+  RaygenConsts cam{};
+  uint32_t W = 0, H = 0, npix = 0;
+  // wavefront
+  uint64_t wf_capacity = 0;  // paths
+  float4* d_state = nullptr; // 6 arrays of wf_capacity float4: o0 d0 t0 o1 d1 t1
+  uint64_t* d_status = nullptr;
+  WfCtrl* d_ctrl = nullptr;
+  unsigned long long* d_live = nullptr;  // kMaxDepth totals
+  uint32_t epoch = 0;
+  uint64_t paths_total = 0;
+  uint64_t launches = 0;     // kernels of this library launched on behalf of this context
+  // image
+  float4* d_accum = nullptr;
+  float* d_rgb = nullptr;      // staging for packed RGB
+  uchar4* d_rgba8 = nullptr;   // staging for the 8-bit resolve
+  int grid_blocks[4] = {0, 0, 0, 0};  // persistent grid per (FIRST,LAST) variant
+  size_t smem_bytes = 0;
+};
+
+static const uint64_t kDefaultWavefrontPaths = 16ull << 20;
+static const int kMaxSmemGeoms = 1024;  // 104 KB of shared memory per chunk at most
+
+// host-side camera constants; must follow oracle or_raygen's operation order exactly (binary32, unfused)
+static f3 h_mk(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+static f3 h_normalize(f3 v) {
+  float sqr = (v.x * v.x + v.y * v.y) + v.z * v.z;
+  float inv = 1.0f / sqrtf(sqr);
+  return h_mk(v.x * inv, v.y * inv, v.z * inv);
+}
+static f3 h_cross(f3 x, f3 y) { return h_mk(x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y); }
+static RaygenConsts make_raygen(const pt_camera_data& c, const pt_lens* lens) {
+  RaygenConsts R;
+  R.eye = h_mk(c.position[0], c.position[1], c.position[2]);
+  R.w = h_normalize(h_mk(c.view[0], c.view[1], c.view[2]));
+  R.right = h_normalize(h_cross(R.w, h_mk(c.up[0], c.up[1], c.up[2])));
+  R.vup = h_cross(R.right, R.w);
+  float tx = tanf(c.fov[0] * 0.017453292f);
+  float ty = tanf(c.fov[1] * 0.017453292f);
+  R.Hh = h_mk(R.right.x * tx, R.right.y * tx, R.right.z * tx);
+  R.Vv = h_mk(R.vup.x * ty, R.vup.y * ty, R.vup.z * ty);
+  R.fw = c.resolution[0];
+  R.fh = c.resolution[1];
+  R.W = (uint32_t)(int)c.resolution[0];
+  R.npix = R.W * (uint32_t)(int)c.resolution[1];
+  R.aperture = lens ? lens->aperture : 0.0f;
+  R.focal = lens ? lens->focal_distance : 0.0f;
+  return R;
+}
+
+template <bool F, bool L>
+static int setup_variant(pt_context* c, int slot) {
+  CU(cudaFuncSetAttribute(k_bounce<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce<F, L>, kTile, c->smem_bytes));
+  if (per_sm < 1) { pt_set_error_("k_bounce does not fit on an SM"); return PT_ERR_CUDA; }
+  c->grid_blocks[slot] = per_sm * c->sm_count;
+  return PT_OK;
+}
+
+static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms, const pt_material* mats, int n_mats,
+                        const pt_camera_data* cam, const pt_lens* lens, bool first) {
+  if (!geoms || n_geoms <= 0 || !mats || n_mats <= 0 || !cam) {
+    pt_set_error_("geoms, materials and camera are required and must be non-empty");
+    return PT_ERR_INVALID;
+  }
+  const int Wi = (int)cam->resolution[0], Hi = (int)cam->resolution[1];
+  if (Wi <= 0 || Hi <= 0 || (uint64_t)Wi * (uint64_t)Hi > (1ull << 31)) {
+    pt_set_error_("bad resolution %d x %d", Wi, Hi);
+    return PT_ERR_INVALID;
+  }
+  if (!first && ((uint32_t)Wi != c->W || (uint32_t)Hi != c->H)) {
+    pt_set_error_("pt_update_scene cannot change the resolution (%ux%u -> %dx%d)", c->W, c->H, Wi, Hi);
+    return PT_ERR_INVALID;
+  }
+  for (int i = 0; i < n_geoms; i++) {
+    if (geoms[i].type <= 1 && (geoms[i].materialid < 0 || geoms[i].materialid >= n_mats)) {
+      pt_set_error_("object %d references material %d, but there are %d materials", i, geoms[i].materialid, n_mats);
+      return PT_ERR_INVALID;
+    }
+  }
+  // array of structures (172-byte staticGeom) -> structure of arrays of float4 rows
+  std::vector<float4> rows((size_t)6 * n_geoms);
+  std::vector<int2> meta(n_geoms);
+  for (int i = 0; i < n_geoms; i++) {
+    const float* inv = geoms[i].inverseTransform;
+    const float* fwd = geoms[i].transform;
+    for (int r = 0; r < 3; r++) {
+      rows[(size_t)r * n_geoms + i] = make_float4(inv[4 * r], inv[4 * r + 1], inv[4 * r + 2], inv[4 * r + 3]);
+      rows[(size_t)(3 + r) * n_geoms + i] = make_float4(fwd[4 * r], fwd[4 * r + 1], fwd[4 * r + 2], fwd[4 * r + 3]);
+    }
+    meta[i] = make_int2(geoms[i].type, geoms[i].type <= 1 ? geoms[i].materialid : 0);
+  }
+  if (n_geoms != c->n_geoms) {
+    if (c->d_rows) CU(cudaFree(c->d_rows));
+    if (c->d_meta) CU(cudaFree(c->d_meta));
+    c->d_rows = nullptr; c->d_meta = nullptr;
+    CU(cudaMalloc(&c->d_rows, rows.size() * sizeof(float4)));
+    CU(cudaMalloc(&c->d_meta, meta.size() * sizeof(int2)));
+  }
+  if (n_mats != c->n_mats) {
+    if (c->d_mats) CU(cudaFree(c->d_mats));
+    c->d_mats = nullptr;
+    CU(cudaMalloc(&c->d_mats, (size_t)n_mats * sizeof(pt_material)));
+  }
+  CU(cudaMemcpyAsync(c->d_rows, rows.data(), rows.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_meta, meta.data(), meta.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_mats, mats, (size_t)n_mats * sizeof(pt_material), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // the host vectors die at return
+  c->n_geoms = n_geoms;
+  c->n_mats = n_mats;
+  c->g.inv0 = c->d_rows; c->g.inv1 = c->d_rows + n_geoms; c->g.inv2 = c->d_rows + 2 * (size_t)n_geoms;
+  c->g.fwd0 = c->d_rows + 3 * (size_t)n_geoms; c->g.fwd1 = c->d_rows + 4 * (size_t)n_geoms;
+  c->g.fwd2 = c->d_rows + 5 * (size_t)n_geoms;
+  c->g.meta = c->d_meta;
+  c->cam = make_raygen(*cam, lens);
+  c->W = (uint32_t)Wi; c->H = (uint32_t)Hi; c->npix = c->W * c->H;
+  const int cap = n_geoms < kMaxSmemGeoms ? n_geoms : kMaxSmemGeoms;
+  if (cap != c->geom_cap) {
+    c->geom_cap = cap;
+    c->smem_bytes = geom_smem_bytes(cap);
+    int rc;
+    if ((rc = setup_variant<true, false>(c, 0))) return rc;
+    if ((rc = setup_variant<true, true>(c, 1))) return rc;
+    if ((rc = setup_variant<false, false>(c, 2))) return rc;
+    if ((rc = setup_variant<false, true>(c, 3))) return rc;
+    CU(cudaFuncSetAttribute(k_intersect_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  }
+  return PT_OK;
+}
+
+static int alloc_wavefront(pt_context* c, uint64_t max_paths) {
+  uint64_t spp = max_paths / c->npix;
+  if (spp < 1) spp = 1;
+  const uint64_t cap = spp * c->npix;
+  if (cap > 0xFFFFFF00ull) { pt_set_error_("wavefront of %llu paths exceeds 2^32", (unsigned long long)cap); return PT_ERR_INVALID; }
+  if (cap == c->wf_capacity) return PT_OK;
+  if (c->d_state) CU(cudaFree(c->d_state));
+  if (c->d_status) CU(cudaFree(c->d_status));
+  c->d_state = nullptr; c->d_status = nullptr; c->wf_capacity = 0;
+  CU(cudaMalloc(&c->d_state, 6 * cap * sizeof(float4)));
+  const uint64_t tiles = (cap + kTile - 1) / kTile;
+  CU(cudaMalloc(&c->d_status, tiles * sizeof(uint64_t)));
+  CU(cudaMemsetAsync(c->d_status, 0, tiles * sizeof(uint64_t), c->stream));
+  c->wf_capacity = cap;
+  return PT_OK;
+}
+
+extern "C" int pt_context_destroy(pt_context* c) {
+  if (!c) return PT_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_rows); cudaFree(c->d_meta); cudaFree(c->d_mats); cudaFree(c->d_state); cudaFree(c->d_status);
+  cudaFree(c->d_ctrl); cudaFree(c->d_live); cudaFree(c->d_accum); cudaFree(c->d_rgb); cudaFree(c->d_rgba8);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return PT_OK;
+}
+
+extern "C" int pt_context_create(const pt_static_geom* geoms, int n_geoms, const pt_material* materials,
+                                 int n_materials, const pt_camera_data* cam, const pt_lens* lens, int device,
+                                 pt_context** out) {
+  if (!out) { pt_set_error_("out is NULL"); return PT_ERR_INVALID; }
+  *out = nullptr;
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { pt_set_error_("device %d out of range (%d devices)", device, ndev); return PT_ERR_INVALID; }
+  CU(cudaSetDevice(device));
+  pt_context* c = new pt_context();
+  c->device = device;
+  int rc = PT_OK;
+  auto fail = [&](int code) { std::string keep = g_err; pt_context_destroy(c); g_err = keep; return code; };
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { pt_set_error_("cudaGetDeviceProperties failed"); return fail(PT_ERR_CUDA); }
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+    pt_set_error_("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(PT_ERR_CUDA);
+  }
+  c->stream = c->own_stream;
+  if ((rc = upload_scene(c, geoms, n_geoms, materials, n_materials, cam, lens, true))) return fail(rc);
+  if (cudaMalloc(&c->d_accum, (size_t)c->npix * sizeof(float4)) != cudaSuccess ||
+      cudaMalloc(&c->d_rgb, (size_t)c->npix * 3 * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&c->d_rgba8, (size_t)c->npix * sizeof(uchar4)) != cudaSuccess ||
+      cudaMalloc(&c->d_ctrl, sizeof(WfCtrl)) != cudaSuccess ||
+      cudaMalloc(&c->d_live, kMaxDepth * sizeof(unsigned long long)) != cudaSuccess) {
+    pt_set_error_("cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(PT_ERR_CUDA);
+  }
+  if ((rc = alloc_wavefront(c, kDefaultWavefrontPaths))) return fail(rc);
+  if ((rc = pt_clear(c))) return fail(rc);
+  *out = c;
+  return PT_OK;
+}
+
+#define CTX(c)                                                       \
+  do {                                                               \
+    if (!(c)) { pt_set_error_("context is NULL"); return PT_ERR_STATE; } \
+    CU(cudaSetDevice((c)->device));                                  \
+  } while (0)
+
+extern "C" int pt_update_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms, const pt_material* materials,
+                               int n_materials, const pt_camera_data* cam, const pt_lens* lens) {
+  CTX(c);
+  CU(cudaStreamSynchronize(c->stream));
+  return upload_scene(c, geoms, n_geoms, materials, n_materials, cam, lens, false);
+}
+
+extern "C" int pt_set_wavefront_paths(pt_context* c, uint64_t max_paths) {
+  CTX(c);
+  CU(cudaStreamSynchronize(c->stream));
+  return alloc_wavefront(c, max_paths);
+}
+
+extern "C" int pt_set_stream(pt_context* c, void* cuda_stream) {
+  CTX(c);
+  CU(cudaStreamSynchronize(c->stream));
+  c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  return PT_OK;
+}
+
+extern "C" int pt_clear(pt_context* c) {
+  CTX(c);
+  CU(cudaMemsetAsync(c->d_accum, 0, (size_t)c->npix * sizeof(float4), c->stream));
+  CU(cudaMemsetAsync(c->d_live, 0, kMaxDepth * sizeof(unsigned long long), c->stream));
+  c->paths_total = 0;
+  return PT_OK;
+}
+
+template <bool F, bool L>
+static cudaError_t launch_bounce(pt_context* c, int slot, const BounceParams& P, uint32_t n_upper) {
+  uint32_t tiles = (n_upper + kTile - 1) / kTile;
+  uint32_t grid = (uint32_t)c->grid_blocks[slot];
+  if (tiles < grid) grid = tiles ? tiles : 1;
+  k_bounce<F, L><<<grid, kTile, c->smem_bytes, c->stream>>>(P);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_samples, int max_depth, uint64_t seed) {
+  CTX(c);
+  if (max_depth < 1 || max_depth > kMaxDepth) { pt_set_error_("max_depth %d outside [1,%d]", max_depth, kMaxDepth); return PT_ERR_INVALID; }
+  if ((uint64_t)first_sample + n_samples > 0xFFFFFFFFull) { pt_set_error_("sample index overflow"); return PT_ERR_INVALID; }
+  CU(cudaEventRecord(c->ev0, c->stream));
+  const uint32_t spp_wf = (uint32_t)(c->wf_capacity / c->npix);
+  float4* S = c->d_state;
+  const uint64_t cap = c->wf_capacity;
+  for (uint32_t s0 = 0; s0 < n_samples; s0 += spp_wf) {
+    const uint32_t ns = (n_samples - s0 < spp_wf) ? (n_samples - s0) : spp_wf;
+    const uint32_t n_first = ns * c->npix;
+    CU(cudaMemsetAsync(c->d_ctrl, 0, sizeof(WfCtrl), c->stream));
+    for (int depth = 0; depth < max_depth; depth++) {
+      BounceParams P;
+      const int in = depth & 1, outb = in ^ 1;
+      P.in_o = S + (3 * in + 0) * cap; P.in_d = S + (3 * in + 1) * cap; P.in_t = S + (3 * in + 2) * cap;
+      P.out_o = S + (3 * outb + 0) * cap; P.out_d = S + (3 * outb + 1) * cap; P.out_t = S + (3 * outb + 2) * cap;
+      P.accum = c->d_accum;
+      P.g = c->g; P.n_geoms = c->n_geoms; P.geom_cap = c->geom_cap;
+      P.mats = c->d_mats;
+      P.cam = c->cam;
+      P.ctrl = c->d_ctrl;
+      P.status = c->d_status;
+      P.epoch = (++c->epoch) & 0x3FFFFFFFu;
+      if (P.epoch == 0) P.epoch = (++c->epoch) & 0x3FFFFFFFu;
+      P.depth = (uint32_t)depth;
+      P.seed = seed;
+      P.first_sample = first_sample + s0;
+      P.n_first = n_first;
+      const bool first = depth == 0, last = depth == max_depth - 1;
+      cudaError_t e;
+      if (first && last) e = launch_bounce<true, true>(c, 1, P, n_first);
+      else if (first) e = launch_bounce<true, false>(c, 0, P, n_first);
+      else if (last) e = launch_bounce<false, true>(c, 3, P, n_first);
+      else e = launch_bounce<false, false>(c, 2, P, n_first);
+      if (e != cudaSuccess) { pt_set_error_("k_bounce launch failed: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
+    }
+    k_accum_counts<<<1, kMaxDepth, 0, c->stream>>>(c->d_ctrl, c->d_live, max_depth);
+    c->launches++;
+    CU(cudaGetLastError());
+    c->paths_total += n_first;
+  }
+  CU(cudaEventRecord(c->ev1, c->stream));
+  c->timed = true;
+  return PT_OK;
+}
+
+extern "C" int pt_sync(pt_context* c) {
+  CTX(c);
+  CU(cudaStreamSynchronize(c->stream));
+  return PT_OK;
+}
+
+extern "C" int pt_last_render_ms(pt_context* c, float* ms) {
+  CTX(c);
+  if (!ms) { pt_set_error_("ms is NULL"); return PT_ERR_INVALID; }
+  if (!c->timed) { pt_set_error_("no render has been recorded"); return PT_ERR_STATE; }
+  CU(cudaEventSynchronize(c->ev1));
+  CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return PT_OK;
+}
+
+static int download_rgb(pt_context* c, float* rgb, float spp, int divide) {
+  if (!rgb) { pt_set_error_("rgb is NULL"); return PT_ERR_INVALID; }
+  const uint32_t blocks = (c->npix + 255) / 256;
+  k_resolve_rgb<<<blocks, 256, 0, c->stream>>>(c->d_accum, c->npix, spp, divide, c->d_rgb);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(rgb, c->d_rgb, (size_t)c->npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return PT_OK;
+}
+extern "C" int pt_download_sum(pt_context* c, float* rgb) { CTX(c); return download_rgb(c, rgb, 1.0f, 0); }
+extern "C" int pt_download_mean(pt_context* c, float* rgb, uint32_t spp) {
+  CTX(c);
+  if (spp == 0) { pt_set_error_("spp is 0"); return PT_ERR_INVALID; }
+  return download_rgb(c, rgb, (float)spp, 1);
+}
+
+extern "C" int pt_upload_sum(pt_context* c, const float* rgb) {
+  CTX(c);
+  if (!rgb) { pt_set_error_("rgb is NULL"); return PT_ERR_INVALID; }
+  CU(cudaMemcpyAsync(c->d_rgb, rgb, (size_t)c->npix * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  k_upload_rgb<<<(c->npix + 255) / 256, 256, 0, c->stream>>>(c->d_rgb, c->npix, c->d_accum);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  return PT_OK;
+}
+
+extern "C" int pt_resolve_rgba8(pt_context* c, uint32_t spp, uint8_t* host_rgba8, void* device_rgba8) {
+  CTX(c);
+  if (spp == 0) { pt_set_error_("spp is 0"); return PT_ERR_INVALID; }
+  uchar4* dst = device_rgba8 ? (uchar4*)device_rgba8 : c->d_rgba8;
+  k_resolve_rgba8<<<(c->npix + 255) / 256, 256, 0, c->stream>>>(c->d_accum, c->npix, (float)spp, dst);
+  CU(cudaGetLastError());
+  if (host_rgba8) CU(cudaMemcpyAsync(host_rgba8, dst, (size_t)c->npix * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return PT_OK;
+}
+
+extern "C" int pt_accum_device_ptr(pt_context* c, void** device_ptr, size_t* bytes) {
+  CTX(c);
+  if (device_ptr) *device_ptr = c->d_accum;
+  if (bytes) *bytes = (size_t)c->npix * sizeof(float4);
+  return PT_OK;
+}
+
+extern "C" int pt_launch_count(pt_context* c, uint64_t* launches) {
+  CTX(c);
+  if (!launches) { pt_set_error_("launches is NULL"); return PT_ERR_INVALID; }
+  *launches = c->launches;
+  return PT_OK;
+}
+
+extern "C" int pt_counters(pt_context* c, uint64_t* paths, uint64_t* segments, uint64_t* live) {
+  CTX(c);
+  unsigned long long h[kMaxDepth];
+  CU(cudaMemcpyAsync(h, c->d_live, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  uint64_t seg = 0;
+  for (int i = 0; i < kMaxDepth; i++) { seg += h[i]; if (live) live[i] = h[i]; }
+  if (segments) *segments = seg;
+  if (paths) *paths = c->paths_total;
+  return PT_OK;
+}
+
+// ---------------------------------------------------------------- stage entry points
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
+};
+
+extern "C" int pt_raygen(pt_context* c, uint64_t seed, int n, const uint32_t* pixel, const uint32_t* sample,
+                         float* origin, float* direction) {
+  CTX(c);
+  if (n < 0 || (n > 0 && (!pixel || !sample || !origin || !direction))) { pt_set_error_("bad arguments"); return PT_ERR_INVALID; }
+  if (n == 0) return PT_OK;
+  for (int i = 0; i < n; i++)
+    if (pixel[i] >= c->npix) { pt_set_error_("pixel[%d] = %u outside the %u-pixel frame", i, pixel[i], c->npix); return PT_ERR_INVALID; }
+  DevBuf<uint32_t> dp, ds;
+  DevBuf<float> dor, ddr;
+  CU(dp.alloc(n)); CU(ds.alloc(n)); CU(dor.alloc(3 * (size_t)n)); CU(ddr.alloc(3 * (size_t)n));
+  CU(cudaMemcpyAsync(dp.p, pixel, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(ds.p, sample, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  k_raygen_list<<<(n + 255) / 256, 256, 0, c->stream>>>(c->cam, seed, n, dp.p, ds.p, dor.p, ddr.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(origin, dor.p, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(direction, ddr.p, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return PT_OK;
+}
+
+extern "C" int pt_intersect(pt_context* c, int n, const float* origin, const float* direction, int32_t* geom_id,
+                            float* t, float* point, float* normal) {
+  CTX(c);
+  if (n < 0 || (n > 0 && (!origin || !direction || !geom_id || !t || !point || !normal))) { pt_set_error_("bad arguments"); return PT_ERR_INVALID; }
+  if (n == 0) return PT_OK;
+  DevBuf<float> dor, ddr, dt, dpnt, dn;
+  DevBuf<int> did;
+  const size_t v = 3 * (size_t)n;
+  CU(dor.alloc(v)); CU(ddr.alloc(v)); CU(dt.alloc(n)); CU(dpnt.alloc(v)); CU(dn.alloc(v)); CU(did.alloc(n));
+  CU(cudaMemcpyAsync(dor.p, origin, v * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(ddr.p, direction, v * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  k_intersect_list<<<(n + kTile - 1) / kTile, kTile, c->smem_bytes, c->stream>>>(c->g, c->n_geoms, c->geom_cap, n, dor.p,
+                                                                                 ddr.p, did.p, dt.p, dpnt.p, dn.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(geom_id, did.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(t, dt.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(point, dpnt.p, v * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(normal, dn.p, v * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return PT_OK;
+}
+
+extern "C" int pt_compact_u32(int device, const uint32_t* values, const uint8_t* flags, uint64_t n, uint32_t* out,
+                              uint64_t* n_out) {
+  if (!n_out || (n > 0 && (!values || !flags || !out))) { pt_set_error_("bad arguments"); return PT_ERR_INVALID; }
+  *n_out = 0;
+  if (n == 0) return PT_OK;
+  if (n > 0xFFFFFF00ull) { pt_set_error_("n too large"); return PT_ERR_INVALID; }
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { pt_set_error_("device %d out of range", device); return PT_ERR_INVALID; }
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  DevBuf<uint32_t> dv, dout, dctl;
+  DevBuf<uint8_t> df;
+  DevBuf<uint64_t> dst;
+  const uint64_t tiles = (n + kTile - 1) / kTile;
+  CU(dv.alloc(n)); CU(dout.alloc(n)); CU(dctl.alloc(2)); CU(df.alloc(n)); CU(dst.alloc(tiles));
+  CU(cudaMemcpy(dv.p, values, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(df.p, flags, n, cudaMemcpyHostToDevice));
+  CU(cudaMemset(dctl.p, 0, 2 * sizeof(uint32_t)));
+  CU(cudaMemset(dst.p, 0, tiles * sizeof(uint64_t)));
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_compact_u32, kTile, 0));
+  uint64_t grid = (uint64_t)per_sm * prop.multiProcessorCount;
+  if (tiles < grid) grid = tiles;
+  k_compact_u32<<<(unsigned)grid, kTile>>>(dv.p, df.p, (uint32_t)n, dout.p, dctl.p + 1, dctl.p, dst.p, 1u);
+  CU(cudaGetLastError());
+  uint32_t cnt = 0;
+  CU(cudaMemcpy(&cnt, dctl.p + 1, sizeof(cnt), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(out, dout.p, (size_t)cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  *n_out = cnt;
+  return PT_OK;
+}

@@ -1,0 +1,311 @@
+// pt_kernels.cuh -- the wavefront kernels (sm_100a).
+//
+//   k_bounce<FIRST,LAST>  one path segment for every live path of the wavefront, fused:
+//                           [FIRST: raygen + depth of field]  (raycastFromCameraKernel, src/raytraceKernel.cu:40-45)
+//                           closest hit over SoA geometry staged in shared memory (src/intersections.h:74-117)
+//                           BSDF sampling with Philox (calculateBSDF, src/interactions.h:99-104)
+//                           radiance accumulation in HBM (the running image of src/raytraceKernel.cu:118-120,154)
+//                           stream compaction of the survivors (README.md:63-70): warp ballot -> block scan ->
+//                           decoupled look-back across tiles, survivors written once, in order, to the other
+//                           ping-pong buffer.
+//                         Persistent CTAs take tiles from a ticket counter, so a tile's predecessors are always
+//                         resident and the look-back cannot deadlock; the live count never visits the host.
+//   k_raygen_list / k_intersect_list   the same device functions on caller-supplied lists (parity entry points)
+//   k_compact_u32                      the compaction primitive on its own
+//   k_resolve_*                        accumulation buffer -> float RGB / uchar4 (sendImageToPBO, :58-89)
+#pragma once
+#include "pt_device.cuh"
+
+namespace ptd {
+
+constexpr int kMaxDepth = 64;
+constexpr int kTile = 256;  // paths per tile = threads per CTA
+
+// per-wavefront control block in HBM, zeroed before each wavefront
+struct WfCtrl {
+  uint32_t count[kMaxDepth + 1];     // count[d] = live paths entering depth d
+  uint32_t tile_ctr[kMaxDepth + 1];  // ticket counter of the depth-d launch
+};
+
+// ---- decoupled look-back (Merrill & Garland 2016) on 64-bit status words ----
+// word = epoch[63:34] | state[33:32] | value[31:0]; a word is valid only if its epoch equals the launch's, so the
+// array never needs clearing between launches (or CUDA-graph replays).
+constexpr uint32_t kStAggregate = 1u, kStPrefix = 2u;
+__device__ __forceinline__ uint64_t st_pack(uint32_t epoch, uint32_t state, uint32_t value) {
+  return ((uint64_t)epoch << 34) | ((uint64_t)state << 32) | (uint64_t)value;
+}
+__device__ __forceinline__ void st_store(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t st_load(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Called by ONE full warp of the CTA that owns `tile`.  aggregate = number of survivors in this tile.
+// Returns the number of survivors in all earlier tiles (exclusive prefix) to every lane.
+__device__ __forceinline__ uint32_t lookback_exclusive(uint64_t* status, uint32_t tile, uint32_t epoch,
+                                                       uint32_t aggregate) {
+  const uint32_t lane = threadIdx.x & 31u;
+  if (lane == 0) st_store(status + tile, st_pack(epoch, tile == 0 ? kStPrefix : kStAggregate, aggregate));
+  if (tile == 0) return 0;
+  uint32_t exclusive = 0;
+  int look = (int)tile - 1;
+  for (;;) {
+    const int t = look - (int)lane;
+    uint32_t state = kStPrefix, value = 0;  // tiles before the first one: empty prefix
+    if (t >= 0) {
+      uint64_t w;
+      do { w = st_load(status + t); } while ((uint32_t)(w >> 34) != epoch);
+      state = (uint32_t)(w >> 32) & 3u;
+      value = (uint32_t)w;
+    }
+    const uint32_t pmask = __ballot_sync(0xffffffffu, state == kStPrefix);
+    const int firstp = pmask ? (__ffs(pmask) - 1) : 31;
+    uint32_t contrib = ((int)lane <= firstp) ? value : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+    exclusive += contrib;
+    if (pmask) break;
+    look -= 32;
+  }
+  if (lane == 0) st_store(status + tile, st_pack(epoch, kStPrefix, exclusive + aggregate));
+  return exclusive;
+}
+
+// Block-level part shared by k_bounce and k_compact_u32: every thread passes its flag, gets its output slot.
+// s_warp (>= 8 words) and s_base are shared scratch.  All threads of the CTA must call.
+// Returns the global slot of this thread's item (meaningful if keep) and the tile's inclusive total via *incl.
+__device__ __forceinline__ uint32_t compact_slot(bool keep, uint64_t* status, uint32_t tile, uint32_t epoch,
+                                                 uint32_t* s_warp, uint32_t* s_base, uint32_t* incl) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+  const uint32_t lane_off = __popc(ballot & ((1u << lane) - 1u));
+  if (lane == 0) s_warp[warp] = __popc(ballot);
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t nw = blockDim.x >> 5;
+    uint32_t c = lane < nw ? s_warp[lane] : 0u;
+    uint32_t incl_w = c;  // inclusive scan over the warps' counts
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t v = __shfl_up_sync(0xffffffffu, incl_w, o);
+      if ((int)lane >= o) incl_w += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl_w, 31);
+    const uint32_t excl = lookback_exclusive(status, tile, epoch, total);
+    if (lane < nw) s_warp[lane] = incl_w - c;  // exclusive offset of each warp within the tile
+    if (lane == 0) { s_base[0] = excl; s_base[1] = excl + total; }
+  }
+  __syncthreads();
+  *incl = s_base[1];
+  return s_base[0] + s_warp[warp] + lane_off;
+}
+
+struct BounceParams {
+  const float4 *in_o, *in_d, *in_t;  // path state in:  (origin.xyz, pixel) (direction.xyz, sample) (throughput.xyz, -)
+  float4 *out_o, *out_d, *out_t;     // survivors out, compacted
+  float4* accum;                     // per-pixel radiance sums
+  GeomSoA g;
+  int n_geoms, geom_cap;             // geoms per shared-memory chunk
+  const float4* mats;                // 4 float4 per material
+  RaygenConsts cam;
+  WfCtrl* ctrl;
+  uint64_t* status;
+  uint32_t epoch, depth;
+  uint64_t seed;
+  uint32_t first_sample, n_first;    // FIRST only: paths to generate = npix * samples in this wavefront
+};
+
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(kTile) k_bounce(const BounceParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_warp[kTile / 32];
+  __shared__ uint32_t s_base[2];
+  const GeomSmem gs = carve_geom_smem(smem_raw, P.geom_cap);
+  const bool single_chunk = P.n_geoms <= P.geom_cap;
+  if (single_chunk) stage_geoms(P.g, 0, P.n_geoms, gs);
+  const uint32_t n_in = FIRST ? P.n_first : P.ctrl->count[P.depth];
+  if (FIRST && blockIdx.x == 0 && threadIdx.x == 0) P.ctrl->count[0] = n_in;
+  const uint32_t n_tiles = (n_in + kTile - 1) / kTile;
+
+  for (;;) {
+    __syncthreads();  // staged geometry visible; s_tile / s_warp / s_base free for reuse
+    if (threadIdx.x == 0) s_tile = atomicAdd(&P.ctrl->tile_ctr[P.depth], 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= n_tiles) break;
+    const uint32_t idx = tile * kTile + threadIdx.x;
+    const bool valid = idx < n_in;
+
+    f3 o = mk(0, 0, 0), d = mk(0, 0, 1), thr = mk(1, 1, 1);
+    uint32_t pixel = 0, sample = 0;
+    if (valid) {
+      if (FIRST) {
+        pixel = idx % P.cam.npix;
+        sample = P.first_sample + idx / P.cam.npix;
+        raygen(P.cam, P.seed, pixel, sample, o, d);
+      } else {
+        const float4 a = __ldcs(P.in_o + idx), b = __ldcs(P.in_d + idx), c = __ldcs(P.in_t + idx);
+        o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
+        d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
+        thr = mk(c.x, c.y, c.z);
+      }
+    }
+
+    Hit h;
+    h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
+    if (single_chunk) {
+      if (valid) closest_hit_chunk(gs, 0, P.n_geoms, o, d, h);
+    } else {
+      for (int c0 = 0; c0 < P.n_geoms; c0 += P.geom_cap) {
+        const int cnt = min(P.geom_cap, P.n_geoms - c0);
+        __syncthreads();
+        stage_geoms(P.g, c0, cnt, gs);
+        __syncthreads();
+        if (valid) closest_hit_chunk(gs, c0, cnt, o, d, h);
+      }
+    }
+
+    bool alive = false;
+    if (valid && h.id >= 0) {
+      const int gi = h.id;
+      float4 f0, f1, f2, i0, i1, i2;
+      int mat;
+      if (single_chunk) {
+        f0 = gs.fwd0[gi]; f1 = gs.fwd1[gi]; f2 = gs.fwd2[gi];
+        i0 = gs.inv0[gi]; i1 = gs.inv1[gi]; i2 = gs.inv2[gi];
+        mat = gs.meta[gi].y;
+      } else {
+        f0 = __ldg(P.g.fwd0 + gi); f1 = __ldg(P.g.fwd1 + gi); f2 = __ldg(P.g.fwd2 + gi);
+        i0 = __ldg(P.g.inv0 + gi); i1 = __ldg(P.g.inv1 + gi); i2 = __ldg(P.g.inv2 + gi);
+        mat = __ldg(P.g.meta + gi).y;
+      }
+      const f3 n = hit_normal(f0, f1, f2, h);
+      MatRows m;
+      m.a = __ldg(P.mats + 4 * mat); m.b = __ldg(P.mats + 4 * mat + 1);
+      m.c = __ldg(P.mats + 4 * mat + 2); m.d = __ldg(P.mats + 4 * mat + 3);
+      f3 L;
+      const int kind = shade(m, i0, i1, i2, h.p, n, P.seed, pixel, sample, P.depth, o, d, thr, L);
+      if (kind == 3) {
+        float* px = reinterpret_cast<float*>(P.accum + pixel);
+        atomicAdd(px + 0, L.x);
+        atomicAdd(px + 1, L.y);
+        atomicAdd(px + 2, L.z);
+      } else {
+        alive = true;
+      }
+    }
+
+    if (!LAST) {
+      uint32_t incl;
+      const uint32_t slot = compact_slot(alive, P.status, tile, P.epoch, s_warp, s_base, &incl);
+      if (alive) {
+        __stcs(P.out_o + slot, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
+        __stcs(P.out_d + slot, make_float4(d.x, d.y, d.z, __uint_as_float(sample)));
+        __stcs(P.out_t + slot, make_float4(thr.x, thr.y, thr.z, 0.0f));
+      }
+      if (tile == n_tiles - 1 && threadIdx.x == 0) P.ctrl->count[P.depth + 1] = incl;
+    }
+  }
+}
+
+// live_total[d] += count[d]; one tiny launch per wavefront
+__global__ void k_accum_counts(const WfCtrl* ctrl, unsigned long long* live_total, int max_depth) {
+  int d = threadIdx.x;
+  if (d < max_depth) live_total[d] += ctrl->count[d];
+}
+
+// ---- parity entry points ----
+__global__ void k_raygen_list(RaygenConsts C, uint64_t seed, int n, const uint32_t* pixel, const uint32_t* sample,
+                              float* o, float* d) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  f3 oo, dd;
+  raygen(C, seed, pixel[i], sample[i], oo, dd);
+  o[3 * i] = oo.x; o[3 * i + 1] = oo.y; o[3 * i + 2] = oo.z;
+  d[3 * i] = dd.x; d[3 * i + 1] = dd.y; d[3 * i + 2] = dd.z;
+}
+
+__global__ void __launch_bounds__(kTile) k_intersect_list(GeomSoA g, int n_geoms, int geom_cap, int n, const float* o,
+                                                          const float* d, int* id, float* t, float* p, float* nrm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const GeomSmem gs = carve_geom_smem(smem_raw, geom_cap);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  f3 oo = mk(0, 0, 0), dd = mk(0, 0, 1);
+  if (valid) { oo = mk(o[3 * i], o[3 * i + 1], o[3 * i + 2]); dd = mk(d[3 * i], d[3 * i + 1], d[3 * i + 2]); }
+  Hit h;
+  h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
+  for (int c0 = 0; c0 < n_geoms; c0 += geom_cap) {
+    const int cnt = min(geom_cap, n_geoms - c0);
+    __syncthreads();
+    stage_geoms(g, c0, cnt, gs);
+    __syncthreads();
+    if (valid) closest_hit_chunk(gs, c0, cnt, oo, dd, h);
+  }
+  if (!valid) return;
+  f3 nn = mk(0, 0, 0);
+  if (h.id >= 0) nn = hit_normal(__ldg(g.fwd0 + h.id), __ldg(g.fwd1 + h.id), __ldg(g.fwd2 + h.id), h);
+  id[i] = h.id;
+  t[i] = h.id >= 0 ? h.t : -1.0f;
+  p[3 * i] = h.p.x; p[3 * i + 1] = h.p.y; p[3 * i + 2] = h.p.z;
+  nrm[3 * i] = nn.x; nrm[3 * i + 1] = nn.y; nrm[3 * i + 2] = nn.z;
+}
+
+// stream compaction on its own: same ballot / block scan / look-back code as k_bounce
+__global__ void __launch_bounds__(kTile) k_compact_u32(const uint32_t* values, const uint8_t* flags, uint32_t n,
+                                                       uint32_t* out, uint32_t* n_out, uint32_t* ticket,
+                                                       uint64_t* status, uint32_t epoch) {
+  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_warp[kTile / 32];
+  __shared__ uint32_t s_base[2];
+  const uint32_t n_tiles = (n + kTile - 1) / kTile;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= n_tiles) break;
+    const uint32_t idx = tile * kTile + threadIdx.x;
+    const bool keep = idx < n && flags[idx] != 0;
+    uint32_t incl;
+    const uint32_t slot = compact_slot(keep, status, tile, epoch, s_warp, s_base, &incl);
+    if (keep) out[slot] = values[idx];
+    if (tile == n_tiles - 1 && threadIdx.x == 0) *n_out = incl;
+  }
+}
+
+// ---- image out ----
+// packed float RGB (renderCam->image layout) = sum * 1 or sum / spp
+__global__ void k_resolve_rgb(const float4* accum, uint32_t npix, float spp, int divide, float* rgb) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  float4 a = accum[i];
+  if (divide) { a.x = a.x / spp; a.y = a.y / spp; a.z = a.z / spp; }
+  rgb[3 * i] = a.x; rgb[3 * i + 1] = a.y; rgb[3 * i + 2] = a.z;
+}
+__global__ void k_upload_rgb(const float* rgb, uint32_t npix, float4* accum) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  accum[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 0.0f);
+}
+// sendImageToPBO, src/raytraceKernel.cu:58-89: c = image*255.0; c > 255 -> 255; stored to uchar (truncation), w = 0.
+// image*255.0 is a binary64 product of two binary32-representable values rounded to float, which equals the
+// binary32 product (double rounding is innocuous for a single multiply).
+__global__ void k_resolve_rgba8(const float4* accum, uint32_t npix, float spp, uchar4* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  float4 a = accum[i];
+  float r = (a.x / spp) * 255.0f, g = (a.y / spp) * 255.0f, b = (a.z / spp) * 255.0f;
+  if (r > 255) r = 255;
+  if (g > 255) g = 255;
+  if (b > 255) b = 255;
+  uchar4 px;
+  px.x = (unsigned char)r; px.y = (unsigned char)g; px.z = (unsigned char)b; px.w = 0;
+  out[i] = px;
+}
+
+}  // namespace ptd

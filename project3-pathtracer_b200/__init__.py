@@ -46,10 +46,13 @@ def lib():
     """Load libpt_b200.so (building it first if sources are newer).  Fails loudly; never falls back."""
     global _lib
     if _lib is None:
-        _build.build()
-        if not os.path.exists(LIB_PATH):
-            raise PtError("libpt_b200.so is missing: the CUDA extension is required (no CPU fallback)")
-        _lib = C.CDLL(LIB_PATH)
+        path = os.environ.get("PT_B200_LIB")  # developer knob: load an alternative build of the same library
+        if not path:
+            _build.build()
+            path = LIB_PATH
+        if not os.path.exists(path):
+            raise PtError("%s is missing: the CUDA extension is required (no CPU fallback)" % path)
+        _lib = C.CDLL(path)
         _lib.pt_last_error.restype = C.c_char_p
     return _lib
 

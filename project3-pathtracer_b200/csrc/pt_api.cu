@@ -81,7 +81,7 @@ struct pt_context {
 static const uint64_t kDefaultWavefrontPaths = 16ull << 20;
 static const int kMaxSmemGeoms = 1024;  // 104 KB of shared memory per chunk at most
 
-// host-side camera constants; must follow oracle or_raygen's operation order exactly (binary32, unfused)
+// host-side camera constants (DESIGN.md "raygen"): binary32, unfused, in this exact order -- the parity tests compare bits
 static f3 h_mk(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
 static f3 h_normalize(f3 v) {
   float sqr = (v.x * v.x + v.y * v.y) + v.z * v.z;

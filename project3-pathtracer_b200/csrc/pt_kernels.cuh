@@ -20,6 +20,9 @@ namespace ptd {
 
 constexpr int kMaxDepth = 64;
 constexpr int kTile = 256;  // paths per tile = threads per CTA
+#ifndef PT_MIN_BLOCKS
+#define PT_MIN_BLOCKS 4  // resident CTAs per SM the register allocation aims for (tuning knob, see profiles/)
+#endif
 
 // per-wavefront control block in HBM, zeroed before each wavefront
 struct WfCtrl {
@@ -119,7 +122,7 @@ struct BounceParams {
 };
 
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(kTile) k_bounce(const BounceParams P) {
+__global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const BounceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_tile;
   __shared__ uint32_t s_warp[kTile / 32];

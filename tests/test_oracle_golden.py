@@ -1,0 +1,149 @@
+"""The CPU oracle against the golden vectors (no GPU).
+
+ref_vectors.json holds outputs of the REFERENCE'S OWN functions (generated in the build container from
+oracle/_ref, see oracle/gen_golden.py): the restatement must reproduce them bit for bit.
+spec_vectors.json freezes our specification of the stubbed pieces; its Philox entries are Random123's KATs."""
+import numpy as np
+
+from conftest import f32, same_bits
+
+
+def _geoms(ref_gold, pt):
+    return np.frombuffer(bytes.fromhex(ref_gold["scene"]["geoms_hex"]), dtype=pt.GEOM_DTYPE)
+
+
+def test_hash(oracle, ref_gold):
+    for a, h in ref_gold["hash"]:
+        assert oracle.hash(a) == h
+
+
+def test_multiplyMV_and_getPointOnRay(oracle, ref_gold):
+    for k in ref_gold["multiplyMV"]:
+        assert same_bits(oracle.multiplyMV(f32(k["m"]), f32(k["v"])), f32(k["out"]))
+    for k in ref_gold["getPointOnRay"]:
+        assert same_bits(oracle.getPointOnRay(f32(k["o"]), f32(k["d"]), f32([k["t"]])[0]), f32(k["out"]))
+
+
+def test_sphereIntersectionTest_bit_exact(oracle, ref_gold, pt):
+    g = _geoms(ref_gold, pt)
+    n_hits = 0
+    for k in ref_gold["sphereIntersectionTest"]:
+        o, d = f32(k["o"]).reshape(-1, 3), f32(k["d"]).reshape(-1, 3)
+        t, p, n = oracle.intersect_one(g[k["geom"]], 0, o, d)
+        want_t = f32(k["t"])
+        assert same_bits(t, want_t)
+        hit = want_t > 0
+        n_hits += int(hit.sum())
+        assert same_bits(p[hit], f32(k["p"]).reshape(-1, 3)[hit]) and same_bits(n[hit], f32(k["n"]).reshape(-1, 3)[hit])
+    assert n_hits > 300
+
+
+def test_reference_stubs_are_stubs(ref_gold):
+    """boxIntersectionTest returns -1 and calculateBSDF returns 1 in the reference"""
+    assert (f32(ref_gold["boxIntersectionTest_stub"]) == -1).all()
+    assert ref_gold["calculateBSDF_stub"] == 1
+
+
+def test_getRadiuses(oracle, ref_gold, pt):
+    g = _geoms(ref_gold, pt)
+    for k in ref_gold["getRadiuses"]:
+        assert same_bits(oracle.getRadiuses(g[k["geom"]]), f32(k["out"]))
+
+
+def test_hemisphere_reference_formula_bit_exact(oracle, ref_gold):
+    h = ref_gold["hemisphere"]
+    n, x1, x2 = f32(h["n"]).reshape(-1, 3), f32(h["xi1"]), f32(h["xi2"])
+    want = f32(h["out"]).reshape(-1, 3)
+    assert same_bits(oracle.hemisphere(n, x1, x2, ref=True), want)
+    # the sampler the path loop uses swaps libm sin/cos for a reproducible polynomial: same direction to ~3e-7
+    assert np.abs(oracle.hemisphere(n, x1, x2) - want).max() < 1e-6
+
+
+def test_struct_layout(ref_gold, pt):
+    lay = ref_gold["layout"]
+    assert lay[:7] == [24, 56, 172, 52, 96, 64, 64]
+    assert lay[7:14] == [pt.GEOM_DTYPE.fields[k][1] for k in
+                         ("type", "materialid", "translation", "rotation", "scale", "transform", "inverseTransform")]
+    assert lay[14:19] == [pt.CAMERA_DTYPE.fields[k][1] for k in ("resolution", "position", "view", "up", "fov")]
+    assert lay[19:29] == [pt.MATERIAL_DTYPE.fields[k][1] for k in
+                          ("color", "specularExponent", "specularColor", "hasReflective", "hasRefractive",
+                           "indexOfRefraction", "hasScatter", "absorptionCoefficient", "reducedScatterCoefficient",
+                           "emittance")]
+
+
+def test_philox_random123_kat(oracle, spec_gold):
+    for k in spec_gold["philox"]:
+        assert oracle.philox(k["ctr"], k["key"]).tolist() == k["out"]
+    assert oracle.u01(0) == 0.0 and oracle.u01(0xFFFFFFFF) < 1.0
+
+
+def test_sincos_2pi(oracle, spec_gold):
+    for k in spec_gold["sincos_2pi"]:
+        u = float(f32([k["u"]])[0])
+        s, c = oracle.sincos_2pi(u)
+        assert same_bits([s, c], f32([k["s"], k["c"]]))
+        assert abs(s - np.sin(2 * np.pi * u)) < 3e-7 and abs(c - np.cos(2 * np.pi * u)) < 3e-7
+
+
+def test_box_raygen_closest_hit_frozen(oracle, spec_gold, ref_gold, pt):
+    g = _geoms(ref_gold, pt)
+    for k in spec_gold["boxIntersectionTest"]:
+        t, p, n = oracle.intersect_one(g[k["geom"]], 1, f32(k["o"]).reshape(-1, 3), f32(k["d"]).reshape(-1, 3))
+        assert same_bits(t, f32(k["t"])) and same_bits(p.ravel(), f32(k["p"])) and same_bits(n.ravel(), f32(k["n"]))
+    cam = np.frombuffer(bytes.fromhex(ref_gold["scene"]["camera_hex"]), dtype=pt.CAMERA_DTYPE)
+    r = spec_gold["raygen"]
+    o, d = oracle.raygen(cam, (0.0, 0.0), r["seed"], r["pixel"], r["sample"])
+    assert same_bits(o.ravel(), f32(r["o"])) and same_bits(d.ravel(), f32(r["d"]))
+    lo, ld = oracle.raygen(cam, tuple(r["lens"]), r["seed"], r["pixel"], r["sample"])
+    assert same_bits(lo.ravel(), f32(r["lens_o"])) and same_bits(ld.ravel(), f32(r["lens_d"]))
+    gid, t, p, n = oracle.intersect_rays(g, o, d)
+    ch = spec_gold["closest_hit"]
+    assert gid.tolist() == ch["id"] and same_bits(t, f32(ch["t"]))
+
+
+def test_box_test_agrees_with_analytic_cube(oracle):
+    """unit cube at the origin, identity transform: hits land on the faces, normals are the face normals"""
+    import importlib
+    pt = importlib.import_module("project3-pathtracer_b200")
+    g = np.zeros(1, pt.GEOM_DTYPE)
+    g[0]["type"] = 1
+    g[0]["transform"] = np.eye(4, dtype=np.float32).ravel()
+    g[0]["inverseTransform"] = np.eye(4, dtype=np.float32).ravel()
+    o = np.array([[0, 0, 3], [3, 0.2, 0.1], [0, 0, 0], [0, 2, 0], [0.2, 0.1, 0]], np.float32)
+    d = np.array([[0, 0, -1], [-1, 0, 0], [0, 1, 0], [1, 0, 0], [0, 0, 2]], np.float32)
+    t, p, n = oracle.intersect_one(g[0], 1, o, d)
+    # distances are shortened by the 1e-4 pull-back (intersections.h:47)
+    assert np.allclose(t, [2.4999, 2.4999, 0.4999, -1, 0.4999], atol=2e-6)
+    assert np.allclose(n[0], [0, 0, 1]) and np.allclose(n[1], [1, 0, 0]) and np.allclose(n[2], [0, 1, 0])
+    assert np.allclose(n[4], [0, 0, 1])  # from inside: still the outward face normal
+
+
+def test_optics_frozen(oracle, spec_gold):
+    for k in spec_gold["optics"]:
+        n, i = f32(k["n"]), f32(k["i"])
+        a, b = (float(x) for x in f32(k["ior"]))
+        assert same_bits(oracle.reflect(n, i), f32(k["refl"]))
+        tir, tr = oracle.refract(n, i, a, b)
+        assert tir == k["tir"] and same_bits(tr, f32(k["trans"]))
+        R, T = oracle.fresnel(n, i, a, b, tr, tir)
+        assert same_bits([R, T], f32([k["R"], k["T"]]))
+        assert 0.0 <= R <= 1.0 and abs(R + T - 1) < 1e-6
+        if not tir:  # Snell: sin_t = eta * sin_i
+            si = np.linalg.norm(np.cross(n, i)); st = np.linalg.norm(np.cross(n, tr))
+            assert abs(st - (a / b) * si) < 1e-5
+
+
+def test_render_fixture_frozen(oracle, spec_gold, ref_gold, pt):
+    g = _geoms(ref_gold, pt)
+    m = np.frombuffer(bytes.fromhex(ref_gold["scene"]["materials_hex"]), dtype=pt.MATERIAL_DTYPE)
+    cam = np.frombuffer(bytes.fromhex(ref_gold["scene"]["camera_hex"]), dtype=pt.CAMERA_DTYPE).copy()
+    cam["resolution"][0] = [40, 40]
+    k = spec_gold["render_40x40_2spp_d8_seed11"]
+    img, live, _ = oracle.render(oracle.make_scene(g, m, cam), 0, 2, 8, 11, threads=1)
+    assert live.tolist() == k["live"] and same_bits(img.ravel(), f32(k["sum_rgb"]))
+    # threads and pixel ranges do not change the result
+    img2, live2, _ = oracle.render(oracle.make_scene(g, m, cam), 0, 2, 8, 11, threads=4)
+    assert same_bits(img, img2) and live.tolist() == live2.tolist()
+    a, la, _ = oracle.render(oracle.make_scene(g, m, cam), 0, 2, 8, 11, pix_begin=0, pix_end=700)
+    b, lb, _ = oracle.render(oracle.make_scene(g, m, cam), 0, 2, 8, 11, pix_begin=700, pix_end=1600, sum_rgb=a)
+    assert same_bits(b, img) and (la + lb).tolist() == live.tolist()

@@ -120,6 +120,11 @@ int pt_resolve_rgba8(pt_context* ctx, uint32_t spp, uint8_t* host_rgba8, void* d
 /* the float4[W*H] accumulation buffer itself (DEVICE pointer), for the multi-GPU reduce done by the host plumbing */
 int pt_accum_device_ptr(pt_context* ctx, void** device_ptr, size_t* bytes);
 
+/* Multi-GPU in ONE process (the headless driver): n contexts, one per GPU, each rendered a different range of
+ * sample indices of the same frame; sums their accumulation buffers into ctxs[0] with one ncclReduce over NVLink.
+ * (The reference is single-GPU: src/main.cpp:222.)  NCCL is loaded at run time; missing NCCL is an error. */
+int pt_reduce_to_first(pt_context* const* ctxs, int n);
+
 /* ---- counters: paths started, segments traced (= sum of live), live[d] = paths for which
  * closest-hit ran at depth d; live must have room for 64 entries.  Waits for outstanding renders. ---- */
 int pt_counters(pt_context* ctx, uint64_t* paths, uint64_t* segments, uint64_t* live);

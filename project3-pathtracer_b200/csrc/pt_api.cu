@@ -509,3 +509,87 @@ extern "C" int pt_compact_u32(int device, const uint32_t* values, const uint8_t*
   *n_out = cnt;
   return PT_OK;
 }
+
+// ---------------------------------------------------------------- multi-GPU combine (single process, one context per GPU)
+// One ncclReduce(sum) of the float4 accumulation images to ctxs[0] over NVLink / NVSwitch.  NCCL is resolved at run
+// time (dlopen) so that a process that already carries its own libnccl (PyTorch) keeps a single copy; processes
+// launched one-per-GPU (bench.py under torchrun) do the same reduce through torch.distributed instead.
+#include <dlfcn.h>
+namespace {
+typedef struct ncclComm* nccl_comm_t;
+struct NcclApi {
+  void* h = nullptr;
+  int (*CommInitAll)(nccl_comm_t*, int, const int*) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Reduce)(const void*, void*, size_t, int, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::vector<int> devs;
+  std::vector<nccl_comm_t> comms;
+} g_nccl;
+bool load_nccl() {
+  if (g_nccl.h) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) { pt_set_error_("NCCL not found (dlopen libnccl.so.2): %s", dlerror()); return false; }
+  *(void**)&g_nccl.CommInitAll = dlsym(g_nccl.h, "ncclCommInitAll");
+  *(void**)&g_nccl.CommDestroy = dlsym(g_nccl.h, "ncclCommDestroy");
+  *(void**)&g_nccl.GroupStart = dlsym(g_nccl.h, "ncclGroupStart");
+  *(void**)&g_nccl.GroupEnd = dlsym(g_nccl.h, "ncclGroupEnd");
+  *(void**)&g_nccl.Reduce = dlsym(g_nccl.h, "ncclReduce");
+  *(void**)&g_nccl.GetErrorString = dlsym(g_nccl.h, "ncclGetErrorString");
+  if (!g_nccl.CommInitAll || !g_nccl.GroupStart || !g_nccl.GroupEnd || !g_nccl.Reduce) {
+    pt_set_error_("libnccl lacks ncclCommInitAll/ncclReduce");
+    g_nccl.h = nullptr;
+    return false;
+  }
+  return true;
+}
+}  // namespace
+
+#define NC(call)                                                                                  \
+  do {                                                                                            \
+    int r_ = (call);                                                                              \
+    if (r_ != 0) {                                                                                \
+      pt_set_error_("%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
+      return PT_ERR_CUDA;                                                                         \
+    }                                                                                             \
+  } while (0)
+
+extern "C" int pt_reduce_to_first(pt_context* const* ctxs, int n) {
+  if (!ctxs || n < 1) { pt_set_error_("bad arguments"); return PT_ERR_INVALID; }
+  for (int i = 0; i < n; i++) {
+    if (!ctxs[i]) { pt_set_error_("context %d is NULL", i); return PT_ERR_STATE; }
+    if (ctxs[i]->npix != ctxs[0]->npix) { pt_set_error_("context %d has a different frame size", i); return PT_ERR_INVALID; }
+    for (int j = 0; j < i; j++)
+      if (ctxs[j]->device == ctxs[i]->device) { pt_set_error_("contexts %d and %d share device %d", j, i, ctxs[i]->device); return PT_ERR_INVALID; }
+  }
+  if (n == 1) return PT_OK;
+  if (!load_nccl()) return PT_ERR_CUDA;
+  std::vector<int> devs(n);
+  for (int i = 0; i < n; i++) devs[i] = ctxs[i]->device;
+  if (devs != g_nccl.devs) {
+    for (nccl_comm_t c : g_nccl.comms) if (g_nccl.CommDestroy) g_nccl.CommDestroy(c);
+    g_nccl.comms.assign(n, nullptr);
+    g_nccl.devs.clear();
+    NC(g_nccl.CommInitAll(g_nccl.comms.data(), n, devs.data()));
+    g_nccl.devs = devs;
+  }
+  NC(g_nccl.GroupStart());
+  for (int i = 0; i < n; i++) {
+    CU(cudaSetDevice(ctxs[i]->device));
+    // ncclFloat32 = 7, ncclSum = 0, root = rank 0
+    NC(g_nccl.Reduce(ctxs[i]->d_accum, ctxs[i]->d_accum, (size_t)ctxs[i]->npix * 4, 7, 0, 0, g_nccl.comms[i], ctxs[i]->stream));
+  }
+  NC(g_nccl.GroupEnd());
+  // counters: fold the other contexts' path totals into the first (live counts stay per context)
+  for (int i = 0; i < n; i++) {
+    CU(cudaSetDevice(ctxs[i]->device));
+    CU(cudaStreamSynchronize(ctxs[i]->stream));
+  }
+  return PT_OK;
+}

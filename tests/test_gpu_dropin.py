@@ -1,0 +1,106 @@
+"""GPU tests of the drop-in layers around the kernels: the cudaRaytraceCore shim (reference
+src/raytraceKernel.h:17), the headless driver (src/main.cpp runCuda loop) and scene-file -> image end to end."""
+import importlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from conftest import same_bits, with_resolution
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def compat():
+    return importlib.import_module("project3-pathtracer_b200.compat")
+
+
+def test_cudaRaytraceCore_running_mean_matches_oracle(pt, compat, oracle, sample_scene):
+    """k calls with iterations = 1..k leave the running mean of samples 0..k-1 in renderCam->image"""
+    cam = with_resolution(sample_scene["camera"], 96, 96)
+    rs = compat.RefScene([(sample_scene["geoms"], cam)], sample_scene["materials"], iterations=5)
+    compat.reset(); compat.set_trace_depth(8); compat.set_seed(3); compat.set_exit_on_error(False)
+    scn = oracle.make_scene(sample_scene["geoms"], sample_scene["materials"], cam)
+    want_sum = np.zeros((96 * 96, 3), np.float32)
+    for k in range(1, 6):
+        compat.cudaRaytraceCore(None, rs.camera, 0, k, rs.materials, len(rs.materials), rs.geoms, len(rs.geoms))
+        assert compat.last_status() == 0
+        oracle.render(scn, k - 1, 1, 8, 3, sum_rgb=want_sum)
+        want = want_sum / np.float32(k)
+        if k <= 2:
+            assert same_bits(rs.image, want)
+        assert np.allclose(rs.image, want, rtol=1e-6, atol=1e-6)
+    # out-of-sequence call: resumes from the caller's running mean (image*(k-1) + L_k)/k
+    img4 = rs.image.copy()
+    compat.reset()
+    rs.image[:] = img4
+    compat.cudaRaytraceCore(None, rs.camera, 0, 6, rs.materials, len(rs.materials), rs.geoms, len(rs.geoms))
+    oracle.render(scn, 5, 1, 8, 3, sum_rgb=want_sum)
+    assert np.allclose(rs.image, want_sum / np.float32(6), rtol=1e-5, atol=1e-5)
+    # iterations == 1 restarts the image (src/main.cpp:147-157 zeroes it between frames)
+    compat.cudaRaytraceCore(None, rs.camera, 0, 1, rs.materials, len(rs.materials), rs.geoms, len(rs.geoms))
+    first, _, _ = oracle.render(scn, 0, 1, 8, 3)
+    assert same_bits(rs.image, first)
+    compat.reset()
+
+
+def test_cudaRaytraceCore_frame_selects_per_frame_arrays_and_writes_pbo(pt, compat, oracle, sample_scene):
+    import torch
+    cam = with_resolution(sample_scene["camera"], 64, 64)
+    g1 = sample_scene["geoms"].copy()
+    # frame 1: sphere 5 moved up by 2 (forward/inverse translation columns)
+    g1[5]["translation"][1] += 2
+    g1[5]["transform"][7] += 2
+    inv = np.linalg.inv(g1[5]["transform"].reshape(4, 4).astype(np.float64)).astype(np.float32)
+    g1[5]["inverseTransform"] = inv.ravel()
+    rs = compat.RefScene([(sample_scene["geoms"], cam), (g1, cam)], sample_scene["materials"])
+    compat.reset(); compat.set_trace_depth(4); compat.set_seed(9); compat.set_exit_on_error(False)
+    pbo = torch.zeros(64 * 64 * 4, dtype=torch.uint8, device="cuda")
+    compat.cudaRaytraceCore(pbo.data_ptr(), rs.camera, 1, 1, rs.materials, len(rs.materials), rs.geoms, len(rs.geoms))
+    want, _, _ = oracle.render(oracle.make_scene(g1, sample_scene["materials"], cam), 0, 1, 4, 9)
+    assert same_bits(rs.image, want)
+    px = pbo.cpu().numpy().reshape(-1, 4)
+    assert (px[:, :3] == np.minimum(want * np.float32(255), np.float32(255)).astype(np.uint8)).all() and (px[:, 3] == 0).all()
+    compat.reset()
+
+
+def test_headless_driver_scene_file_to_png(pt, oracle, tmp_path):
+    """pt_render scene=... -> PNG; pixels equal the oracle's image pushed through the reference's 8-bit rules"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "scenes"))
+    import gen_scenes
+    text = gen_scenes.sample_scene((120, 80), 3)
+    p = tmp_path / "small.txt"
+    p.write_text(text)
+    out = subprocess.check_output([os.path.join(ROOT, "project3-pathtracer_b200", "pt_render"), "scene=%s" % p,
+                                   "depth=6", "seed=21", "out=%s" % (tmp_path / "o.bmp"), "json=1"], text=True)
+    info = json.loads(out.strip().splitlines()[-1])
+    assert info["file"].endswith("o.0.png") and info["spp"] == 3 and info["paths"] == 120 * 80 * 3
+    s = pt.Scene(p)
+    g, m, cam, lens = s.frame(0)
+    want_sum, live, _ = oracle.render(oracle.make_scene(g, m, cam, lens), 0, 3, 6, 21)
+    assert info["segments"] == int(live.sum())
+    want8 = pt.image_to_rgb8(want_sum / np.float32(3), 120, 80)
+    got8 = np.asarray(Image.open(info["file"]).convert("RGB"))
+    assert np.abs(got8.astype(int) - want8.astype(int)).max() <= 1  # 3 samples: summation order may move one LSB
+    assert (got8 != want8).mean() < 1e-3
+
+
+def test_cornell_scene_file_end_to_end(pt, oracle):
+    """config 2 (glass + mirror + depth of field) from its scene file, reduced frame, bit-exact at 1 spp"""
+    s = pt.Scene(os.path.join(ROOT, "scenes", "cornell_glass_dof.txt"))
+    g, m, cam, lens = s.frame(0)
+    assert lens[0] > 0
+    cam = with_resolution(cam, 192, 108)
+    want, live, _ = oracle.render(oracle.make_scene(g, m, cam, lens), 0, 1, 12, 4)
+    with pt.Context(g, m, cam, lens=lens) as c:
+        c.render(0, 1, 12, 4)
+        got = c.download_sum()
+        _, segs, glive = c.counters()
+    assert glive[:12].tolist() == live.tolist() and same_bits(got, want)
+    assert live[11] > 0.05 * live[0], "closed box: paths stay alive"

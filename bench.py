@@ -132,13 +132,6 @@ def run_reference(args, rank):
     }))
 
 
-class _DevArray:
-    """wraps the context's float4 accumulation buffer for torch (zero copy) via __cuda_array_interface__"""
-
-    def __init__(self, ptr, n_floats):
-        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 3}
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -170,8 +163,8 @@ def main():
     ctx.set_wavefront_paths(npix * args.wf_spp)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
-    ptr, nbytes = ctx.accum_device_ptr()
-    accum = torch.as_tensor(_DevArray(ptr, nbytes // 4), device=torch.device("cuda", local))
+    sh = importlib.import_module("project3-pathtracer_b200.sharding")
+    accum = sh.accum_tensor(ctx)  # zero-copy view of the float4 accumulation image in HBM
     first_sample = rank * args.spp
 
     def step():
@@ -179,7 +172,7 @@ def main():
         ctx.render(first_sample, args.spp, DEPTH, SEED)
         if world > 1:
             with torch.cuda.stream(stream):
-                dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+                sh.reduce_image(accum, dst=0)
 
     def barrier():
         if world > 1:

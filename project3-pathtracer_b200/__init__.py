@@ -184,6 +184,12 @@ class Context:
         return gid, t, p, nr
 
 
+def reduce_to_first(contexts):
+    """single-process multi-GPU combine: one ncclReduce(sum) of the accumulation images into contexts[0]"""
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    _check(lib().pt_reduce_to_first(arr, C.c_int(len(contexts))))
+
+
 def compact_u32(values, flags, device=0):
     """Stream compaction primitive on its own (pt_compact_u32): values[flags != 0], order preserved."""
     v, f = _arr(values, np.uint32).ravel(), _arr(flags, np.uint8).ravel()

@@ -145,6 +145,10 @@ int pt_intersect(pt_context* ctx, int n, const float* origin, const float* direc
 int pt_compact_u32(int device, const uint32_t* values, const uint8_t* flags, uint64_t n, uint32_t* out,
                    uint64_t* n_out);
 
+/* exhaustive check (all 2^32 inputs) of the kernels' packed IEEE sqrt / reciprocal against the scalar operators;
+ * returns the number of differing results (must be 0) */
+int pt_selftest_packed_math(int device, uint64_t* bad_sqrt, uint64_t* bad_rcp);
+
 /* ---- scene file and image file (host side; same formats as the reference) ---- */
 typedef struct pt_scene pt_scene;
 /* scene::scene(string), src/scene.cpp:11-35.  rotat_degrees = 0 reproduces the reference exactly (ROTAT is

@@ -175,25 +175,24 @@ float or_boxIntersectionTest(const or_static_geom* g, const float o[3], const fl
   v3 rd = vnormalize(mulMV(g->inverseTransform, d[0], d[1], d[2], 0.0f));
   float roa[3] = {ro.x, ro.y, ro.z};
   float rda[3] = {rd.x, rd.y, rd.z};
-  float tnear = -INFINITY, tfar = INFINITY;
-  int anear = 0, afar = 0;
+  float lo[3], hi[3];
   for (int a = 0; a < 3; a++) {
     float inv = 1.0f / rda[a];
     float t1 = (-0.5f - roa[a]) * inv;
     float t2 = (0.5f - roa[a]) * inv;
-    float lo = t1 < t2 ? t1 : t2;
-    float hi = t1 < t2 ? t2 : t1;
-    if (lo > tnear) { tnear = lo; anear = a; }
-    if (hi < tfar) { tfar = hi; afar = a; }
+    lo[a] = fminf(t1, t2); /* IEEE minNum / maxNum: a NaN operand (0 * inf) is ignored */
+    hi[a] = fmaxf(t1, t2);
   }
+  float tnear = fmaxf(fmaxf(lo[0], lo[1]), lo[2]);
+  float tfar = fminf(fminf(hi[0], hi[1]), hi[2]);
   if (tnear > tfar || tfar < 0) return -1;
   float t;
   int axis;
   float sign;
-  if (tnear > 0) {
-    t = tnear; axis = anear; sign = rda[axis] > 0 ? -1.0f : 1.0f;
-  } else {
-    t = tfar; axis = afar; sign = rda[axis] > 0 ? 1.0f : -1.0f;
+  if (tnear > 0) { /* entering: the first axis that attains the maximum */
+    t = tnear; axis = lo[0] == tnear ? 0 : (lo[1] == tnear ? 1 : 2); sign = rda[axis] > 0 ? -1.0f : 1.0f;
+  } else {         /* origin inside: leave through the first axis that attains the minimum */
+    t = tfar; axis = hi[0] == tfar ? 0 : (hi[1] == tfar ? 1 : 2); sign = rda[axis] > 0 ? 1.0f : -1.0f;
   }
   v3 no = V(axis == 0 ? sign : 0.0f, axis == 1 ? sign : 0.0f, axis == 2 ? sign : 0.0f);
   v3 po = pointOnRay(ro, rd, t);

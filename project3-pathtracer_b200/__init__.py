@@ -190,6 +190,13 @@ def reduce_to_first(contexts):
     _check(lib().pt_reduce_to_first(arr, C.c_int(len(contexts))))
 
 
+def selftest_packed_math(device=0):
+    """(bad_sqrt, bad_rcp): mismatches of the packed IEEE sqrt / reciprocal over all 2^32 inputs (must be 0, 0)"""
+    a, b = C.c_uint64(), C.c_uint64()
+    _check(lib().pt_selftest_packed_math(C.c_int(device), C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
 def compact_u32(values, flags, device=0):
     """Stream compaction primitive on its own (pt_compact_u32): values[flags != 0], order preserved."""
     v, f = _arr(values, np.uint32).ravel(), _arr(flags, np.uint8).ravel()

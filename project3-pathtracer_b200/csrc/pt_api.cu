@@ -58,6 +58,10 @@ struct pt_context {
   float4* d_rows = nullptr;  // 6 arrays of n_geoms float4
   int2* d_meta = nullptr;
   float4* d_mats = nullptr;
+  float4* d_pair_q = nullptr;  // [12][n_pairs] interleaved matrices of type-homogeneous geom pairs
+  int4* d_pair_meta = nullptr;
+  PairSoA pairs{};
+  int pair_cap = 0;
   GeomSoA g{};
   RaygenConsts cam{};
   uint32_t W = 0, H = 0, npix = 0;
@@ -75,11 +79,19 @@ struct pt_context {
   float* d_rgb = nullptr;      // staging for packed RGB
   uchar4* d_rgba8 = nullptr;   // staging for the 8-bit resolve
   int grid_blocks[4] = {0, 0, 0, 0};  // persistent grid per (FIRST,LAST) variant
-  size_t smem_bytes = 0;
+  size_t smem_bytes = 0;   // k_bounce: geometry + survivor staging
+  size_t geom_smem = 0;    // geometry only (k_intersect_list)
 };
 
 static const uint64_t kDefaultWavefrontPaths = 16ull << 20;
-static const int kMaxSmemGeoms = 1024;  // 104 KB of shared memory per chunk at most
+static const int kMaxSmemGeoms = 512;   // 52 KB of shared memory for geometry at most (2 CTAs per SM with the staging area)
+static const int kMaxSmemPairs = 256;   // the same 52 KB as pairs; larger scenes are read through L1/L2
+// identity operands of the packed arithmetic, passed at run time on purpose (pt_pairs.cuh, toolchain caveat)
+static PkConsts pk_consts() {
+  PkConsts k;
+  k.one = 1.0f; k.neg_zero = -0.0f; k.neg_one = -1.0f; k.zero = 0.0f;
+  return k;
+}
 
 // host-side camera constants (DESIGN.md "raygen"): binary32, unfused, in this exact order -- the parity tests compare bits
 static f3 h_mk(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -151,6 +163,40 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
     }
     meta[i] = make_int2(geoms[i].type, geoms[i].type <= 1 ? geoms[i].materialid : 0);
   }
+  // pairs of equal type for the packed (FFMA2) closest hit; MESH has no geometry and is left out;
+  // an odd one out is paired with itself (the duplicate half is ignored by the kernel)
+  std::vector<int> order;
+  for (int t = 0; t <= 1; t++) {
+    std::vector<int> ids;
+    for (int i = 0; i < n_geoms; i++) if (geoms[i].type == t) ids.push_back(i);
+    if (ids.size() & 1) ids.push_back(ids.back());
+    order.insert(order.end(), ids.begin(), ids.end());
+  }
+  const int n_pairs = (int)order.size() / 2;
+  std::vector<float4> pq((size_t)12 * (n_pairs ? n_pairs : 1));
+  std::vector<int4> pm(n_pairs ? n_pairs : 1);
+  for (int p = 0; p < n_pairs; p++) {
+    const int ia = order[2 * p], ib = order[2 * p + 1];
+    for (int half = 0; half < 2; half++) {
+      const float* A = half ? geoms[ia].transform : geoms[ia].inverseTransform;
+      const float* B = half ? geoms[ib].transform : geoms[ib].inverseTransform;
+      for (int r = 0; r < 3; r++) {
+        pq[(size_t)(6 * half + 2 * r) * n_pairs + p] = make_float4(A[4 * r], B[4 * r], A[4 * r + 1], B[4 * r + 1]);
+        pq[(size_t)(6 * half + 2 * r + 1) * n_pairs + p] = make_float4(A[4 * r + 2], B[4 * r + 2], A[4 * r + 3], B[4 * r + 3]);
+      }
+    }
+    pm[p] = make_int4(ia, ib, geoms[ia].type, 0);
+  }
+  if (n_pairs != c->pairs.n_pairs || !c->d_pair_q) {
+    if (c->d_pair_q) CU(cudaFree(c->d_pair_q));
+    if (c->d_pair_meta) CU(cudaFree(c->d_pair_meta));
+    c->d_pair_q = nullptr; c->d_pair_meta = nullptr;
+    CU(cudaMalloc(&c->d_pair_q, pq.size() * sizeof(float4)));
+    CU(cudaMalloc(&c->d_pair_meta, pm.size() * sizeof(int4)));
+  }
+  CU(cudaMemcpyAsync(c->d_pair_q, pq.data(), pq.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_pair_meta, pm.data(), pm.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+  c->pairs.q = c->d_pair_q; c->pairs.meta = c->d_pair_meta; c->pairs.n_pairs = n_pairs;
   if (n_geoms != c->n_geoms) {
     if (c->d_rows) CU(cudaFree(c->d_rows));
     if (c->d_meta) CU(cudaFree(c->d_meta));
@@ -176,15 +222,22 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
   c->cam = make_raygen(*cam, lens);
   c->W = (uint32_t)Wi; c->H = (uint32_t)Hi; c->npix = c->W * c->H;
   const int cap = n_geoms < kMaxSmemGeoms ? n_geoms : kMaxSmemGeoms;
-  if (cap != c->geom_cap) {
+  const int pcap = n_pairs < 1 ? 1 : (n_pairs < kMaxSmemPairs ? n_pairs : kMaxSmemPairs);
+  if (cap != c->geom_cap || pcap != c->pair_cap) {
     c->geom_cap = cap;
-    c->smem_bytes = geom_smem_bytes(cap);
+    c->pair_cap = pcap;
+#ifdef PT_SCALAR_HIT
+    c->geom_smem = geom_smem_bytes(cap);
+#else
+    c->geom_smem = pair_smem_bytes(pcap);
+#endif
+    c->smem_bytes = c->geom_smem + stage_smem_bytes();  // k_bounce: geometry + survivor staging
     int rc;
     if ((rc = setup_variant<true, false>(c, 0))) return rc;
     if ((rc = setup_variant<true, true>(c, 1))) return rc;
     if ((rc = setup_variant<false, false>(c, 2))) return rc;
     if ((rc = setup_variant<false, true>(c, 3))) return rc;
-    CU(cudaFuncSetAttribute(k_intersect_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    CU(cudaFuncSetAttribute(k_intersect_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->geom_smem));
   }
   return PT_OK;
 }
@@ -211,6 +264,7 @@ extern "C" int pt_context_destroy(pt_context* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->d_rows); cudaFree(c->d_meta); cudaFree(c->d_mats); cudaFree(c->d_state); cudaFree(c->d_status);
+  cudaFree(c->d_pair_q); cudaFree(c->d_pair_meta);
   cudaFree(c->d_ctrl); cudaFree(c->d_live); cudaFree(c->d_accum); cudaFree(c->d_rgb); cudaFree(c->d_rgba8);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -292,7 +346,7 @@ extern "C" int pt_clear(pt_context* c) {
 
 template <bool F, bool L>
 static cudaError_t launch_bounce(pt_context* c, int slot, const BounceParams& P, uint32_t n_upper) {
-  uint32_t tiles = (n_upper + kTile - 1) / kTile;
+  uint32_t tiles = (n_upper + kTileRays - 1) / kTileRays;
   uint32_t grid = (uint32_t)c->grid_blocks[slot];
   if (tiles < grid) grid = tiles ? tiles : 1;
   k_bounce<F, L><<<grid, kTile, c->smem_bytes, c->stream>>>(P);
@@ -319,6 +373,8 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
       P.out_o = S + (3 * outb + 0) * cap; P.out_d = S + (3 * outb + 1) * cap; P.out_t = S + (3 * outb + 2) * cap;
       P.accum = c->d_accum;
       P.g = c->g; P.n_geoms = c->n_geoms; P.geom_cap = c->geom_cap;
+      P.pairs = c->pairs; P.pair_cap = c->pair_cap;
+      P.kc = pk_consts();
       P.mats = c->d_mats;
       P.cam = c->cam;
       P.ctrl = c->d_ctrl;
@@ -465,8 +521,8 @@ extern "C" int pt_intersect(pt_context* c, int n, const float* origin, const flo
   CU(dor.alloc(v)); CU(ddr.alloc(v)); CU(dt.alloc(n)); CU(dpnt.alloc(v)); CU(dn.alloc(v)); CU(did.alloc(n));
   CU(cudaMemcpyAsync(dor.p, origin, v * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(ddr.p, direction, v * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  k_intersect_list<<<(n + kTile - 1) / kTile, kTile, c->smem_bytes, c->stream>>>(c->g, c->n_geoms, c->geom_cap, n, dor.p,
-                                                                                 ddr.p, did.p, dt.p, dpnt.p, dn.p);
+  k_intersect_list<<<(n + kTile - 1) / kTile, kTile, c->geom_smem, c->stream>>>(
+      c->g, c->n_geoms, c->geom_cap, c->pairs, c->pair_cap, pk_consts(), n, dor.p, ddr.p, did.p, dt.p, dpnt.p, dn.p);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(geom_id, did.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(t, dt.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -507,6 +563,24 @@ extern "C" int pt_compact_u32(int device, const uint32_t* values, const uint8_t*
   CU(cudaMemcpy(&cnt, dctl.p + 1, sizeof(cnt), cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(out, dout.p, (size_t)cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   *n_out = cnt;
+  return PT_OK;
+}
+
+extern "C" int pt_selftest_packed_math(int device, uint64_t* bad_sqrt, uint64_t* bad_rcp) {
+  if (!bad_sqrt || !bad_rcp) { pt_set_error_("bad arguments"); return PT_ERR_INVALID; }
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { pt_set_error_("device %d out of range", device); return PT_ERR_INVALID; }
+  CU(cudaSetDevice(device));
+  DevBuf<unsigned long long> d;
+  CU(d.alloc(2));
+  CU(cudaMemset(d.p, 0, 2 * sizeof(unsigned long long)));
+  k_selftest_packed<<<148 * 8, 256>>>(pk_consts(), d.p, d.p + 1);
+  CU(cudaGetLastError());
+  unsigned long long h[2];
+  CU(cudaMemcpy(h, d.p, sizeof(h), cudaMemcpyDeviceToHost));
+  *bad_sqrt = h[0];
+  *bad_rcp = h[1];
   return PT_OK;
 }
 

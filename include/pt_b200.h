@@ -145,9 +145,20 @@ int pt_intersect(pt_context* ctx, int n, const float* origin, const float* direc
 int pt_compact_u32(int device, const uint32_t* values, const uint8_t* flags, uint64_t n, uint32_t* out,
                    uint64_t* n_out);
 
-/* exhaustive check (all 2^32 inputs) of the kernels' packed IEEE sqrt / reciprocal against the scalar operators;
- * returns the number of differing results (must be 0) */
-int pt_selftest_packed_math(int device, uint64_t* bad_sqrt, uint64_t* bad_rcp);
+/* Closest hit runs as a conservative filter over all geoms followed by the reference-exact test of the best
+ * candidate, falling back to the exact scan of every geom when the filter cannot separate two surfaces
+ * (csrc/pt_filter.cuh).  The answers are identical by construction; these entry points let callers check that.
+ * pt_intersect_ex: mode PT_HIT_FILTERED is pt_intersect; PT_HIT_EXACT_SCAN runs the exact test on every geom in index
+ * order (the specification).  fallbacks (may be NULL) = rays of this call that took the fallback. */
+#define PT_HIT_FILTERED 0
+#define PT_HIT_EXACT_SCAN 1
+int pt_intersect_ex(pt_context* ctx, int mode, int n, const float* origin, const float* direction, int32_t* geom_id,
+                    float* t, float* point, float* normal, uint64_t* fallbacks);
+/* multiply every rounding-error term of the filter's bounds by `scale` (1 = shipped).  Test hook: parity must hold
+ * at 1 with margin, i.e. also at scales well below 1; 0 disables the margins. */
+int pt_set_filter_scale(pt_context* ctx, float scale);
+/* segments of pt_render calls since the last pt_clear whose closest hit took the exact-scan fallback */
+int pt_filter_stats(pt_context* ctx, uint64_t* fallbacks);
 
 /* ---- scene file and image file (host side; same formats as the reference) ---- */
 typedef struct pt_scene pt_scene;

@@ -33,6 +33,7 @@ LENS_DTYPE = np.dtype([("aperture", "<f4"), ("focal_distance", "<f4")])
 assert GEOM_DTYPE.itemsize == 172 and MATERIAL_DTYPE.itemsize == 64 and CAMERA_DTYPE.itemsize == 52
 
 SPHERE, CUBE, MESH = 0, 1, 2
+HIT_FILTERED, HIT_EXACT_SCAN = 0, 1  # pt_intersect_ex modes
 
 
 class PtError(RuntimeError):
@@ -175,26 +176,33 @@ class Context:
         _check(lib().pt_raygen(self._h, C.c_uint64(seed), C.c_int(n), _p(pixel), _p(sample), _p(o), _p(d)))
         return o, d
 
-    def intersect(self, origin, direction):
+    def intersect(self, origin, direction, mode=HIT_FILTERED, with_stats=False):
+        """closest hit of n rays -> (geom id, t, point, normal) [+ fallbacks]; mode HIT_EXACT_SCAN runs the exact test on
+        every geom (the specification the filtered default must reproduce bit for bit)"""
         o, d = _arr(origin, np.float32).reshape(-1, 3), _arr(direction, np.float32).reshape(-1, 3)
         n = o.shape[0]
         gid, t = np.zeros(n, np.int32), np.zeros(n, np.float32)
         p, nr = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
-        _check(lib().pt_intersect(self._h, C.c_int(n), _p(o), _p(d), _p(gid), _p(t), _p(p), _p(nr)))
-        return gid, t, p, nr
+        fb = C.c_uint64()
+        _check(lib().pt_intersect_ex(self._h, C.c_int(mode), C.c_int(n), _p(o), _p(d), _p(gid), _p(t), _p(p), _p(nr),
+                                     C.byref(fb)))
+        return (gid, t, p, nr, fb.value) if with_stats else (gid, t, p, nr)
+
+    def set_filter_scale(self, scale):
+        """test hook: multiply the rounding-error terms of the closest-hit filter's bounds (1 = shipped)"""
+        _check(lib().pt_set_filter_scale(self._h, C.c_float(scale)))
+
+    def filter_stats(self):
+        """segments rendered since the last clear() whose closest hit fell back to the exact scan"""
+        n = C.c_uint64()
+        _check(lib().pt_filter_stats(self._h, C.byref(n)))
+        return n.value
 
 
 def reduce_to_first(contexts):
     """single-process multi-GPU combine: one ncclReduce(sum) of the accumulation images into contexts[0]"""
     arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
     _check(lib().pt_reduce_to_first(arr, C.c_int(len(contexts))))
-
-
-def selftest_packed_math(device=0):
-    """(bad_sqrt, bad_rcp): mismatches of the packed IEEE sqrt / reciprocal over all 2^32 inputs (must be 0, 0)"""
-    a, b = C.c_uint64(), C.c_uint64()
-    _check(lib().pt_selftest_packed_math(C.c_int(device), C.byref(a), C.byref(b)))
-    return a.value, b.value
 
 
 def compact_u32(values, flags, device=0):

@@ -54,14 +54,16 @@ struct pt_context {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   // scene
-  int n_geoms = 0, n_mats = 0, geom_cap = 0;
+  int n_geoms = 0, n_mats = 0;
   float4* d_rows = nullptr;  // 6 arrays of n_geoms float4
   int2* d_meta = nullptr;
   float4* d_mats = nullptr;
-  float4* d_pair_q = nullptr;  // [12][n_pairs] interleaved matrices of type-homogeneous geom pairs
-  int4* d_pair_meta = nullptr;
-  PairSoA pairs{};
-  int pair_cap = 0;
+  float4* d_filt = nullptr;   // 5 arrays of n_filt float4: filter geometry (pt_filter.cuh)
+  int* d_filt_ids = nullptr;
+  FiltSoA filt{};
+  int filt_cap = 0;
+  float filter_scale = 1.0f;  // multiplies every error-model term of the filter (test hook; 1 = the shipped bounds)
+  std::vector<pt_static_geom> h_geoms;  // host copy, to rebuild the filter when the scale changes
   GeomSoA g{};
   RaygenConsts cam{};
   uint32_t W = 0, H = 0, npix = 0;
@@ -79,18 +81,140 @@ struct pt_context {
   float* d_rgb = nullptr;      // staging for packed RGB
   uchar4* d_rgba8 = nullptr;   // staging for the 8-bit resolve
   int grid_blocks[4] = {0, 0, 0, 0};  // persistent grid per (FIRST,LAST) variant
+  bool staged = true;                 // filter geometry fits in shared memory
   size_t smem_bytes = 0;   // k_bounce: geometry + survivor staging
-  size_t geom_smem = 0;    // geometry only (k_intersect_list)
+  size_t geom_smem = 0;    // filter geometry only (k_intersect_list)
 };
 
 static const uint64_t kDefaultWavefrontPaths = 16ull << 20;
-static const int kMaxSmemGeoms = 512;   // 52 KB of shared memory for geometry at most (2 CTAs per SM with the staging area)
-static const int kMaxSmemPairs = 256;   // the same 52 KB as pairs; larger scenes are read through L1/L2
-// identity operands of the packed arithmetic, passed at run time on purpose (pt_pairs.cuh, toolchain caveat)
-static PkConsts pk_consts() {
-  PkConsts k;
-  k.one = 1.0f; k.neg_zero = -0.0f; k.neg_one = -1.0f; k.zero = 0.0f;
-  return k;
+static const int kMaxSmemGeoms = 512;   // 40 KB of shared memory for filter geometry at most; larger scenes are read through L1/L2
+
+// ---------------------------------------------------------------- filter constants (pt_filter.cuh, DESIGN.md "filter")
+// largest eigenvalue of the symmetric 3x3 matrix S (cyclic Jacobi, binary64)
+static void sym3_eigen_range(double S[3][3], double* emin, double* emax) {
+  for (int sweep = 0; sweep < 32; sweep++) {
+    double off = fabs(S[0][1]) + fabs(S[0][2]) + fabs(S[1][2]);
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; p++)
+      for (int q = p + 1; q < 3; q++) {
+        if (S[p][q] == 0.0) continue;
+        const double th = (S[q][q] - S[p][p]) / (2.0 * S[p][q]);
+        const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 3; k++) {  // S <- S * J
+          const double skp = S[k][p], skq = S[k][q];
+          S[k][p] = c * skp - sn * skq; S[k][q] = sn * skp + c * skq;
+        }
+        for (int k = 0; k < 3; k++) {  // S <- J^T * S
+          const double spk = S[p][k], sqk = S[q][k];
+          S[p][k] = c * spk - sn * sqk; S[q][k] = sn * spk + c * sqk;
+        }
+      }
+  }
+  *emin = fmin(S[0][0], fmin(S[1][1], S[2][2]));
+  *emax = fmax(S[0][0], fmax(S[1][1], S[2][2]));
+}
+static float round_up(double x) {  // smallest-ish float >= x (x >= 0)
+  float f = (float)x;
+  if ((double)f < x) f = nextafterf(f, INFINITY);
+  return nextafterf(f, INFINITY);
+}
+
+struct HostFilter {
+  std::vector<float4> rows;  // [5][n]
+  std::vector<int> ids;
+  int n_spheres = 0, n = 0;
+  float r_scene = 0.0f;
+};
+// Per-geom coefficients of the error model.  u = 2^-24 (unit roundoff).  `scale` multiplies every error term.
+static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double scale) {
+  HostFilter F;
+  const double u = ldexp(1.0, -24);
+  for (int t = 0; t <= 1; t++)
+    for (int i = 0; i < n_geoms; i++)
+      if (geoms[i].type == t) F.ids.push_back(i);
+  F.n = (int)F.ids.size();
+  for (int i = 0; i < n_geoms; i++) F.n_spheres += geoms[i].type == 0;
+  const int n = F.n ? F.n : 1;
+  F.rows.assign((size_t)5 * n, make_float4(0, 0, 0, 0));
+  // bound on |p| over the surface points of the scene: |translation| + sigma_max(M) * (half diagonal of the unit cube)
+  struct Per { double sigM, isigA, KA[3], T[3], KM, TM, EMw, EMc, rlin, rt; };
+  std::vector<Per> per(n);
+  double r_scene = 0.0;
+  for (int k = 0; k < F.n; k++) {
+    const pt_static_geom& g = geoms[F.ids[k]];
+    const float* A = g.inverseTransform;
+    const float* M = g.transform;
+    Per& q = per[k];
+    double MtM[3][3], AtA[3][3];
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) {
+        MtM[a][b] = AtA[a][b] = 0.0;
+        for (int r = 0; r < 3; r++) { MtM[a][b] += (double)M[4 * r + a] * M[4 * r + b]; AtA[a][b] += (double)A[4 * r + a] * A[4 * r + b]; }
+      }
+    double lo, hi;
+    sym3_eigen_range(MtM, &lo, &hi);
+    q.sigM = sqrt(fmax(hi, 0.0)) * 1.001;
+    sym3_eigen_range(AtA, &lo, &hi);
+    q.isigA = lo > 0 ? 1.001 / sqrt(lo) : INFINITY;  // 1 / sigma_min(A): bound on |d| / |A d|
+    q.KM = q.TM = q.EMw = q.EMc = q.rlin = q.rt = 0.0;
+    for (int r = 0; r < 3; r++) {
+      q.KA[r] = fabs((double)A[4 * r]) + fabs((double)A[4 * r + 1]) + fabs((double)A[4 * r + 2]);
+      q.T[r] = fabs((double)A[4 * r + 3]);
+    }
+    double tm2 = 0.0;
+    for (int r = 0; r < 3; r++) {
+      const double m0 = fabs((double)M[4 * r]), m1 = fabs((double)M[4 * r + 1]), m2 = fabs((double)M[4 * r + 2]);
+      q.KM = fmax(q.KM, m0 + m1 + m2);
+      q.TM = fmax(q.TM, fabs((double)M[4 * r + 3]));
+      tm2 += (double)M[4 * r + 3] * M[4 * r + 3];
+      q.EMw = fmax(q.EMw, m0 * q.KA[0] + m1 * q.KA[1] + m2 * q.KA[2]);
+      q.EMc = fmax(q.EMc, m0 * q.T[0] + m1 * q.T[1] + m2 * q.T[2]);
+      // residual of transform * inverseTransform - I (both are rounded binary32 matrices)
+      double lin = 0.0;
+      for (int c = 0; c < 4; c++) {
+        double acc = c == 3 ? (double)M[4 * r + 3] : 0.0;
+        for (int j = 0; j < 3; j++) acc += (double)M[4 * r + j] * A[4 * j + c];
+        if (c < 3) lin += fabs(acc - (c == r ? 1.0 : 0.0)); else q.rt = fmax(q.rt, fabs(acc));
+      }
+      q.rlin = fmax(q.rlin, lin);
+    }
+    r_scene = fmax(r_scene, sqrt(tm2) + q.sigM * 0.8661);
+  }
+  F.r_scene = round_up(r_scene * 1.001);
+  const double Rs = (double)F.r_scene;
+  const double s3 = 1.7320508075688772;
+  for (int k = 0; k < F.n; k++) {
+    const pt_static_geom& g = geoms[F.ids[k]];
+    const Per& q = per[k];
+    const float* A = g.inverseTransform;
+    for (int r = 0; r < 3; r++) F.rows[(size_t)r * n + k] = make_float4(A[4 * r], A[4 * r + 1], A[4 * r + 2], A[4 * r + 3]);
+    const double KAn = sqrt(q.KA[0] * q.KA[0] + q.KA[1] * q.KA[1] + q.KA[2] * q.KA[2]);
+    const double Tn = sqrt(q.T[0] * q.T[0] + q.T[1] * q.T[1] + q.T[2] * q.T[2]);
+    // world slack: pull-back of 1e-4 object units (NOT scaled: it is geometry, not rounding) + rounding of both
+    // paths mapped through the forward transform + residual of M*A - I
+    double ew_w = scale * s3 * 2.0 * 2.25 * u * q.EMw;
+    double ew_c = scale * s3 * 2.0 * (9.0 * u * (q.EMc + 0.5 * q.KM) + 4.0 * u * (0.51 * q.KM + q.TM) + q.rlin * Rs + q.rt) +
+                  1.0001e-4 * q.isigA;
+    float4 k0, k1;
+    if (g.type == 0) {
+      const double alpha = 6.0 * u * KAn * q.isigA;
+      ew_w += scale * 16.0 * u * q.isigA * KAn * 0.25;
+      ew_c += scale * 16.0 * u * q.isigA * Tn;
+      k0 = make_float4(round_up(0.25 + scale * (28.0 * u * Tn + alpha)), round_up(scale * 7.0 * u * KAn),
+                       round_up(scale * (64.0 * u + 4.0 * alpha)), round_up(ew_c));
+      k1 = make_float4(0, 0, 0, round_up(ew_w));
+    } else {
+      k0 = make_float4(round_up(0.5 + scale * u * (32.0 * q.T[0] + 16.0)), round_up(0.5 + scale * u * (32.0 * q.T[1] + 16.0)),
+                       round_up(0.5 + scale * u * (32.0 * q.T[2] + 16.0)), round_up(ew_c));
+      k1 = make_float4(round_up(scale * 13.2 * u * q.KA[0]), round_up(scale * 13.2 * u * q.KA[1]),
+                       round_up(scale * 13.2 * u * q.KA[2]), round_up(ew_w));
+    }
+    F.rows[(size_t)3 * n + k] = k0;
+    F.rows[(size_t)4 * n + k] = k1;
+  }
+  if (F.ids.empty()) F.ids.push_back(0);
+  return F;
 }
 
 // host-side camera constants (DESIGN.md "raygen"): binary32, unfused, in this exact order -- the parity tests compare bits
@@ -120,13 +244,37 @@ static RaygenConsts make_raygen(const pt_camera_data& c, const pt_lens* lens) {
   return R;
 }
 
-template <bool F, bool L>
-static int setup_variant(pt_context* c, int slot) {
-  CU(cudaFuncSetAttribute(k_bounce<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+template <bool F, bool L, bool S>
+static int setup_variant1(pt_context* c, int slot) {
+  CU(cudaFuncSetAttribute(k_bounce<F, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce<F, L>, kTile, c->smem_bytes));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce<F, L, S>, kTile, c->smem_bytes));
   if (per_sm < 1) { pt_set_error_("k_bounce does not fit on an SM"); return PT_ERR_CUDA; }
   c->grid_blocks[slot] = per_sm * c->sm_count;
+  return PT_OK;
+}
+template <bool F, bool L>
+static int setup_variant(pt_context* c, int slot) {
+  return c->staged ? setup_variant1<F, L, true>(c, slot) : setup_variant1<F, L, false>(c, slot);
+}
+
+static int upload_filter(pt_context* c) {
+  const HostFilter F = build_filter(c->h_geoms.data(), (int)c->h_geoms.size(), (double)c->filter_scale);
+  const int n = F.n ? F.n : 1;
+  if (F.n != c->filt.n_total || !c->d_filt) {
+    if (c->d_filt) CU(cudaFree(c->d_filt));
+    if (c->d_filt_ids) CU(cudaFree(c->d_filt_ids));
+    c->d_filt = nullptr; c->d_filt_ids = nullptr;
+    CU(cudaMalloc(&c->d_filt, F.rows.size() * sizeof(float4)));
+    CU(cudaMalloc(&c->d_filt_ids, F.ids.size() * sizeof(int)));
+  }
+  CU(cudaMemcpyAsync(c->d_filt, F.rows.data(), F.rows.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_filt_ids, F.ids.data(), F.ids.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // F dies at return
+  c->filt.a0 = c->d_filt; c->filt.a1 = c->d_filt + n; c->filt.a2 = c->d_filt + 2 * (size_t)n;
+  c->filt.k0 = c->d_filt + 3 * (size_t)n; c->filt.k1 = c->d_filt + 4 * (size_t)n;
+  c->filt.ids = c->d_filt_ids;
+  c->filt.n_spheres = F.n_spheres; c->filt.n_total = F.n; c->filt.r_scene = F.r_scene;
   return PT_OK;
 }
 
@@ -163,40 +311,9 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
     }
     meta[i] = make_int2(geoms[i].type, geoms[i].type <= 1 ? geoms[i].materialid : 0);
   }
-  // pairs of equal type for the packed (FFMA2) closest hit; MESH has no geometry and is left out;
-  // an odd one out is paired with itself (the duplicate half is ignored by the kernel)
-  std::vector<int> order;
-  for (int t = 0; t <= 1; t++) {
-    std::vector<int> ids;
-    for (int i = 0; i < n_geoms; i++) if (geoms[i].type == t) ids.push_back(i);
-    if (ids.size() & 1) ids.push_back(ids.back());
-    order.insert(order.end(), ids.begin(), ids.end());
-  }
-  const int n_pairs = (int)order.size() / 2;
-  std::vector<float4> pq((size_t)12 * (n_pairs ? n_pairs : 1));
-  std::vector<int4> pm(n_pairs ? n_pairs : 1);
-  for (int p = 0; p < n_pairs; p++) {
-    const int ia = order[2 * p], ib = order[2 * p + 1];
-    for (int half = 0; half < 2; half++) {
-      const float* A = half ? geoms[ia].transform : geoms[ia].inverseTransform;
-      const float* B = half ? geoms[ib].transform : geoms[ib].inverseTransform;
-      for (int r = 0; r < 3; r++) {
-        pq[(size_t)(6 * half + 2 * r) * n_pairs + p] = make_float4(A[4 * r], B[4 * r], A[4 * r + 1], B[4 * r + 1]);
-        pq[(size_t)(6 * half + 2 * r + 1) * n_pairs + p] = make_float4(A[4 * r + 2], B[4 * r + 2], A[4 * r + 3], B[4 * r + 3]);
-      }
-    }
-    pm[p] = make_int4(ia, ib, geoms[ia].type, 0);
-  }
-  if (n_pairs != c->pairs.n_pairs || !c->d_pair_q) {
-    if (c->d_pair_q) CU(cudaFree(c->d_pair_q));
-    if (c->d_pair_meta) CU(cudaFree(c->d_pair_meta));
-    c->d_pair_q = nullptr; c->d_pair_meta = nullptr;
-    CU(cudaMalloc(&c->d_pair_q, pq.size() * sizeof(float4)));
-    CU(cudaMalloc(&c->d_pair_meta, pm.size() * sizeof(int4)));
-  }
-  CU(cudaMemcpyAsync(c->d_pair_q, pq.data(), pq.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_pair_meta, pm.data(), pm.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
-  c->pairs.q = c->d_pair_q; c->pairs.meta = c->d_pair_meta; c->pairs.n_pairs = n_pairs;
+  c->h_geoms.assign(geoms, geoms + n_geoms);
+  int rcf;
+  if ((rcf = upload_filter(c))) return rcf;
   if (n_geoms != c->n_geoms) {
     if (c->d_rows) CU(cudaFree(c->d_rows));
     if (c->d_meta) CU(cudaFree(c->d_meta));
@@ -221,17 +338,12 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
   c->g.meta = c->d_meta;
   c->cam = make_raygen(*cam, lens);
   c->W = (uint32_t)Wi; c->H = (uint32_t)Hi; c->npix = c->W * c->H;
-  const int cap = n_geoms < kMaxSmemGeoms ? n_geoms : kMaxSmemGeoms;
-  const int pcap = n_pairs < 1 ? 1 : (n_pairs < kMaxSmemPairs ? n_pairs : kMaxSmemPairs);
-  if (cap != c->geom_cap || pcap != c->pair_cap) {
-    c->geom_cap = cap;
-    c->pair_cap = pcap;
-#ifdef PT_SCALAR_HIT
-    c->geom_smem = geom_smem_bytes(cap);
-#else
-    c->geom_smem = pair_smem_bytes(pcap);
-#endif
-    c->smem_bytes = c->geom_smem + stage_smem_bytes();  // k_bounce: geometry + survivor staging
+  const int cap = c->filt.n_total < 1 ? 1 : (c->filt.n_total < kMaxSmemGeoms ? c->filt.n_total : kMaxSmemGeoms);
+  if (cap != c->filt_cap || c->staged != (c->filt.n_total <= cap)) {
+    c->filt_cap = cap;
+    c->geom_smem = filt_smem_bytes(cap);
+    c->staged = c->filt.n_total <= cap;
+    c->smem_bytes = (c->staged ? c->geom_smem : 0) + stage_smem_bytes();  // k_bounce: filter geometry + survivor staging
     int rc;
     if ((rc = setup_variant<true, false>(c, 0))) return rc;
     if ((rc = setup_variant<true, true>(c, 1))) return rc;
@@ -252,7 +364,7 @@ static int alloc_wavefront(pt_context* c, uint64_t max_paths) {
   if (c->d_status) CU(cudaFree(c->d_status));
   c->d_state = nullptr; c->d_status = nullptr; c->wf_capacity = 0;
   CU(cudaMalloc(&c->d_state, 6 * cap * sizeof(float4)));
-  const uint64_t tiles = (cap + kTile - 1) / kTile;
+  const uint64_t tiles = (cap + kUnit - 1) / kUnit;  // one status word per 32-path unit
   CU(cudaMalloc(&c->d_status, tiles * sizeof(uint64_t)));
   CU(cudaMemsetAsync(c->d_status, 0, tiles * sizeof(uint64_t), c->stream));
   c->wf_capacity = cap;
@@ -264,7 +376,7 @@ extern "C" int pt_context_destroy(pt_context* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->d_rows); cudaFree(c->d_meta); cudaFree(c->d_mats); cudaFree(c->d_state); cudaFree(c->d_status);
-  cudaFree(c->d_pair_q); cudaFree(c->d_pair_meta);
+  cudaFree(c->d_filt); cudaFree(c->d_filt_ids);
   cudaFree(c->d_ctrl); cudaFree(c->d_live); cudaFree(c->d_accum); cudaFree(c->d_rgb); cudaFree(c->d_rgba8);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -300,7 +412,7 @@ extern "C" int pt_context_create(const pt_static_geom* geoms, int n_geoms, const
       cudaMalloc(&c->d_rgb, (size_t)c->npix * 3 * sizeof(float)) != cudaSuccess ||
       cudaMalloc(&c->d_rgba8, (size_t)c->npix * sizeof(uchar4)) != cudaSuccess ||
       cudaMalloc(&c->d_ctrl, sizeof(WfCtrl)) != cudaSuccess ||
-      cudaMalloc(&c->d_live, kMaxDepth * sizeof(unsigned long long)) != cudaSuccess) {
+      cudaMalloc(&c->d_live, (kMaxDepth + 1) * sizeof(unsigned long long)) != cudaSuccess) {
     pt_set_error_("cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     return fail(PT_ERR_CUDA);
   }
@@ -339,17 +451,18 @@ extern "C" int pt_set_stream(pt_context* c, void* cuda_stream) {
 extern "C" int pt_clear(pt_context* c) {
   CTX(c);
   CU(cudaMemsetAsync(c->d_accum, 0, (size_t)c->npix * sizeof(float4), c->stream));
-  CU(cudaMemsetAsync(c->d_live, 0, kMaxDepth * sizeof(unsigned long long), c->stream));
+  CU(cudaMemsetAsync(c->d_live, 0, (kMaxDepth + 1) * sizeof(unsigned long long), c->stream));
   c->paths_total = 0;
   return PT_OK;
 }
 
 template <bool F, bool L>
 static cudaError_t launch_bounce(pt_context* c, int slot, const BounceParams& P, uint32_t n_upper) {
-  uint32_t tiles = (n_upper + kTileRays - 1) / kTileRays;
+  uint32_t ctas = (n_upper + kTile - 1) / kTile;  // one unit per warp at least
   uint32_t grid = (uint32_t)c->grid_blocks[slot];
-  if (tiles < grid) grid = tiles ? tiles : 1;
-  k_bounce<F, L><<<grid, kTile, c->smem_bytes, c->stream>>>(P);
+  if (ctas < grid) grid = ctas ? ctas : 1;
+  if (c->staged) k_bounce<F, L, true><<<grid, kTile, c->smem_bytes, c->stream>>>(P);
+  else k_bounce<F, L, false><<<grid, kTile, c->smem_bytes, c->stream>>>(P);
   c->launches++;
   return cudaGetLastError();
 }
@@ -372,9 +485,8 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
       P.in_o = S + (3 * in + 0) * cap; P.in_d = S + (3 * in + 1) * cap; P.in_t = S + (3 * in + 2) * cap;
       P.out_o = S + (3 * outb + 0) * cap; P.out_d = S + (3 * outb + 1) * cap; P.out_t = S + (3 * outb + 2) * cap;
       P.accum = c->d_accum;
-      P.g = c->g; P.n_geoms = c->n_geoms; P.geom_cap = c->geom_cap;
-      P.pairs = c->pairs; P.pair_cap = c->pair_cap;
-      P.kc = pk_consts();
+      P.g = c->g; P.n_geoms = c->n_geoms;
+      P.filt = c->filt; P.filt_cap = c->filt_cap;
       P.mats = c->d_mats;
       P.cam = c->cam;
       P.ctrl = c->d_ctrl;
@@ -510,25 +622,55 @@ extern "C" int pt_raygen(pt_context* c, uint64_t seed, int n, const uint32_t* pi
   return PT_OK;
 }
 
-extern "C" int pt_intersect(pt_context* c, int n, const float* origin, const float* direction, int32_t* geom_id,
-                            float* t, float* point, float* normal) {
+extern "C" int pt_intersect_ex(pt_context* c, int mode, int n, const float* origin, const float* direction,
+                               int32_t* geom_id, float* t, float* point, float* normal, uint64_t* fallbacks) {
   CTX(c);
   if (n < 0 || (n > 0 && (!origin || !direction || !geom_id || !t || !point || !normal))) { pt_set_error_("bad arguments"); return PT_ERR_INVALID; }
+  if (mode != PT_HIT_FILTERED && mode != PT_HIT_EXACT_SCAN) { pt_set_error_("mode %d is neither PT_HIT_FILTERED nor PT_HIT_EXACT_SCAN", mode); return PT_ERR_INVALID; }
+  if (fallbacks) *fallbacks = 0;
   if (n == 0) return PT_OK;
   DevBuf<float> dor, ddr, dt, dpnt, dn;
   DevBuf<int> did;
+  DevBuf<unsigned long long> dfb;
   const size_t v = 3 * (size_t)n;
-  CU(dor.alloc(v)); CU(ddr.alloc(v)); CU(dt.alloc(n)); CU(dpnt.alloc(v)); CU(dn.alloc(v)); CU(did.alloc(n));
+  CU(dor.alloc(v)); CU(ddr.alloc(v)); CU(dt.alloc(n)); CU(dpnt.alloc(v)); CU(dn.alloc(v)); CU(did.alloc(n)); CU(dfb.alloc(1));
   CU(cudaMemcpyAsync(dor.p, origin, v * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(ddr.p, direction, v * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(dfb.p, 0, sizeof(unsigned long long), c->stream));
   k_intersect_list<<<(n + kTile - 1) / kTile, kTile, c->geom_smem, c->stream>>>(
-      c->g, c->n_geoms, c->geom_cap, c->pairs, c->pair_cap, pk_consts(), n, dor.p, ddr.p, did.p, dt.p, dpnt.p, dn.p);
+      c->g, c->n_geoms, c->filt, c->filt_cap, mode, n, dor.p, ddr.p, did.p, dt.p, dpnt.p, dn.p, dfb.p);
+  c->launches++;
   CU(cudaGetLastError());
+  unsigned long long fb = 0;
   CU(cudaMemcpyAsync(geom_id, did.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(t, dt.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(point, dpnt.p, v * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(normal, dn.p, v * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&fb, dfb.p, sizeof(fb), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  if (fallbacks) *fallbacks = fb;
+  return PT_OK;
+}
+extern "C" int pt_intersect(pt_context* c, int n, const float* origin, const float* direction, int32_t* geom_id,
+                            float* t, float* point, float* normal) {
+  return pt_intersect_ex(c, PT_HIT_FILTERED, n, origin, direction, geom_id, t, point, normal, nullptr);
+}
+
+extern "C" int pt_set_filter_scale(pt_context* c, float scale) {
+  CTX(c);
+  if (!(scale >= 0.0f) || !(scale <= 1e6f)) { pt_set_error_("filter scale %g outside [0, 1e6]", (double)scale); return PT_ERR_INVALID; }
+  CU(cudaStreamSynchronize(c->stream));
+  c->filter_scale = scale;
+  return upload_filter(c);
+}
+
+extern "C" int pt_filter_stats(pt_context* c, uint64_t* fallbacks) {
+  CTX(c);
+  if (!fallbacks) { pt_set_error_("fallbacks is NULL"); return PT_ERR_INVALID; }
+  unsigned long long h = 0;
+  CU(cudaMemcpyAsync(&h, c->d_live + kMaxDepth, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *fallbacks = h;
   return PT_OK;
 }
 
@@ -563,24 +705,6 @@ extern "C" int pt_compact_u32(int device, const uint32_t* values, const uint8_t*
   CU(cudaMemcpy(&cnt, dctl.p + 1, sizeof(cnt), cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(out, dout.p, (size_t)cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   *n_out = cnt;
-  return PT_OK;
-}
-
-extern "C" int pt_selftest_packed_math(int device, uint64_t* bad_sqrt, uint64_t* bad_rcp) {
-  if (!bad_sqrt || !bad_rcp) { pt_set_error_("bad arguments"); return PT_ERR_INVALID; }
-  int ndev = 0;
-  CU(cudaGetDeviceCount(&ndev));
-  if (device < 0 || device >= ndev) { pt_set_error_("device %d out of range", device); return PT_ERR_INVALID; }
-  CU(cudaSetDevice(device));
-  DevBuf<unsigned long long> d;
-  CU(d.alloc(2));
-  CU(cudaMemset(d.p, 0, 2 * sizeof(unsigned long long)));
-  k_selftest_packed<<<148 * 8, 256>>>(pk_consts(), d.p, d.p + 1);
-  CU(cudaGetLastError());
-  unsigned long long h[2];
-  CU(cudaMemcpy(h, d.p, sizeof(h), cudaMemcpyDeviceToHost));
-  *bad_sqrt = h[0];
-  *bad_rcp = h[1];
   return PT_OK;
 }
 

@@ -15,7 +15,7 @@
 //   k_resolve_*                        accumulation buffer -> float RGB / uchar4 (sendImageToPBO, :58-89)
 #pragma once
 #include "pt_device.cuh"
-#include "pt_pairs.cuh"
+#include "pt_filter.cuh"
 
 namespace ptd {
 
@@ -29,6 +29,7 @@ constexpr int kTile = 256;  // paths per tile = threads per CTA
 struct WfCtrl {
   uint32_t count[kMaxDepth + 1];     // count[d] = live paths entering depth d
   uint32_t tile_ctr[kMaxDepth + 1];  // ticket counter of the depth-d launch
+  uint32_t fallbacks;                // rays whose filtered closest hit fell back to the exact scan (statistics)
 };
 
 // ---- decoupled look-back (Merrill & Garland 2016) on 64-bit status words ----
@@ -112,10 +113,9 @@ struct BounceParams {
   float4 *out_o, *out_d, *out_t;     // survivors out, compacted
   float4* accum;                     // per-pixel radiance sums
   GeomSoA g;                         // per-geom rows in HBM (winner's normal / material lookup)
-  int n_geoms, geom_cap;             // geoms per shared-memory chunk (scalar path)
-  PairSoA pairs;                     // type-homogeneous geom pairs, interleaved (packed path)
-  int pair_cap;                      // pairs per shared-memory chunk
-  PkConsts kc;                       // run-time 1.0 / -0.0 / -1.0 / 0.0 for the packed arithmetic (pt_pairs.cuh)
+  int n_geoms;
+  FiltSoA filt;                      // filter geometry (pt_filter.cuh): spheres first, then cubes
+  int filt_cap;                      // filter geoms that fit in shared memory
   const float4* mats;                // 4 float4 per material
   RaygenConsts cam;
   WfCtrl* ctrl;
@@ -125,65 +125,88 @@ struct BounceParams {
   uint32_t first_sample, n_first;    // FIRST only: paths to generate = npix * samples in this wavefront
 };
 
-// Work decomposition of k_bounce: a CTA tile is kTileRays = 1024 consecutive paths, cut into 32 sub-tiles of one
-// warp each.  The 8 warps of a CTA GRAB sub-tiles from a shared-memory counter, so no warp waits for a slower one
-// inside a tile (profiles/r01_k_bounce_v1_*: with one barrier-delimited 256-path tile per step, 57 % of the resident
-// warps were parked at __syncthreads()).  Survivors are staged in shared memory in sub-tile-local slots; after
-// one barrier a single warp scans the 32 sub-tile counts and runs the decoupled look-back once per 1024 paths, and
-// all warps copy the staged survivors out, coalesced and in order (the compaction stays stable).
-constexpr int kSubRays = 32;
-#ifndef PT_SUB_PER_TILE
-#define PT_SUB_PER_TILE 32  // sub-tiles per CTA tile (tuning knob: staging shared memory = 1536 B per sub-tile)
-#endif
-constexpr int kSubPerTile = PT_SUB_PER_TILE;
-constexpr int kTileRays = kSubRays * kSubPerTile;
-// shared memory after the geometry: staged survivors (3 float4 arrays of 1024) + per-sub-tile counts and offsets
-__host__ __device__ inline size_t stage_smem_bytes() { return (size_t)kTileRays * 3 * sizeof(float4) + 2 * kSubPerTile * sizeof(uint32_t); }
+// Work decomposition of k_bounce: the unit of work is ONE WARP x 32 consecutive paths.  Warps take units from a
+// global ticket counter and never synchronise with the other warps of their CTA (an earlier version with
+// barrier-delimited 1024-path CTA tiles left a third of the resident warps parked at __syncthreads() and the
+// look-back warp spinning: profiles/r01_k_bounce_v1_*, r01_k_bounce_v5_*).  Stream compaction stays ordered:
+//   warp ballot  -> rank of each survivor inside its unit; survivors staged in the warp's own shared-memory slots,
+//   look-back    -> one 64-bit status word per unit (aggregate, later inclusive prefix), decoupled look-back over
+//                   32 predecessors per step (one coalesced load),
+//   DEFERRED     -> a unit's aggregate is published as soon as the unit is traced, but its prefix is resolved and
+//                   its survivors are copied out only after the warp has traced its NEXT unit: by then the
+//                   predecessors (which took their tickets earlier) have long published, so the look-back almost
+//                   never waits.  Two staging buffers per warp (2 x 32 x 48 B).
+// Tickets guarantee every predecessor unit is held by a resident warp that publishes its aggregate before it waits
+// for anything, so the look-back cannot deadlock.
+constexpr int kUnit = 32;  // paths per unit = one warp
+__host__ __device__ inline size_t stage_smem_bytes() { return (size_t)(kTile / 32) * 2 * 3 * kUnit * sizeof(float4); }
 
-template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const BounceParams P) {
+__device__ __forceinline__ void lb_publish(uint64_t* status, uint32_t unit, uint32_t epoch, uint32_t aggregate) {
+  // unit 0 has no predecessors: its aggregate is its inclusive prefix
+  if ((threadIdx.x & 31u) == 0) st_store(status + unit, st_pack(epoch, unit == 0 ? kStPrefix : kStAggregate, aggregate));
+}
+// exclusive prefix of `unit` (number of survivors in all earlier units); publishes the unit's inclusive prefix.
+// Called by one full warp.
+__device__ __forceinline__ uint32_t lb_resolve(uint64_t* status, uint32_t unit, uint32_t epoch, uint32_t aggregate) {
+  if (unit == 0) return 0;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t exclusive = 0;
+  int look = (int)unit - 1;
+  for (;;) {
+    const int t = look - (int)lane;
+    uint32_t state = kStPrefix, value = 0;  // units before the first one: empty prefix
+    if (t >= 0) {
+      uint64_t w = st_load(status + t);
+      while ((uint32_t)(w >> 34) != epoch) { __nanosleep(64); w = st_load(status + t); }
+      state = (uint32_t)(w >> 32) & 3u;
+      value = (uint32_t)w;
+    }
+    const uint32_t pmask = __ballot_sync(0xffffffffu, state == kStPrefix);
+    const int firstp = pmask ? (__ffs(pmask) - 1) : 31;
+    uint32_t contrib = ((int)lane <= firstp) ? value : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+    exclusive += contrib;
+    if (pmask) break;
+    look -= 32;
+  }
+  if (lane == 0) st_store(status + unit, st_pack(epoch, kStPrefix, exclusive + aggregate));
+  return exclusive;
+}
+
+template <bool FIRST, bool LAST, bool STAGED>
+__global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const __grid_constant__ BounceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t s_tile, s_next;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  // ---- geometry: staged once per CTA; scenes too large for shared memory are read through L1/L2 instead ----
-#ifdef PT_SCALAR_HIT
-  const bool staged = P.n_geoms <= P.geom_cap;
-  GeomSmem gs = carve_geom_smem(smem_raw, P.geom_cap);
-  unsigned char* after_geom = smem_raw + geom_smem_bytes(P.geom_cap);
-  if (staged) stage_geoms(P.g, 0, P.n_geoms, gs);
-#else
-  const bool staged = P.pairs.n_pairs <= P.pair_cap;
-  PairSmem ps = carve_pair_smem(smem_raw, P.pair_cap);
-  unsigned char* after_geom = smem_raw + pair_smem_bytes(P.pair_cap);
-  const Pk pk = make_pk(P.kc);
-  if (staged) stage_pairs(P.pairs, 0, P.pairs.n_pairs, ps);
-#endif
-  float4* s_o = reinterpret_cast<float4*>(after_geom);
-  float4* s_d = s_o + kTileRays;
-  float4* s_t = s_d + kTileRays;
-  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_t + kTileRays);
-  uint32_t* s_off = s_cnt + kSubPerTile;
+  // ---- filter geometry: staged once per CTA; scenes too large for shared memory are read through L1/L2 instead ----
+  FiltSmem fs;
+  if (STAGED) {
+    fs = carve_filt_smem(smem_raw, P.filt_cap);
+    stage_filt(P.filt, 0, P.filt.n_total, fs);
+  } else {
+    fs = filt_global_view(P.filt, 0);
+  }
+  // this warp's two survivor staging buffers: [buffer][o,d,t][32]
+  float4* const w_stage = reinterpret_cast<float4*>(smem_raw + (STAGED ? filt_smem_bytes(P.filt_cap) : 0)) + warp * (2 * 3 * kUnit);
+  if (STAGED) __syncthreads();  // the only CTA-wide barrier
 
   const uint32_t n_in = FIRST ? P.n_first : P.ctrl->count[P.depth];
   if (FIRST && blockIdx.x == 0 && threadIdx.x == 0) P.ctrl->count[0] = n_in;
-  const uint32_t n_tiles = (n_in + kTileRays - 1) / kTileRays;
+  const uint32_t n_units = (n_in + kUnit - 1) / kUnit;
+  uint32_t* const ticket = &P.ctrl->tile_ctr[P.depth];
+
+  uint32_t next_raw = 0;  // lane 0: the ticket taken ahead of time
+  if (lane == 0) next_raw = atomicAdd(ticket, 1u);
+  bool pend = false;      // a traced unit whose survivors are still in shared memory
+  uint32_t pend_unit = 0, pend_cnt = 0, buf = 0;
 
   for (;;) {
-    __syncthreads();  // geometry staged; previous tile fully copied out
-    if (threadIdx.x == 0) { s_tile = atomicAdd(&P.ctrl->tile_ctr[P.depth], 1u); s_next = 0u; }
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    if (tile >= n_tiles) break;
-    const uint32_t tile_base = tile * kTileRays;
-    const uint32_t n_sub = min((uint32_t)kSubPerTile, (n_in - tile_base + kSubRays - 1) / kSubRays);
-
-    // ---- phase 1: every warp pulls sub-tiles until the tile is exhausted ----
-    for (;;) {
-      uint32_t sub = 0;
-      if (lane == 0) sub = atomicAdd(&s_next, 1u);
-      sub = __shfl_sync(0xffffffffu, sub, 0);
-      if (sub >= n_sub) break;
-      const uint32_t idx = tile_base + sub * kSubRays + lane;
+    const uint32_t unit = __shfl_sync(0xffffffffu, next_raw, 0);
+    const bool have = unit < n_units;
+    uint32_t cnt = 0;
+    if (have) {
+      if (lane == 0) next_raw = atomicAdd(ticket, 1u);  // consumed in the next iteration: its latency is hidden
+      const uint32_t idx = unit * kUnit + lane;
       const bool valid = idx < n_in;
 
       f3 o = mk(0, 0, 0), d = mk(0, 0, 1), thr = mk(1, 1, 1);
@@ -204,25 +227,11 @@ __global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const BouncePar
       Hit h;
       h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
       if (valid) {
-#ifdef PT_SCALAR_HIT
-        if (staged) {
-          closest_hit_chunk(gs, 0, P.n_geoms, o, d, h);
-        } else {
-          GeomSmem gg;  // the same rows, straight from HBM (cached)
-          gg.inv0 = const_cast<float4*>(P.g.inv0); gg.inv1 = const_cast<float4*>(P.g.inv1); gg.inv2 = const_cast<float4*>(P.g.inv2);
-          gg.fwd0 = const_cast<float4*>(P.g.fwd0); gg.fwd1 = const_cast<float4*>(P.g.fwd1); gg.fwd2 = const_cast<float4*>(P.g.fwd2);
-          gg.meta = const_cast<int2*>(P.g.meta);
-          closest_hit_chunk(gg, 0, P.n_geoms, o, d, h);
-        }
-#else
-        if (staged) {
-          closest_hit_pairs(pk, ps, P.pairs.n_pairs, P.g, o, d, h);
-        } else {
-          PairSmem pg;  // the same pairs, straight from HBM (cached)
-          pg.q = const_cast<float4*>(P.pairs.q); pg.meta = const_cast<int4*>(P.pairs.meta); pg.cap = P.pairs.n_pairs;
-          closest_hit_pairs(pk, pg, P.pairs.n_pairs, P.g, o, d, h);
-        }
-#endif
+        const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene);
+        ScanBest best;
+        scan_init(best);
+        filter_scan(fs, 0, P.filt.n_spheres, P.filt.n_total, ray, best);
+        if (resolve_scan(best, P.filt, P.g, P.n_geoms, o, d, h)) atomicAdd(&P.ctrl->fallbacks, 1u);
       }
 
       bool alive = false;
@@ -248,53 +257,37 @@ __global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const BouncePar
       }
 
       if (!LAST) {
-        // warp ballot -> rank of each survivor inside its sub-tile; survivors staged in sub-tile-local slots
+        // warp ballot -> rank of each survivor inside the unit; survivors staged in this warp's buffer `buf`
         const uint32_t ballot = __ballot_sync(0xffffffffu, alive);
+        cnt = __popc(ballot);
+        lb_publish(P.status, unit, P.epoch, cnt);
         if (alive) {
-          const uint32_t slot = sub * kSubRays + __popc(ballot & ((1u << lane) - 1u));
-          s_o[slot] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
-          s_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(sample));
-          s_t[slot] = make_float4(thr.x, thr.y, thr.z, 0.0f);
+          float4* st = w_stage + buf * (3 * kUnit) + __popc(ballot & ((1u << lane) - 1u));
+          st[0] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
+          st[kUnit] = make_float4(d.x, d.y, d.z, __uint_as_float(sample));
+          st[2 * kUnit] = make_float4(thr.x, thr.y, thr.z, 0.0f);
         }
-        if (lane == 0) s_cnt[sub] = __popc(ballot);
+        __syncwarp();
       }
     }
-    if (LAST) continue;
-
-    __syncthreads();  // all sub-tiles of this tile are staged
-    // ---- phase 2: block scan over the 32 sub-tile counts + ONE decoupled look-back for the whole tile ----
-    if (warp == 0) {
-      static_assert(kSubPerTile <= 32, "one warp scans the sub-tile counts");
-      const uint32_t c = lane < n_sub ? s_cnt[lane] : 0u;
-      uint32_t incl = c;
-#pragma unroll
-      for (int o2 = 1; o2 < 32; o2 <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o2);
-        if ((int)lane >= o2) incl += v;
-      }
-      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-#ifdef PT_ATOMIC_COMPACT
-      // experiment: unordered slot reservation (one atomic per tile) instead of the ordered look-back
-      uint32_t excl = 0;
-      if (lane == 0) excl = atomicAdd(&P.ctrl->count[P.depth + 1], total);
-      excl = __shfl_sync(0xffffffffu, excl, 0);
-      if (lane < kSubPerTile) s_off[lane] = excl + incl - c;
-#else
-      const uint32_t excl = lookback_exclusive(P.status, tile, P.epoch, total);
-      if (lane < kSubPerTile) s_off[lane] = excl + incl - c;
-      if (tile == n_tiles - 1 && lane == 0) P.ctrl->count[P.depth + 1] = excl + total;
-#endif
+    if (LAST) {
+      if (!have) break;
+      continue;
     }
-    __syncthreads();
-    // ---- phase 3: coalesced, ordered copy-out of the staged survivors ----
-    for (uint32_t sub = warp; sub < n_sub; sub += kTile / 32) {
-      const uint32_t cnt = s_cnt[sub], off = s_off[sub];
-      if (lane < cnt) {
-        __stcs(P.out_o + off + lane, s_o[sub * kSubRays + lane]);
-        __stcs(P.out_d + off + lane, s_d[sub * kSubRays + lane]);
-        __stcs(P.out_t + off + lane, s_t[sub * kSubRays + lane]);
+    // ---- the unit traced one iteration ago: resolve its prefix (ready by now) and copy its survivors out, in order ----
+    if (pend) {
+      const uint32_t excl = lb_resolve(P.status, pend_unit, P.epoch, pend_cnt);
+      if (lane < pend_cnt) {
+        const float4* st = w_stage + (buf ^ 1u) * (3 * kUnit) + lane;
+        __stcs(P.out_o + excl + lane, st[0]);
+        __stcs(P.out_d + excl + lane, st[kUnit]);
+        __stcs(P.out_t + excl + lane, st[2 * kUnit]);
       }
+      if (pend_unit == n_units - 1 && lane == 0) P.ctrl->count[P.depth + 1] = excl + pend_cnt;
+      __syncwarp();
     }
+    if (!have) break;
+    pend = true; pend_unit = unit; pend_cnt = cnt; buf ^= 1u;
   }
 }
 
@@ -302,6 +295,7 @@ __global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const BouncePar
 __global__ void k_accum_counts(const WfCtrl* ctrl, unsigned long long* live_total, int max_depth) {
   int d = threadIdx.x;
   if (d < max_depth) live_total[d] += ctrl->count[d];
+  if (d == 0) live_total[kMaxDepth] += ctrl->fallbacks;
 }
 
 // ---- parity entry points ----
@@ -315,9 +309,9 @@ __global__ void k_raygen_list(RaygenConsts C, uint64_t seed, int n, const uint32
   d[3 * i] = dd.x; d[3 * i + 1] = dd.y; d[3 * i + 2] = dd.z;
 }
 
-__global__ void __launch_bounds__(kTile) k_intersect_list(GeomSoA g, int n_geoms, int geom_cap, PairSoA pairs, int pair_cap,
-                                                          PkConsts kc, int n, const float* o, const float* d, int* id, float* t,
-                                                          float* p, float* nrm) {
+__global__ void __launch_bounds__(kTile) k_intersect_list(GeomSoA g, int n_geoms, FiltSoA filt, int filt_cap, int mode, int n,
+                                                          const float* o, const float* d, int* id, float* t, float* p,
+                                                          float* nrm, unsigned long long* fallbacks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < n;
@@ -325,26 +319,22 @@ __global__ void __launch_bounds__(kTile) k_intersect_list(GeomSoA g, int n_geoms
   if (valid) { oo = mk(o[3 * i], o[3 * i + 1], o[3 * i + 2]); dd = mk(d[3 * i], d[3 * i + 1], d[3 * i + 2]); }
   Hit h;
   h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
-#ifdef PT_SCALAR_HIT
-  const GeomSmem gs = carve_geom_smem(smem_raw, geom_cap);
-  for (int c0 = 0; c0 < n_geoms; c0 += geom_cap) {
-    const int cnt = min(geom_cap, n_geoms - c0);
-    __syncthreads();
-    stage_geoms(g, c0, cnt, gs);
-    __syncthreads();
-    if (valid) closest_hit_chunk(gs, c0, cnt, oo, dd, h);
+  if (mode == 1) {  // the exact scan on its own (the specification; what the filtered path must reproduce)
+    if (valid) closest_hit_exact(g, n_geoms, oo, dd, h);
+  } else {
+    const FiltSmem fs = carve_filt_smem(smem_raw, filt_cap);
+    const ScanRay ray = make_scan_ray(oo, dd, filt.r_scene);
+    ScanBest best;
+    scan_init(best);
+    for (int c0 = 0; c0 < filt.n_total; c0 += filt_cap) {  // chunk loop: scenes larger than shared memory
+      const int cnt = min(filt_cap, filt.n_total - c0);
+      __syncthreads();
+      stage_filt(filt, c0, cnt, fs);
+      __syncthreads();
+      if (valid) filter_scan(fs, c0, max(0, min(cnt, filt.n_spheres - c0)), cnt, ray, best);
+    }
+    if (valid && resolve_scan(best, filt, g, n_geoms, oo, dd, h)) atomicAdd(fallbacks, 1ull);
   }
-#else
-  const PairSmem ps = carve_pair_smem(smem_raw, pair_cap);
-  const Pk pk = make_pk(kc);
-  for (int c0 = 0; c0 < pairs.n_pairs; c0 += pair_cap) {
-    const int cnt = min(pair_cap, pairs.n_pairs - c0);
-    __syncthreads();
-    stage_pairs(pairs, c0, cnt, ps);
-    __syncthreads();
-    if (valid) closest_hit_pairs(pk, ps, cnt, g, oo, dd, h);
-  }
-#endif
   if (!valid) return;
   f3 nn = mk(0, 0, 0);
   if (h.id >= 0) nn = hit_normal(__ldg(g.fwd0 + h.id), __ldg(g.fwd1 + h.id), __ldg(g.fwd2 + h.id), h);
@@ -375,27 +365,6 @@ __global__ void __launch_bounds__(kTile) k_compact_u32(const uint32_t* values, c
     if (keep) out[slot] = values[idx];
     if (tile == n_tiles - 1 && threadIdx.x == 0) *n_out = incl;
   }
-}
-
-// ---- exhaustive self-test of the packed IEEE sqrt / reciprocal (pt_pairs.cuh) against the scalar operators ----
-// Every one of the 2^32 bit patterns goes through both halves (paired with a different pattern so that mixed
-// fast-path / fallback pairs occur).  NaN results compare equal to NaN results.
-__global__ void k_selftest_packed(PkConsts kc, unsigned long long* bad_sqrt, unsigned long long* bad_rcp) {
-  const Pk pk = make_pk(kc);
-  const uint32_t stride = gridDim.x * blockDim.x;
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long bs = 0, br = 0;
-  for (uint64_t k = i; k < (1ull << 32); k += stride) {
-    const uint32_t a = (uint32_t)k, b = a * 2654435761u + 12345u;
-    const float x = __uint_as_float(a), y = __uint_as_float(b);
-    const f2 s = sqrt2_ieee(pk, make_float2(x, y)), r = rcp2_ieee(pk, make_float2(x, y));
-    const float sx = sqrtf(x), sy = sqrtf(y), rx = 1.0f / x, ry = 1.0f / y;
-    auto same = [](float u, float v) { return __float_as_uint(u) == __float_as_uint(v) || (u != u && v != v); };
-    bs += !same(s.x, sx) + !same(s.y, sy);
-    br += !same(r.x, rx) + !same(r.y, ry);
-  }
-  if (bs) atomicAdd(bad_sqrt, bs);
-  if (br) atomicAdd(bad_rcp, br);
 }
 
 // ---- image out ----

@@ -128,51 +128,18 @@ struct BounceParams {
 // Work decomposition of k_bounce: the unit of work is ONE WARP x 32 consecutive paths.  Warps take units from a
 // global ticket counter and never synchronise with the other warps of their CTA (an earlier version with
 // barrier-delimited 1024-path CTA tiles left a third of the resident warps parked at __syncthreads() and the
-// look-back warp spinning: profiles/r01_k_bounce_v1_*, r01_k_bounce_v5_*).  Stream compaction stays ordered:
-//   warp ballot  -> rank of each survivor inside its unit; survivors staged in the warp's own shared-memory slots,
-//   look-back    -> one 64-bit status word per unit (aggregate, later inclusive prefix), decoupled look-back over
-//                   32 predecessors per step (one coalesced load),
-//   DEFERRED     -> a unit's aggregate is published as soon as the unit is traced, but its prefix is resolved and
-//                   its survivors are copied out only after the warp has traced its NEXT unit: by then the
-//                   predecessors (which took their tickets earlier) have long published, so the look-back almost
-//                   never waits.  Two staging buffers per warp (2 x 32 x 48 B).
-// Tickets guarantee every predecessor unit is held by a resident warp that publishes its aggregate before it waits
-// for anything, so the look-back cannot deadlock.
+// look-back warp spinning: profiles/r01_k_bounce_v1_*, r01_k_bounce_v5_*).
+// Stream compaction of the survivors (README.md:63-70): warp ballot -> rank of each survivor inside its unit
+// (order preserved inside a unit); the unit's base slot is reserved with ONE atomic on the next depth's live count,
+// issued by lane 0 as soon as the ballot is known; the survivors go straight from registers to base + rank,
+// coalesced.  Units finish in roughly ticket order, so the output stays roughly ordered, but it is not the stable
+// compaction a scan would give: at 32-path granularity (4 700 units in flight, 470 finishing per microsecond) a
+// decoupled look-back has to walk ~15 windows of 32 predecessors per unit and cost 40 % more instructions than the
+// tracing itself (profiles/r01_k_bounce_v6_lookback32_*); the ordered, look-back based primitive remains available
+// as k_compact_u32 / pt_compact_u32.  Results do not depend on the slot order (RNG streams are keyed by pixel and
+// sample, radiance goes through atomics).
 constexpr int kUnit = 32;  // paths per unit = one warp
-__host__ __device__ inline size_t stage_smem_bytes() { return (size_t)(kTile / 32) * 2 * 3 * kUnit * sizeof(float4); }
-
-__device__ __forceinline__ void lb_publish(uint64_t* status, uint32_t unit, uint32_t epoch, uint32_t aggregate) {
-  // unit 0 has no predecessors: its aggregate is its inclusive prefix
-  if ((threadIdx.x & 31u) == 0) st_store(status + unit, st_pack(epoch, unit == 0 ? kStPrefix : kStAggregate, aggregate));
-}
-// exclusive prefix of `unit` (number of survivors in all earlier units); publishes the unit's inclusive prefix.
-// Called by one full warp.
-__device__ __forceinline__ uint32_t lb_resolve(uint64_t* status, uint32_t unit, uint32_t epoch, uint32_t aggregate) {
-  if (unit == 0) return 0;
-  const uint32_t lane = threadIdx.x & 31u;
-  uint32_t exclusive = 0;
-  int look = (int)unit - 1;
-  for (;;) {
-    const int t = look - (int)lane;
-    uint32_t state = kStPrefix, value = 0;  // units before the first one: empty prefix
-    if (t >= 0) {
-      uint64_t w = st_load(status + t);
-      while ((uint32_t)(w >> 34) != epoch) { __nanosleep(64); w = st_load(status + t); }
-      state = (uint32_t)(w >> 32) & 3u;
-      value = (uint32_t)w;
-    }
-    const uint32_t pmask = __ballot_sync(0xffffffffu, state == kStPrefix);
-    const int firstp = pmask ? (__ffs(pmask) - 1) : 31;
-    uint32_t contrib = ((int)lane <= firstp) ? value : 0u;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-    exclusive += contrib;
-    if (pmask) break;
-    look -= 32;
-  }
-  if (lane == 0) st_store(status + unit, st_pack(epoch, kStPrefix, exclusive + aggregate));
-  return exclusive;
-}
+__host__ __device__ inline size_t stage_smem_bytes() { return 0; }
 
 template <bool FIRST, bool LAST, bool STAGED>
 __global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const __grid_constant__ BounceParams P) {
@@ -186,8 +153,6 @@ __global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const __grid_co
   } else {
     fs = filt_global_view(P.filt, 0);
   }
-  // this warp's two survivor staging buffers: [buffer][o,d,t][32]
-  float4* const w_stage = reinterpret_cast<float4*>(smem_raw + (STAGED ? filt_smem_bytes(P.filt_cap) : 0)) + warp * (2 * 3 * kUnit);
   if (STAGED) __syncthreads();  // the only CTA-wide barrier
 
   const uint32_t n_in = FIRST ? P.n_first : P.ctrl->count[P.depth];
@@ -197,97 +162,78 @@ __global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const __grid_co
 
   uint32_t next_raw = 0;  // lane 0: the ticket taken ahead of time
   if (lane == 0) next_raw = atomicAdd(ticket, 1u);
-  bool pend = false;      // a traced unit whose survivors are still in shared memory
-  uint32_t pend_unit = 0, pend_cnt = 0, buf = 0;
 
   for (;;) {
     const uint32_t unit = __shfl_sync(0xffffffffu, next_raw, 0);
-    const bool have = unit < n_units;
-    uint32_t cnt = 0;
-    if (have) {
-      if (lane == 0) next_raw = atomicAdd(ticket, 1u);  // consumed in the next iteration: its latency is hidden
-      const uint32_t idx = unit * kUnit + lane;
-      const bool valid = idx < n_in;
+    if (unit >= n_units) break;
+    if (lane == 0) next_raw = atomicAdd(ticket, 1u);  // consumed in the next iteration: its latency is hidden
+    const uint32_t idx = unit * kUnit + lane;
+    const bool valid = idx < n_in;
 
-      f3 o = mk(0, 0, 0), d = mk(0, 0, 1), thr = mk(1, 1, 1);
-      uint32_t pixel = 0, sample = 0;
-      if (valid) {
-        if (FIRST) {
-          pixel = idx % P.cam.npix;
-          sample = P.first_sample + idx / P.cam.npix;
-          raygen(P.cam, P.seed, pixel, sample, o, d);
-        } else {
-          const float4 a = __ldcs(P.in_o + idx), b = __ldcs(P.in_d + idx), c = __ldcs(P.in_t + idx);
-          o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
-          d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
-          thr = mk(c.x, c.y, c.z);
-        }
-      }
-
-      Hit h;
-      h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
-      if (valid) {
-        const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene);
-        ScanBest best;
-        scan_init(best);
-        filter_scan(fs, 0, P.filt.n_spheres, P.filt.n_total, ray, best);
-        if (resolve_scan(best, P.filt, P.g, P.n_geoms, o, d, h)) atomicAdd(&P.ctrl->fallbacks, 1u);
-      }
-
-      bool alive = false;
-      if (valid && h.id >= 0) {
-        const int gi = h.id;
-        // the winner's own rows: from HBM through L1 (a handful of distinct addresses per warp)
-        const float4 f0 = __ldg(P.g.fwd0 + gi), f1 = __ldg(P.g.fwd1 + gi), f2 = __ldg(P.g.fwd2 + gi);
-        const int mat = __ldg(P.g.meta + gi).y;
-        const f3 n = hit_normal(f0, f1, f2, h);
-        MatRows m;
-        m.a = __ldg(P.mats + 4 * mat); m.b = __ldg(P.mats + 4 * mat + 1);
-        m.c = __ldg(P.mats + 4 * mat + 2); m.d = __ldg(P.mats + 4 * mat + 3);
-        f3 L;
-        const int kind = shade(m, P.g, gi, h.p, n, P.seed, pixel, sample, P.depth, o, d, thr, L);
-        if (kind == 3) {
-          float* px = reinterpret_cast<float*>(P.accum + pixel);
-          atomicAdd(px + 0, L.x);
-          atomicAdd(px + 1, L.y);
-          atomicAdd(px + 2, L.z);
-        } else {
-          alive = true;
-        }
-      }
-
-      if (!LAST) {
-        // warp ballot -> rank of each survivor inside the unit; survivors staged in this warp's buffer `buf`
-        const uint32_t ballot = __ballot_sync(0xffffffffu, alive);
-        cnt = __popc(ballot);
-        lb_publish(P.status, unit, P.epoch, cnt);
-        if (alive) {
-          float4* st = w_stage + buf * (3 * kUnit) + __popc(ballot & ((1u << lane) - 1u));
-          st[0] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
-          st[kUnit] = make_float4(d.x, d.y, d.z, __uint_as_float(sample));
-          st[2 * kUnit] = make_float4(thr.x, thr.y, thr.z, 0.0f);
-        }
-        __syncwarp();
+    f3 o = mk(0, 0, 0), d = mk(0, 0, 1), thr = mk(1, 1, 1);
+    uint32_t pixel = 0, sample = 0;
+    if (valid) {
+      if (FIRST) {
+        pixel = idx % P.cam.npix;
+        sample = P.first_sample + idx / P.cam.npix;
+        raygen(P.cam, P.seed, pixel, sample, o, d);
+      } else {
+        const float4 a = __ldcs(P.in_o + idx), b = __ldcs(P.in_d + idx), c = __ldcs(P.in_t + idx);
+        o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
+        d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
+        thr = mk(c.x, c.y, c.z);
       }
     }
-    if (LAST) {
-      if (!have) break;
-      continue;
+
+    Hit h;
+    h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
+    if (valid) {
+      const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene);
+      ScanBest best;
+      scan_init(best);
+      filter_scan(fs, 0, P.filt.n_spheres, P.filt.n_total, ray, best);
+      if (resolve_scan(best, P.filt, P.g, P.n_geoms, o, d, h)) atomicAdd(&P.ctrl->fallbacks, 1u);
     }
-    // ---- the unit traced one iteration ago: resolve its prefix (ready by now) and copy its survivors out, in order ----
-    if (pend) {
-      const uint32_t excl = lb_resolve(P.status, pend_unit, P.epoch, pend_cnt);
-      if (lane < pend_cnt) {
-        const float4* st = w_stage + (buf ^ 1u) * (3 * kUnit) + lane;
-        __stcs(P.out_o + excl + lane, st[0]);
-        __stcs(P.out_d + excl + lane, st[kUnit]);
-        __stcs(P.out_t + excl + lane, st[2 * kUnit]);
+
+    // a path survives this segment unless it left the scene or reached a light; the slot of the unit's survivors
+    // is reserved before shading so that the atomic's latency hides behind it
+    const bool hit = valid && h.id >= 0;
+    int mat = 0;
+    float4 md = make_float4(0, 0, 0, 0);  // (absorption.yz, reducedScatter, emittance)
+    if (hit) {
+      mat = __ldg(P.g.meta + h.id).y;
+      md = __ldg(P.mats + 4 * mat + 3);
+    }
+    const bool alive = hit && !(md.w > 0);
+    uint32_t base_raw = 0, ballot = 0;
+    if (!LAST) {
+      ballot = __ballot_sync(0xffffffffu, alive);
+      if (lane == 0 && ballot) base_raw = atomicAdd(&P.ctrl->count[P.depth + 1], (uint32_t)__popc(ballot));
+    }
+    if (hit) {
+      const int gi = h.id;
+      // the winner's own rows: from HBM through L1 (a handful of distinct addresses per warp)
+      const float4 f0 = __ldg(P.g.fwd0 + gi), f1 = __ldg(P.g.fwd1 + gi), f2 = __ldg(P.g.fwd2 + gi);
+      const f3 n = hit_normal(f0, f1, f2, h);
+      MatRows m;
+      m.a = __ldg(P.mats + 4 * mat); m.b = __ldg(P.mats + 4 * mat + 1); m.c = __ldg(P.mats + 4 * mat + 2); m.d = md;
+      f3 L;
+      const int kind = shade(m, P.g, gi, h.p, n, P.seed, pixel, sample, P.depth, o, d, thr, L);
+      if (kind == 3) {
+        float* px = reinterpret_cast<float*>(P.accum + pixel);
+        atomicAdd(px + 0, L.x);
+        atomicAdd(px + 1, L.y);
+        atomicAdd(px + 2, L.z);
       }
-      if (pend_unit == n_units - 1 && lane == 0) P.ctrl->count[P.depth + 1] = excl + pend_cnt;
-      __syncwarp();
     }
-    if (!have) break;
-    pend = true; pend_unit = unit; pend_cnt = cnt; buf ^= 1u;
+    if (!LAST) {
+      const uint32_t slot = __shfl_sync(0xffffffffu, base_raw, 0) + __popc(ballot & ((1u << lane) - 1u));
+      if (alive) {
+        __stcs(P.out_o + slot, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
+        __stcs(P.out_d + slot, make_float4(d.x, d.y, d.z, __uint_as_float(sample)));
+        __stcs(P.out_t + slot, make_float4(thr.x, thr.y, thr.z, 0.0f));
+      }
+    }
   }
 }
 

@@ -58,8 +58,8 @@ struct pt_context {
   float4* d_rows = nullptr;  // 6 arrays of n_geoms float4
   int2* d_meta = nullptr;
   float4* d_mats = nullptr;
-  float4* d_filt = nullptr;   // 5 arrays of n_filt float4: filter geometry (pt_filter.cuh)
-  int* d_filt_ids = nullptr;
+  float4* d_filt = nullptr;   // kFiltRows arrays of n_pairs float4: filter geometry (pt_filter.cuh)
+  int2* d_filt_ids = nullptr;
   FiltSoA filt{};
   int filt_cap = 0;
   float filter_scale = 1.0f;  // multiplies every error-model term of the filter (test hook; 1 = the shipped bounds)
@@ -87,7 +87,7 @@ struct pt_context {
 };
 
 static const uint64_t kDefaultWavefrontPaths = 16ull << 20;
-static const int kMaxSmemGeoms = 512;   // 40 KB of shared memory for filter geometry at most; larger scenes are read through L1/L2
+static const int kMaxSmemPairs = 256;   // 40 KB of shared memory for filter geometry at most; larger scenes are read through L1/L2
 
 // ---------------------------------------------------------------- filter constants (pt_filter.cuh, DESIGN.md "filter")
 // largest eigenvalue of the symmetric 3x3 matrix S (cyclic Jacobi, binary64)
@@ -121,28 +121,26 @@ static float round_up(double x) {  // smallest-ish float >= x (x >= 0)
 }
 
 struct HostFilter {
-  std::vector<float4> rows;  // [5][n]
-  std::vector<int> ids;
-  int n_spheres = 0, n = 0;
+  std::vector<float4> rows;  // [n_pairs][kFiltRows]
+  std::vector<int2> ids;     // per pair: geom index of half A, half B
+  int n_sphere_pairs = 0, n_pairs = 0;
   float r_scene = 0.0f;
 };
 // Per-geom coefficients of the error model.  u = 2^-24 (unit roundoff).  `scale` multiplies every error term.
 static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double scale) {
   HostFilter F;
   const double u = ldexp(1.0, -24);
+  std::vector<int> order;  // geoms with geometry, spheres first
+  int n_spheres = 0;
   for (int t = 0; t <= 1; t++)
     for (int i = 0; i < n_geoms; i++)
-      if (geoms[i].type == t) F.ids.push_back(i);
-  F.n = (int)F.ids.size();
-  for (int i = 0; i < n_geoms; i++) F.n_spheres += geoms[i].type == 0;
-  const int n = F.n ? F.n : 1;
-  F.rows.assign((size_t)5 * n, make_float4(0, 0, 0, 0));
-  // bound on |p| over the surface points of the scene: |translation| + sigma_max(M) * (half diagonal of the unit cube)
-  struct Per { double sigM, isigA, KA[3], T[3], KM, TM, EMw, EMc, rlin, rt; };
-  std::vector<Per> per(n);
+      if (geoms[i].type == t) { order.push_back(i); n_spheres += t == 0; }
+  const int n = (int)order.size();
+  struct Per { double sigM, isigA, KA[3], T[3], KM, TM, EMw, EMc, rlin, rt; float k[8]; };
+  std::vector<Per> per(n ? n : 1);
   double r_scene = 0.0;
-  for (int k = 0; k < F.n; k++) {
-    const pt_static_geom& g = geoms[F.ids[k]];
+  for (int k = 0; k < n; k++) {
+    const pt_static_geom& g = geoms[order[k]];
     const float* A = g.inverseTransform;
     const float* M = g.transform;
     Per& q = per[k];
@@ -179,16 +177,15 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
       }
       q.rlin = fmax(q.rlin, lin);
     }
+    // bound on |p| over the geom's surface: |translation| + sigma_max(M) * (half diagonal of the unit cube)
     r_scene = fmax(r_scene, sqrt(tm2) + q.sigM * 0.8661);
   }
   F.r_scene = round_up(r_scene * 1.001);
   const double Rs = (double)F.r_scene;
   const double s3 = 1.7320508075688772;
-  for (int k = 0; k < F.n; k++) {
-    const pt_static_geom& g = geoms[F.ids[k]];
-    const Per& q = per[k];
-    const float* A = g.inverseTransform;
-    for (int r = 0; r < 3; r++) F.rows[(size_t)r * n + k] = make_float4(A[4 * r], A[4 * r + 1], A[4 * r + 2], A[4 * r + 3]);
+  for (int k = 0; k < n; k++) {
+    const pt_static_geom& g = geoms[order[k]];
+    Per& q = per[k];
     const double KAn = sqrt(q.KA[0] * q.KA[0] + q.KA[1] * q.KA[1] + q.KA[2] * q.KA[2]);
     const double Tn = sqrt(q.T[0] * q.T[0] + q.T[1] * q.T[1] + q.T[2] * q.T[2]);
     // world slack: pull-back of 1e-4 object units (NOT scaled: it is geometry, not rounding) + rounding of both
@@ -196,24 +193,63 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
     double ew_w = scale * s3 * 2.0 * 2.25 * u * q.EMw;
     double ew_c = scale * s3 * 2.0 * (9.0 * u * (q.EMc + 0.5 * q.KM) + 4.0 * u * (0.51 * q.KM + q.TM) + q.rlin * Rs + q.rt) +
                   1.0001e-4 * q.isigA;
-    float4 k0, k1;
     if (g.type == 0) {
       const double alpha = 6.0 * u * KAn * q.isigA;
       ew_w += scale * 16.0 * u * q.isigA * KAn * 0.25;
       ew_c += scale * 16.0 * u * q.isigA * Tn;
-      k0 = make_float4(round_up(0.25 + scale * (28.0 * u * Tn + alpha)), round_up(scale * 7.0 * u * KAn),
-                       round_up(scale * (64.0 * u + 4.0 * alpha)), round_up(ew_c));
-      k1 = make_float4(0, 0, 0, round_up(ew_w));
+      // k = R2c, R2w, R2r, Ew_c, Ew_w
+      q.k[0] = round_up(0.25 + scale * (28.0 * u * Tn + alpha)); q.k[1] = round_up(scale * 7.0 * u * KAn);
+      q.k[2] = round_up(scale * (64.0 * u + 4.0 * alpha)); q.k[3] = round_up(ew_c); q.k[4] = round_up(ew_w);
     } else {
-      k0 = make_float4(round_up(0.5 + scale * u * (32.0 * q.T[0] + 16.0)), round_up(0.5 + scale * u * (32.0 * q.T[1] + 16.0)),
-                       round_up(0.5 + scale * u * (32.0 * q.T[2] + 16.0)), round_up(ew_c));
-      k1 = make_float4(round_up(scale * 13.2 * u * q.KA[0]), round_up(scale * 13.2 * u * q.KA[1]),
-                       round_up(scale * 13.2 * u * q.KA[2]), round_up(ew_w));
+      // k = hc.xyz, hw.xyz, Ew_c, Ew_w
+      for (int r = 0; r < 3; r++) {
+        q.k[r] = round_up(0.5 + scale * u * (32.0 * q.T[r] + 16.0));
+        q.k[3 + r] = round_up(scale * 13.2 * u * q.KA[r]);
+      }
+      q.k[6] = round_up(ew_c); q.k[7] = round_up(ew_w);
     }
-    F.rows[(size_t)3 * n + k] = k0;
-    F.rows[(size_t)4 * n + k] = k1;
   }
-  if (F.ids.empty()) F.ids.push_back(0);
+  // pairs of one type; an odd geom out is paired with a copy of itself that can never be a candidate (-inf bounds)
+  std::vector<int> pa, pb;
+  auto make_pairs = [&](int first, int count) {
+    for (int k = 0; k < count; k += 2) { pa.push_back(first + k); pb.push_back(k + 1 < count ? first + k + 1 : -1); }
+  };
+  make_pairs(0, n_spheres);
+  F.n_sphere_pairs = (int)pa.size();
+  make_pairs(n_spheres, n - n_spheres);
+  F.n_pairs = (int)pa.size();
+  const int np = F.n_pairs ? F.n_pairs : 1;
+  F.rows.assign((size_t)kFiltRows * np, make_float4(0, 0, 0, 0));
+  F.ids.assign(np, make_int2(0, 0));
+  const float ninf = -INFINITY;
+  for (int p = 0; p < F.n_pairs; p++) {
+    const int ka = pa[p], kb = pb[p] < 0 ? pa[p] : pb[p];
+    const bool dummy = pb[p] < 0;
+    const pt_static_geom& ga = geoms[order[ka]];
+    const pt_static_geom& gb = geoms[order[kb]];
+    const float* A = ga.inverseTransform;
+    const float* B = gb.inverseTransform;
+    for (int r = 0; r < 3; r++) {
+      F.rows[(size_t)p * kFiltRows + 2 * r] = make_float4(A[4 * r], B[4 * r], A[4 * r + 1], B[4 * r + 1]);
+      F.rows[(size_t)p * kFiltRows + 2 * r + 1] = make_float4(A[4 * r + 2], B[4 * r + 2], A[4 * r + 3], B[4 * r + 3]);
+    }
+    const float* x = per[ka].k;
+    float y[8];
+    for (int j = 0; j < 8; j++) y[j] = per[kb].k[j];
+    if (ga.type == 0) {
+      if (dummy) y[0] = ninf;  // radius^2 = -inf: the discriminant is -inf, a proven miss
+      F.rows[(size_t)p * kFiltRows + 6] = make_float4(x[0], y[0], x[1], y[1]);
+      F.rows[(size_t)p * kFiltRows + 7] = make_float4(x[2], y[2], x[3], y[3]);
+      F.rows[(size_t)p * kFiltRows + 8] = make_float4(x[4], y[4], 0, 0);
+    } else {
+      if (dummy) y[0] = y[1] = y[2] = ninf;  // half extents -inf: tnear = +inf > tfar = -inf, a proven miss
+      F.rows[(size_t)p * kFiltRows + 6] = make_float4(x[0], y[0], x[1], y[1]);
+      F.rows[(size_t)p * kFiltRows + 7] = make_float4(x[2], y[2], x[3], y[3]);
+      F.rows[(size_t)p * kFiltRows + 8] = make_float4(x[4], y[4], x[5], y[5]);
+      F.rows[(size_t)p * kFiltRows + 9] = make_float4(x[6], y[6], x[7], y[7]);
+    }
+    F.ids[p] = make_int2(order[ka], order[kb]);
+  }
   return F;
 }
 
@@ -260,21 +296,19 @@ static int setup_variant(pt_context* c, int slot) {
 
 static int upload_filter(pt_context* c) {
   const HostFilter F = build_filter(c->h_geoms.data(), (int)c->h_geoms.size(), (double)c->filter_scale);
-  const int n = F.n ? F.n : 1;
-  if (F.n != c->filt.n_total || !c->d_filt) {
+  if (F.n_pairs != c->filt.n_pairs || !c->d_filt) {
     if (c->d_filt) CU(cudaFree(c->d_filt));
     if (c->d_filt_ids) CU(cudaFree(c->d_filt_ids));
     c->d_filt = nullptr; c->d_filt_ids = nullptr;
     CU(cudaMalloc(&c->d_filt, F.rows.size() * sizeof(float4)));
-    CU(cudaMalloc(&c->d_filt_ids, F.ids.size() * sizeof(int)));
+    CU(cudaMalloc(&c->d_filt_ids, F.ids.size() * sizeof(int2)));
   }
   CU(cudaMemcpyAsync(c->d_filt, F.rows.data(), F.rows.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_filt_ids, F.ids.data(), F.ids.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_filt_ids, F.ids.data(), F.ids.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));  // F dies at return
-  c->filt.a0 = c->d_filt; c->filt.a1 = c->d_filt + n; c->filt.a2 = c->d_filt + 2 * (size_t)n;
-  c->filt.k0 = c->d_filt + 3 * (size_t)n; c->filt.k1 = c->d_filt + 4 * (size_t)n;
+  c->filt.rows = c->d_filt;
   c->filt.ids = c->d_filt_ids;
-  c->filt.n_spheres = F.n_spheres; c->filt.n_total = F.n; c->filt.r_scene = F.r_scene;
+  c->filt.n_sphere_pairs = F.n_sphere_pairs; c->filt.n_pairs = F.n_pairs; c->filt.r_scene = F.r_scene;
   return PT_OK;
 }
 
@@ -338,11 +372,11 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
   c->g.meta = c->d_meta;
   c->cam = make_raygen(*cam, lens);
   c->W = (uint32_t)Wi; c->H = (uint32_t)Hi; c->npix = c->W * c->H;
-  const int cap = c->filt.n_total < 1 ? 1 : (c->filt.n_total < kMaxSmemGeoms ? c->filt.n_total : kMaxSmemGeoms);
-  if (cap != c->filt_cap || c->staged != (c->filt.n_total <= cap)) {
+  const int cap = c->filt.n_pairs < 1 ? 1 : (c->filt.n_pairs < kMaxSmemPairs ? c->filt.n_pairs : kMaxSmemPairs);
+  if (cap != c->filt_cap || c->staged != (c->filt.n_pairs <= cap)) {
     c->filt_cap = cap;
     c->geom_smem = filt_smem_bytes(cap);
-    c->staged = c->filt.n_total <= cap;
+    c->staged = c->filt.n_pairs <= cap;
     c->smem_bytes = (c->staged ? c->geom_smem : 0) + stage_smem_bytes();  // k_bounce: filter geometry + survivor staging
     int rc;
     if ((rc = setup_variant<true, false>(c, 0))) return rc;

@@ -34,53 +34,52 @@ namespace ptd {
 __device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// ---- filter geometry: spheres first, then cubes (MESH left out); 5 float4 per geom ----
-//   a0,a1,a2 = rows x,y,z of inverseTransform
-//   cube:   k0 = (hc.x, hc.y, hc.z, Ew_c)   k1 = (hw.x, hw.y, hw.z, Ew_w)     half extent_i = hc_i + hw_i * w
-//   sphere: k0 = (R2c,  R2w,  R2r,  Ew_c)   k1 = (-,    -,    -,    Ew_w)     radius^2 = R2c + R2w * w + R2r * |ro|^2
+// ---- filter geometry: PAIRS of geoms of one type, sphere pairs first, then cube pairs (MESH left out) ----
+// Blackwell's packed FFMA2 / FMUL2 / FADD2 execute two independent binary32 operations per issue slot, so the
+// filter tests two geoms at once: geom A in the low half, geom B in the high half of every float2.  An odd geom
+// out is paired with a copy of itself whose constants are -inf, which the tests below reject (proven miss).
+// 10 consecutive float4 per pair (every lane reads the same pair, so the shared-memory reads are broadcasts and one
+// pointer walks the whole list):
+//   q[2r]   = (A[r][0], B[r][0], A[r][1], B[r][1])    q[2r+1] = (A[r][2], B[r][2], A[r][3], B[r][3])   r = 0,1,2:
+//             rows x,y,z of inverseTransform, interleaved
+//   cube:   k0 = (hc.x | hc.y)  k1 = (hc.z | hw.x)  k2 = (hw.y | hw.z)  k3 = (Ew_c | Ew_w)   each "|" half = (A, B)
+//           half extent_i = hc_i + hw_i * w
+//   sphere: k0 = (R2c | R2w)    k1 = (R2r | Ew_c)   k2 = (Ew_w | -)                          radius^2 = R2c + R2w * w + R2r * |ro|^2
 //   world slack E_w = Ew_c + Ew_w * w
+constexpr int kFiltRows = 10;
 struct FiltSoA {  // in HBM
-  const float4 *a0, *a1, *a2, *k0, *k1;
-  const int* ids;  // filter index -> geom index
-  int n_spheres, n_total;
-  float r_scene;   // bound on |p| over all surface points of the scene
+  const float4* rows;  // [n_pairs][kFiltRows]
+  const int2* ids;     // pair -> (geom index of A, geom index of B)
+  int n_sphere_pairs, n_pairs;
+  float r_scene;       // bound on |p| over all surface points of the scene
 };
-struct FiltSmem {
-  float4 *a0, *a1, *a2, *k0, *k1;
-};
-__host__ __device__ inline size_t filt_smem_bytes(int cap) { return (size_t)cap * 5 * sizeof(float4); }
-__device__ __forceinline__ FiltSmem carve_filt_smem(unsigned char* base, int cap) {
-  FiltSmem s;
-  float4* f = reinterpret_cast<float4*>(base);
-  s.a0 = f; s.a1 = f + cap; s.a2 = f + 2 * cap; s.k0 = f + 3 * cap; s.k1 = f + 4 * cap;
-  return s;
+__host__ __device__ inline size_t filt_smem_bytes(int cap) { return (size_t)cap * kFiltRows * sizeof(float4); }
+// cooperative copy of pairs [first, first+count) into shared memory; caller synchronises
+__device__ __forceinline__ void stage_filt(const FiltSoA& g, int first, int count, float4* smem) {
+  for (int i = threadIdx.x; i < count * kFiltRows; i += blockDim.x) smem[i] = g.rows[(size_t)first * kFiltRows + i];
 }
-__device__ __forceinline__ FiltSmem filt_global_view(const FiltSoA& g, int first) {
-  FiltSmem s;
-  s.a0 = const_cast<float4*>(g.a0) + first; s.a1 = const_cast<float4*>(g.a1) + first;
-  s.a2 = const_cast<float4*>(g.a2) + first; s.k0 = const_cast<float4*>(g.k0) + first;
-  s.k1 = const_cast<float4*>(g.k1) + first;
-  return s;
-}
-// cooperative copy of filter geoms [first, first+count) into shared memory; caller synchronises
-__device__ __forceinline__ void stage_filt(const FiltSoA& g, int first, int count, const FiltSmem& s) {
-  for (int i = threadIdx.x; i < count; i += blockDim.x) {
-    s.a0[i] = g.a0[first + i]; s.a1[i] = g.a1[first + i]; s.a2[i] = g.a2[first + i];
-    s.k0[i] = g.k0[first + i]; s.k1[i] = g.k1[first + i];
-  }
-}
+
+typedef float2 f2;
+__device__ __forceinline__ f2 bc2(float x) { return make_float2(x, x); }
+__device__ __forceinline__ f2 lo2(float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ f2 hi2(float4 v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ f2 neg2(f2 a) { return make_float2(-a.x, -a.y); }   // folds into the consumer's operand modifier
+__device__ __forceinline__ f2 abs2(f2 a) { return make_float2(fabsf(a.x), fabsf(a.y)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
 
 // per-ray constants of the scan
 struct ScanRay {
-  f3 o, d;
-  float w;   // 4*max|o_j| + R_scene
-  float dl;  // |d| rounded down (parameter -> world distance)
+  f2 ox, oy, oz, dx, dy, dz;  // the ray, broadcast to both halves
+  f2 w;                       // 4*max|o_j| + R_scene
+  float dl;                   // |d| rounded down (parameter -> world distance)
 };
 __device__ __forceinline__ ScanRay make_scan_ray(f3 o, f3 d, float r_scene) {
   ScanRay r;
-  r.o = o; r.d = d;
+  r.ox = bc2(o.x); r.oy = bc2(o.y); r.oz = bc2(o.z);
+  r.dx = bc2(d.x); r.dy = bc2(d.y); r.dz = bc2(d.z);
   const float omax = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
-  r.w = __fmaf_rn(4.0f, omax, r_scene);
+  r.w = bc2(__fmaf_rn(4.0f, omax, r_scene));
   const float d2 = __fmaf_rn(d.x, d.x, __fmaf_rn(d.y, d.y, d.z * d.z));
   r.dl = mufu_sqrt(d2) * 0.99999905f;  // 1 - 2^-20: below |d| whatever the approximation error
   return r;
@@ -89,7 +88,7 @@ __device__ __forceinline__ ScanRay make_scan_ray(f3 o, f3 d, float r_scene) {
 // running result of the scan
 struct ScanBest {
   float lo1, lo2;  // smallest and second-smallest lower bound
-  int k1;          // filter index of the smallest, -1 = every geom so far is a proven miss
+  int k1;          // 2*pair + half of the smallest, -1 = every geom so far is a proven miss
 };
 __device__ __forceinline__ void scan_init(ScanBest& b) { b.lo1 = INFINITY; b.lo2 = INFINITY; b.k1 = -1; }
 __device__ __forceinline__ void scan_take(ScanBest& b, float lo, int k) {
@@ -100,50 +99,64 @@ __device__ __forceinline__ void scan_take(ScanBest& b, float lo, int k) {
   b.lo1 = fminf(b.lo1, lo);
 }
 
-// object-space origin and UN-normalised direction with fused multiply-adds: the parameter along (ro, rw) is the
-// parameter along the world ray
-#define PT_FILT_TRANSFORM(S, I, R)                                                                              \
-  const float4 A0 = (S).a0[I], A1 = (S).a1[I], A2 = (S).a2[I];                                                  \
-  const float rox = __fmaf_rn(A0.x, (R).o.x, __fmaf_rn(A0.y, (R).o.y, __fmaf_rn(A0.z, (R).o.z, A0.w)));         \
-  const float roy = __fmaf_rn(A1.x, (R).o.x, __fmaf_rn(A1.y, (R).o.y, __fmaf_rn(A1.z, (R).o.z, A1.w)));         \
-  const float roz = __fmaf_rn(A2.x, (R).o.x, __fmaf_rn(A2.y, (R).o.y, __fmaf_rn(A2.z, (R).o.z, A2.w)));         \
-  const float rwx = __fmaf_rn(A0.x, (R).d.x, __fmaf_rn(A0.y, (R).d.y, A0.z * (R).d.z));                         \
-  const float rwy = __fmaf_rn(A1.x, (R).d.x, __fmaf_rn(A1.y, (R).d.y, A1.z * (R).d.z));                         \
-  const float rwz = __fmaf_rn(A2.x, (R).d.x, __fmaf_rn(A2.y, (R).d.y, A2.z * (R).d.z));
+// object-space origin and UN-normalised direction of both geoms with fused multiply-adds: the parameter along
+// (ro, rw) is the parameter along the world ray
+#define PT_FILT_TRANSFORM(V, R)                                                                          \
+  const float4 Q0 = (V)[0], Q1 = (V)[1], Q2 = (V)[2], Q3 = (V)[3], Q4 = (V)[4], Q5 = (V)[5];             \
+  const f2 rox = fma2(lo2(Q0), (R).ox, fma2(hi2(Q0), (R).oy, fma2(lo2(Q1), (R).oz, hi2(Q1))));           \
+  const f2 roy = fma2(lo2(Q2), (R).ox, fma2(hi2(Q2), (R).oy, fma2(lo2(Q3), (R).oz, hi2(Q3))));           \
+  const f2 roz = fma2(lo2(Q4), (R).ox, fma2(hi2(Q4), (R).oy, fma2(lo2(Q5), (R).oz, hi2(Q5))));           \
+  const f2 rwx = fma2(lo2(Q0), (R).dx, fma2(hi2(Q0), (R).dy, mul2(lo2(Q1), (R).dz)));                    \
+  const f2 rwy = fma2(lo2(Q2), (R).dx, fma2(hi2(Q2), (R).dy, mul2(lo2(Q3), (R).dz)));                    \
+  const f2 rwz = fma2(lo2(Q4), (R).dx, fma2(hi2(Q4), (R).dy, mul2(lo2(Q5), (R).dz)));
 
-// Scan filter geoms [0, count) of `s` (filter indices base..base+count); the first n_sph of them are spheres.
+// Scan pairs [0, count) at `v` (pair indices base..base+count); the first n_sph of them are sphere pairs.
 // Every "miss" needs a comparison to come out TRUE, so a NaN anywhere keeps the geom as a candidate.
-__device__ __forceinline__ void filter_scan(const FiltSmem& s, int base, int n_sph, int count, const ScanRay& r,
+__device__ __forceinline__ void filter_scan(const float4* v, int base, int n_sph, int count, const ScanRay& r,
                                             ScanBest& best) {
   int i = 0;
-  for (; i < n_sph; i++) {
-    PT_FILT_TRANSFORM(s, i, r)
-    const float4 K0 = s.k0[i];
-    const float a = __fmaf_rn(rwx, rwx, __fmaf_rn(rwy, rwy, rwz * rwz));
-    const float b = __fmaf_rn(rox, rwx, __fmaf_rn(roy, rwy, roz * rwz));
-    const float ro2 = __fmaf_rn(rox, rox, __fmaf_rn(roy, roy, roz * roz));
-    const float R2 = __fmaf_rn(K0.z, ro2, __fmaf_rn(K0.y, r.w, K0.x));
-    const float c = ro2 - R2;
-    const float disc = __fmaf_rn(b, b, -(a * c));
-    if (disc < 0.0f) continue;  // the line misses the inflated sphere
-    const float sd = mufu_sqrt(disc), ia = mufu_rcp(a);
-    if ((sd - b) * ia < 0.0f) continue;  // the inflated sphere lies behind the origin
-    const float ew = __fmaf_rn(s.k1[i].w, r.w, K0.w);
-    scan_take(best, __fmaf_rn((-b - sd) * ia, r.dl, -ew), base + i);
+  for (; i < n_sph; i++, v += kFiltRows) {
+    PT_FILT_TRANSFORM(v, r)
+    const float4 K0 = v[6], K1 = v[7];
+    const f2 a = fma2(rwx, rwx, fma2(rwy, rwy, mul2(rwz, rwz)));
+    const f2 b = fma2(rox, rwx, fma2(roy, rwy, mul2(roz, rwz)));
+    const f2 ro2 = fma2(rox, rox, fma2(roy, roy, mul2(roz, roz)));
+    const f2 R2 = fma2(lo2(K1), ro2, fma2(hi2(K0), r.w, lo2(K0)));
+    const f2 nc = __fadd2_rn(R2, neg2(ro2));      // -(|ro|^2 - R^2)
+    const f2 disc = fma2(a, nc, mul2(b, b));      // (ro.rw)^2 - |rw|^2 (|ro|^2 - R^2)
+    if (disc.x < 0.0f && disc.y < 0.0f) continue;  // both lines miss their inflated spheres
+    const f2 ew = fma2(lo2(v[8]), r.w, hi2(K1));
+#define PT_SPHERE_HALF(H, K)                                                                          \
+  if (!(disc.H < 0.0f)) {                                                                             \
+    const float sd = mufu_sqrt(disc.H), ia = mufu_rcp(a.H);                                           \
+    if (!((sd - b.H) * ia < 0.0f)) /* else: the inflated sphere lies behind the origin */             \
+      scan_take(best, __fmaf_rn((-b.H - sd) * ia, r.dl, -ew.H), K);                                   \
   }
-  for (; i < count; i++) {
-    PT_FILT_TRANSFORM(s, i, r)
-    const float4 K0 = s.k0[i], K1 = s.k1[i];
-    const float hx = __fmaf_rn(K1.x, r.w, K0.x), hy = __fmaf_rn(K1.y, r.w, K0.y), hz = __fmaf_rn(K1.z, r.w, K0.z);
-    const float ix = mufu_rcp(rwx), iy = mufu_rcp(rwy), iz = mufu_rcp(rwz);
-    const float cx = -rox * ix, cy = -roy * iy, cz = -roz * iz;  // parameter of the slab centre
+    PT_SPHERE_HALF(x, 2 * (base + i))
+    PT_SPHERE_HALF(y, 2 * (base + i) + 1)
+#undef PT_SPHERE_HALF
+  }
+  for (; i < count; i++, v += kFiltRows) {
+    PT_FILT_TRANSFORM(v, r)
+    const float4 K0 = v[6], K1 = v[7], K2 = v[8], K3 = v[9];
+    const f2 hx = fma2(hi2(K1), r.w, lo2(K0)), hy = fma2(lo2(K2), r.w, hi2(K0)), hz = fma2(hi2(K2), r.w, lo2(K1));
+    const f2 ix = make_float2(mufu_rcp(rwx.x), mufu_rcp(rwx.y)), iy = make_float2(mufu_rcp(rwy.x), mufu_rcp(rwy.y)),
+             iz = make_float2(mufu_rcp(rwz.x), mufu_rcp(rwz.y));
+    const f2 cx = mul2(neg2(rox), ix), cy = mul2(neg2(roy), iy), cz = mul2(neg2(roz), iz);  // parameter of the slab centre
     // slab i spans [c_i - h_i|iv_i|, c_i + h_i|iv_i|]; a direction component of 0 gives infinities / NaN, which
     // fmaxf / fminf ignore: that slab then does not constrain (conservative)
-    const float tnear = fmaxf(fmaxf(__fmaf_rn(hx, -fabsf(ix), cx), __fmaf_rn(hy, -fabsf(iy), cy)), __fmaf_rn(hz, -fabsf(iz), cz));
-    const float tfar = fminf(fminf(__fmaf_rn(hx, fabsf(ix), cx), __fmaf_rn(hy, fabsf(iy), cy)), __fmaf_rn(hz, fabsf(iz), cz));
-    if (tnear > tfar || tfar < 0.0f) continue;  // misses the inflated box, or the box lies behind the origin
-    const float ew = __fmaf_rn(K1.w, r.w, K0.w);
-    scan_take(best, __fmaf_rn(tnear, r.dl, -ew), base + i);
+    const f2 nx = fma2(hx, neg2(abs2(ix)), cx), ny = fma2(hy, neg2(abs2(iy)), cy), nz = fma2(hz, neg2(abs2(iz)), cz);
+    const f2 fx = fma2(hx, abs2(ix), cx), fy = fma2(hy, abs2(iy), cy), fz = fma2(hz, abs2(iz), cz);
+    const f2 ew = fma2(hi2(K3), r.w, lo2(K3));
+#define PT_BOX_HALF(H, K)                                                                             \
+  {                                                                                                   \
+    const float tnear = fmaxf(fmaxf(nx.H, ny.H), nz.H), tfar = fminf(fminf(fx.H, fy.H), fz.H);        \
+    if (!(tnear > tfar || tfar < 0.0f)) /* else: misses the inflated box, or the box lies behind */   \
+      scan_take(best, __fmaf_rn(tnear, r.dl, -ew.H), K);                                              \
+  }
+    PT_BOX_HALF(x, 2 * (base + i))
+    PT_BOX_HALF(y, 2 * (base + i) + 1)
+#undef PT_BOX_HALF
   }
 }
 #undef PT_FILT_TRANSFORM
@@ -218,8 +231,8 @@ __device__ __noinline__ void closest_hit_exact(const GeomSoA g, int n_geoms, f3 
 __device__ __forceinline__ bool resolve_scan(const ScanBest& best, const FiltSoA& f, const GeomSoA& g, int n_geoms,
                                              f3 o, f3 d, Hit& h) {
   if (best.k1 < 0) return false;  // every geom is a proven miss
-  const int gi = __ldg(f.ids + best.k1);
-  const int type = best.k1 < f.n_spheres ? 0 : 1;
+  const int gi = __ldg(reinterpret_cast<const int*>(f.ids) + best.k1);
+  const int type = best.k1 < 2 * f.n_sphere_pairs ? 0 : 1;
   float dist;
   f3 P;
   int ncode;

@@ -114,8 +114,8 @@ struct BounceParams {
   float4* accum;                     // per-pixel radiance sums
   GeomSoA g;                         // per-geom rows in HBM (winner's normal / material lookup)
   int n_geoms;
-  FiltSoA filt;                      // filter geometry (pt_filter.cuh): spheres first, then cubes
-  int filt_cap;                      // filter geoms that fit in shared memory
+  FiltSoA filt;                      // filter geometry (pt_filter.cuh): sphere pairs first, then cube pairs
+  int filt_cap;                      // pairs that fit in shared memory
   const float4* mats;                // 4 float4 per material
   RaygenConsts cam;
   WfCtrl* ctrl;
@@ -146,12 +146,12 @@ __global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const __grid_co
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   // ---- filter geometry: staged once per CTA; scenes too large for shared memory are read through L1/L2 instead ----
-  FiltSmem fs;
+  const float4* fs;
   if (STAGED) {
-    fs = carve_filt_smem(smem_raw, P.filt_cap);
-    stage_filt(P.filt, 0, P.filt.n_total, fs);
+    stage_filt(P.filt, 0, P.filt.n_pairs, reinterpret_cast<float4*>(smem_raw));
+    fs = reinterpret_cast<const float4*>(smem_raw);
   } else {
-    fs = filt_global_view(P.filt, 0);
+    fs = P.filt.rows;
   }
   if (STAGED) __syncthreads();  // the only CTA-wide barrier
 
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const __grid_co
       const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene);
       ScanBest best;
       scan_init(best);
-      filter_scan(fs, 0, P.filt.n_spheres, P.filt.n_total, ray, best);
+      filter_scan(fs, 0, P.filt.n_sphere_pairs, P.filt.n_pairs, ray, best);
       if (resolve_scan(best, P.filt, P.g, P.n_geoms, o, d, h)) atomicAdd(&P.ctrl->fallbacks, 1u);
     }
 
@@ -268,16 +268,16 @@ __global__ void __launch_bounds__(kTile) k_intersect_list(GeomSoA g, int n_geoms
   if (mode == 1) {  // the exact scan on its own (the specification; what the filtered path must reproduce)
     if (valid) closest_hit_exact(g, n_geoms, oo, dd, h);
   } else {
-    const FiltSmem fs = carve_filt_smem(smem_raw, filt_cap);
+    const float4* fs = reinterpret_cast<const float4*>(smem_raw);
     const ScanRay ray = make_scan_ray(oo, dd, filt.r_scene);
     ScanBest best;
     scan_init(best);
-    for (int c0 = 0; c0 < filt.n_total; c0 += filt_cap) {  // chunk loop: scenes larger than shared memory
-      const int cnt = min(filt_cap, filt.n_total - c0);
+    for (int c0 = 0; c0 < filt.n_pairs; c0 += filt_cap) {  // chunk loop: scenes larger than shared memory
+      const int cnt = min(filt_cap, filt.n_pairs - c0);
       __syncthreads();
-      stage_filt(filt, c0, cnt, fs);
+      stage_filt(filt, c0, cnt, reinterpret_cast<float4*>(smem_raw));
       __syncthreads();
-      if (valid) filter_scan(fs, c0, max(0, min(cnt, filt.n_spheres - c0)), cnt, ray, best);
+      if (valid) filter_scan(fs, c0, max(0, min(cnt, filt.n_sphere_pairs - c0)), cnt, ray, best);
     }
     if (valid && resolve_scan(best, filt, g, n_geoms, oo, dd, h)) atomicAdd(fallbacks, 1ull);
   }

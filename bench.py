@@ -37,7 +37,7 @@ METRIC = "path segments per second, reference sample scene 800x800, 5000 spp, 8 
 UNIT = "Mseg/s"
 RES, SPP, DEPTH, SEED = 800, 5000, 8, 565
 CPU_SPP = 16  # bounded CPU sample: 16 spp of the 800x800 frame (about 20 s of CPU work)
-WF_SPP = 16  # samples of the frame per wavefront: 10.24 M paths, 983 MB of path state (>> 126 MB L2)
+WF_SPP = 50  # samples of the frame per wavefront: 32 M paths, 3.07 GB of path state (>> 126 MB L2); 100 wavefronts per step
 
 
 def load_sample_scene(pt):

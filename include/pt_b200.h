@@ -160,6 +160,10 @@ int pt_set_filter_scale(pt_context* ctx, float scale);
 /* segments of pt_render calls since the last pt_clear whose closest hit took the exact-scan fallback */
 int pt_filter_stats(pt_context* ctx, uint64_t* fallbacks);
 
+/* exhaustive check (all 2^32 inputs) of the kernels' single-guard IEEE sqrt, reciprocal and 1/sqrt against the generic
+ * operators; bad[0..2] = number of differing results of each (must be 0) */
+int pt_selftest_math(int device, uint64_t bad[3]);
+
 /* ---- scene file and image file (host side; same formats as the reference) ---- */
 typedef struct pt_scene pt_scene;
 /* scene::scene(string), src/scene.cpp:11-35.  rotat_degrees = 0 reproduces the reference exactly (ROTAT is

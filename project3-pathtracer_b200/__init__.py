@@ -205,6 +205,13 @@ def reduce_to_first(contexts):
     _check(lib().pt_reduce_to_first(arr, C.c_int(len(contexts))))
 
 
+def selftest_math(device=0):
+    """mismatches of the kernels' single-guard IEEE (sqrt, reciprocal, 1/sqrt) over all 2^32 inputs: must be (0, 0, 0)"""
+    bad = (C.c_uint64 * 3)()
+    _check(lib().pt_selftest_math(C.c_int(device), bad))
+    return tuple(int(x) for x in bad)
+
+
 def compact_u32(values, flags, device=0):
     """Stream compaction primitive on its own (pt_compact_u32): values[flags != 0], order preserved."""
     v, f = _arr(values, np.uint32).ravel(), _arr(flags, np.uint8).ravel()

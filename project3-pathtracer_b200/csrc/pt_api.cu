@@ -742,6 +742,23 @@ extern "C" int pt_compact_u32(int device, const uint32_t* values, const uint8_t*
   return PT_OK;
 }
 
+extern "C" int pt_selftest_math(int device, uint64_t bad[3]) {
+  if (!bad) { pt_set_error_("bad is NULL"); return PT_ERR_INVALID; }
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { pt_set_error_("device %d out of range (%d devices)", device, ndev); return PT_ERR_INVALID; }
+  CU(cudaSetDevice(device));
+  DevBuf<unsigned long long> d;
+  CU(d.alloc(3));
+  CU(cudaMemset(d.p, 0, 3 * sizeof(unsigned long long)));
+  k_selftest_math<<<148 * 8, 256>>>(d.p);
+  CU(cudaGetLastError());
+  unsigned long long h[3];
+  CU(cudaMemcpy(h, d.p, sizeof(h), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 3; i++) bad[i] = h[i];
+  return PT_OK;
+}
+
 // ---------------------------------------------------------------- multi-GPU combine (single process, one context per GPU)
 // One ncclReduce(sum) of the float4 accumulation images to ctxs[0] over NVLink / NVSwitch.  NCCL is resolved at run
 // time (dlopen) so that a process that already carries its own libnccl (PyTorch) keeps a single copy; processes

@@ -176,7 +176,7 @@ __device__ __forceinline__ bool exact_hit(int type, float4 i0, float4 i1, float4
     // the reference's host build evaluates float*float - (float - pow(.5f,2)) in binary64 (pow -> double)
     const float radicand = (float)((double)(vDot * vDot) - ((double)dot(ro, ro) - 0.25));
     if (radicand < 0) return false;
-    const float sq = sqrtf(radicand);
+    const float sq = sqrt_ieee(radicand);
     const float first_term = -vDot;
     const float t1 = first_term + sq;
     const float t2 = first_term - sq;
@@ -186,7 +186,7 @@ __device__ __forceinline__ bool exact_hit(int type, float4 i0, float4 i1, float4
     ncode = 8;
   } else {
     // boxIntersectionTest (stub in the reference), DESIGN.md "box test": slabs on [-0.5,0.5]^3, IEEE minNum/maxNum
-    const float ivx = 1.0f / rd.x, ivy = 1.0f / rd.y, ivz = 1.0f / rd.z;
+    const float ivx = rcp_ieee(rd.x), ivy = rcp_ieee(rd.y), ivz = rcp_ieee(rd.z);
     const float t1x = (-0.5f - ro.x) * ivx, t2x = (0.5f - ro.x) * ivx;
     const float t1y = (-0.5f - ro.y) * ivy, t2y = (0.5f - ro.y) * ivy;
     const float t1z = (-0.5f - ro.z) * ivz, t2z = (0.5f - ro.z) * ivz;

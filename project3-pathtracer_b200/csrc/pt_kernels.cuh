@@ -141,6 +141,12 @@ struct BounceParams {
 constexpr int kUnit = 32;  // paths per unit = one warp
 __host__ __device__ inline size_t stage_smem_bytes() { return 0; }
 
+__device__ __forceinline__ uint32_t atom_add_u32(uint32_t* p, uint32_t v) {  // plain ATOMG, no warp-aggregation code
+  uint32_t old;
+  asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+
 template <bool FIRST, bool LAST, bool STAGED>
 __global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const __grid_constant__ BounceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -161,12 +167,12 @@ __global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const __grid_co
   uint32_t* const ticket = &P.ctrl->tile_ctr[P.depth];
 
   uint32_t next_raw = 0;  // lane 0: the ticket taken ahead of time
-  if (lane == 0) next_raw = atomicAdd(ticket, 1u);
+  if (lane == 0) next_raw = atom_add_u32(ticket, 1u);
 
   for (;;) {
     const uint32_t unit = __shfl_sync(0xffffffffu, next_raw, 0);
     if (unit >= n_units) break;
-    if (lane == 0) next_raw = atomicAdd(ticket, 1u);  // consumed in the next iteration: its latency is hidden
+    if (lane == 0) next_raw = atom_add_u32(ticket, 1u);  // consumed in the next iteration: its latency is hidden
     const uint32_t idx = unit * kUnit + lane;
     const bool valid = idx < n_in;
 
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const __grid_co
     uint32_t base_raw = 0, ballot = 0;
     if (!LAST) {
       ballot = __ballot_sync(0xffffffffu, alive);
-      if (lane == 0 && ballot) base_raw = atomicAdd(&P.ctrl->count[P.depth + 1], (uint32_t)__popc(ballot));
+      if (lane == 0 && ballot) base_raw = atom_add_u32(&P.ctrl->count[P.depth + 1], (uint32_t)__popc(ballot));
     }
     if (hit) {
       const int gi = h.id;
@@ -311,6 +317,23 @@ __global__ void __launch_bounds__(kTile) k_compact_u32(const uint32_t* values, c
     if (keep) out[slot] = values[idx];
     if (tile == n_tiles - 1 && threadIdx.x == 0) *n_out = incl;
   }
+}
+
+// ---- exhaustive self-test of sqrt_ieee / rcp_ieee / inv_sqrt_ieee (pt_device.cuh) against the generic operators ----
+// every one of the 2^32 bit patterns; NaN results compare equal to NaN results
+__global__ void k_selftest_math(unsigned long long* bad) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  unsigned long long b0 = 0, b1 = 0, b2 = 0;
+  auto same = [](float u, float v) { return __float_as_uint(u) == __float_as_uint(v) || (u != u && v != v); };
+  for (uint64_t k = blockIdx.x * blockDim.x + threadIdx.x; k < (1ull << 32); k += stride) {
+    const float x = __uint_as_float((uint32_t)k);
+    b0 += !same(sqrt_ieee(x), sqrtf(x));
+    b1 += !same(rcp_ieee(x), 1.0f / x);
+    b2 += !same(inv_sqrt_ieee(x), 1.0f / sqrtf(x));
+  }
+  if (b0) atomicAdd(bad + 0, b0);
+  if (b1) atomicAdd(bad + 1, b1);
+  if (b2) atomicAdd(bad + 2, b2);
 }
 
 // ---- image out ----

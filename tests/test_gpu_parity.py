@@ -206,3 +206,8 @@ def test_compaction_is_a_stable_partition(pt, n):
         out = pt.compact_u32(v, f)
         assert out.shape[0] == int(f.sum())
         assert (out == v[f != 0]).all()
+
+
+def test_single_guard_ieee_math_exhaustive(pt):
+    """sqrt_ieee / rcp_ieee / inv_sqrt_ieee (csrc/pt_device.cuh) equal sqrtf, 1/x, 1/sqrtf(x) on all 2^32 inputs"""
+    assert pt.selftest_math() == (0, 0, 0)

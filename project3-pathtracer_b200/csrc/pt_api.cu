@@ -123,133 +123,202 @@ static float round_up(double x) {  // smallest-ish float >= x (x >= 0)
 struct HostFilter {
   std::vector<float4> rows;  // [n_pairs][kFiltRows]
   std::vector<int2> ids;     // per pair: geom index of half A, half B
-  int n_sphere_pairs = 0, n_pairs = 0;
+  int end[kFiltClasses] = {0, 0, 0, 0};
   float r_scene = 0.0f;
 };
-// Per-geom coefficients of the error model.  u = 2^-24 (unit roundoff).  `scale` multiplies every error term.
+static bool inv3(const double a[3][3], double r[3][3]) {
+  const double c00 = a[1][1] * a[2][2] - a[1][2] * a[2][1], c01 = a[1][2] * a[2][0] - a[1][0] * a[2][2],
+               c02 = a[1][0] * a[2][1] - a[1][1] * a[2][0];
+  const double det = a[0][0] * c00 + a[0][1] * c01 + a[0][2] * c02;
+  if (!(fabs(det) > 0) || !std::isfinite(det)) return false;
+  const double id = 1.0 / det;
+  r[0][0] = c00 * id; r[0][1] = (a[0][2] * a[2][1] - a[0][1] * a[2][2]) * id; r[0][2] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) * id;
+  r[1][0] = c01 * id; r[1][1] = (a[0][0] * a[2][2] - a[0][2] * a[2][0]) * id; r[1][2] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) * id;
+  r[2][0] = c02 * id; r[2][1] = (a[0][1] * a[2][0] - a[0][0] * a[2][1]) * id; r[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * id;
+  return true;
+}
+// Per-geom coefficients of the error model (DESIGN.md "filter").  u = 2^-24 (unit roundoff).  `scale` multiplies
+// every rounding-error term (test hook; geometry terms such as the 1e-4 pull-back are not scaled).
 static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double scale) {
   HostFilter F;
   const double u = ldexp(1.0, -24);
-  std::vector<int> order;  // geoms with geometry, spheres first
-  int n_spheres = 0;
-  for (int t = 0; t <= 1; t++)
-    for (int i = 0; i < n_geoms; i++)
-      if (geoms[i].type == t) { order.push_back(i); n_spheres += t == 0; }
-  const int n = (int)order.size();
-  struct Per { double sigM, isigA, KA[3], T[3], KM, TM, EMw, EMc, rlin, rt; float k[8]; };
-  std::vector<Per> per(n ? n : 1);
+  const double s3 = 1.7320508075688772;
+  struct Per {
+    int geom, cls;
+    double KA[3], T[3];
+    float k[8];      // object-space constants (classes 1, 3)
+    float c[3];      // world point that inverseTransform maps to the object origin (classes 0, 2)
+    float wk[6];     // class 0: Wc, Ww, Wr;  class 2: Hc.xyz, Hw.xyz
+    float ew_c, ew_w;
+  };
+  std::vector<Per> per;
+  // pass 1: scene bound
   double r_scene = 0.0;
-  for (int k = 0; k < n; k++) {
-    const pt_static_geom& g = geoms[order[k]];
-    const float* A = g.inverseTransform;
-    const float* M = g.transform;
-    Per& q = per[k];
-    double MtM[3][3], AtA[3][3];
+  std::vector<double> sigM(n_geoms, 0.0);
+  for (int i = 0; i < n_geoms; i++) {
+    if (geoms[i].type > 1) continue;
+    const float* M = geoms[i].transform;
+    double MtM[3][3], tm2 = 0.0, lo, hi;
     for (int a = 0; a < 3; a++)
       for (int b = 0; b < 3; b++) {
-        MtM[a][b] = AtA[a][b] = 0.0;
-        for (int r = 0; r < 3; r++) { MtM[a][b] += (double)M[4 * r + a] * M[4 * r + b]; AtA[a][b] += (double)A[4 * r + a] * A[4 * r + b]; }
+        MtM[a][b] = 0.0;
+        for (int r = 0; r < 3; r++) MtM[a][b] += (double)M[4 * r + a] * M[4 * r + b];
       }
-    double lo, hi;
     sym3_eigen_range(MtM, &lo, &hi);
-    q.sigM = sqrt(fmax(hi, 0.0)) * 1.001;
-    sym3_eigen_range(AtA, &lo, &hi);
-    q.isigA = lo > 0 ? 1.001 / sqrt(lo) : INFINITY;  // 1 / sigma_min(A): bound on |d| / |A d|
-    q.KM = q.TM = q.EMw = q.EMc = q.rlin = q.rt = 0.0;
+    sigM[i] = sqrt(fmax(hi, 0.0)) * 1.001;
+    for (int r = 0; r < 3; r++) tm2 += (double)M[4 * r + 3] * M[4 * r + 3];
+    // bound on |p| over the geom's surface: |translation| + sigma_max(M) * (half diagonal of the unit cube)
+    r_scene = fmax(r_scene, sqrt(tm2) + sigM[i] * 0.8661);
+  }
+  F.r_scene = round_up(r_scene * 1.001);
+  const double Rs = (double)F.r_scene;
+  // pass 2: per-geom constants and class
+  for (int i = 0; i < n_geoms; i++) {
+    const pt_static_geom& g = geoms[i];
+    if (g.type > 1) continue;
+    const float* A = g.inverseTransform;
+    const float* M = g.transform;
+    Per q;
+    q.geom = i;
+    double A3[3][3], AtA[3][3], Ai[3][3];
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) {
+        A3[a][b] = (double)A[4 * a + b];
+        AtA[a][b] = 0.0;
+        for (int r = 0; r < 3; r++) AtA[a][b] += (double)A[4 * r + a] * A[4 * r + b];
+      }
+    double lmin, lmax;
+    sym3_eigen_range(AtA, &lmin, &lmax);
+    const double isigA = lmin > 0 ? 1.001 / sqrt(lmin) : INFINITY;  // 1 / sigma_min(A): bound on |d| / |A d|
+    double KM = 0, TM = 0, EMw = 0, EMc = 0, rlin = 0, rt = 0;
     for (int r = 0; r < 3; r++) {
       q.KA[r] = fabs((double)A[4 * r]) + fabs((double)A[4 * r + 1]) + fabs((double)A[4 * r + 2]);
       q.T[r] = fabs((double)A[4 * r + 3]);
     }
-    double tm2 = 0.0;
     for (int r = 0; r < 3; r++) {
       const double m0 = fabs((double)M[4 * r]), m1 = fabs((double)M[4 * r + 1]), m2 = fabs((double)M[4 * r + 2]);
-      q.KM = fmax(q.KM, m0 + m1 + m2);
-      q.TM = fmax(q.TM, fabs((double)M[4 * r + 3]));
-      tm2 += (double)M[4 * r + 3] * M[4 * r + 3];
-      q.EMw = fmax(q.EMw, m0 * q.KA[0] + m1 * q.KA[1] + m2 * q.KA[2]);
-      q.EMc = fmax(q.EMc, m0 * q.T[0] + m1 * q.T[1] + m2 * q.T[2]);
+      KM = fmax(KM, m0 + m1 + m2);
+      TM = fmax(TM, fabs((double)M[4 * r + 3]));
+      EMw = fmax(EMw, m0 * q.KA[0] + m1 * q.KA[1] + m2 * q.KA[2]);
+      EMc = fmax(EMc, m0 * q.T[0] + m1 * q.T[1] + m2 * q.T[2]);
       // residual of transform * inverseTransform - I (both are rounded binary32 matrices)
       double lin = 0.0;
       for (int c = 0; c < 4; c++) {
         double acc = c == 3 ? (double)M[4 * r + 3] : 0.0;
         for (int j = 0; j < 3; j++) acc += (double)M[4 * r + j] * A[4 * j + c];
-        if (c < 3) lin += fabs(acc - (c == r ? 1.0 : 0.0)); else q.rt = fmax(q.rt, fabs(acc));
+        if (c < 3) lin += fabs(acc - (c == r ? 1.0 : 0.0)); else rt = fmax(rt, fabs(acc));
       }
-      q.rlin = fmax(q.rlin, lin);
+      rlin = fmax(rlin, lin);
     }
-    // bound on |p| over the geom's surface: |translation| + sigma_max(M) * (half diagonal of the unit cube)
-    r_scene = fmax(r_scene, sqrt(tm2) + q.sigM * 0.8661);
-  }
-  F.r_scene = round_up(r_scene * 1.001);
-  const double Rs = (double)F.r_scene;
-  const double s3 = 1.7320508075688772;
-  for (int k = 0; k < n; k++) {
-    const pt_static_geom& g = geoms[order[k]];
-    Per& q = per[k];
     const double KAn = sqrt(q.KA[0] * q.KA[0] + q.KA[1] * q.KA[1] + q.KA[2] * q.KA[2]);
     const double Tn = sqrt(q.T[0] * q.T[0] + q.T[1] * q.T[1] + q.T[2] * q.T[2]);
     // world slack: pull-back of 1e-4 object units (NOT scaled: it is geometry, not rounding) + rounding of both
     // paths mapped through the forward transform + residual of M*A - I
-    double ew_w = scale * s3 * 2.0 * 2.25 * u * q.EMw;
-    double ew_c = scale * s3 * 2.0 * (9.0 * u * (q.EMc + 0.5 * q.KM) + 4.0 * u * (0.51 * q.KM + q.TM) + q.rlin * Rs + q.rt) +
-                  1.0001e-4 * q.isigA;
+    double ew_w = scale * s3 * 2.0 * 2.25 * u * EMw;
+    double ew_c = scale * s3 * 2.0 * (9.0 * u * (EMc + 0.5 * KM) + 4.0 * u * (0.51 * KM + TM) + rlin * Rs + rt) + 1.0001e-4 * isigA;
+    double objk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (g.type == 0) {
-      const double alpha = 6.0 * u * KAn * q.isigA;
-      ew_w += scale * 16.0 * u * q.isigA * KAn * 0.25;
-      ew_c += scale * 16.0 * u * q.isigA * Tn;
-      // k = R2c, R2w, R2r, Ew_c, Ew_w
-      q.k[0] = round_up(0.25 + scale * (28.0 * u * Tn + alpha)); q.k[1] = round_up(scale * 7.0 * u * KAn);
-      q.k[2] = round_up(scale * (64.0 * u + 4.0 * alpha)); q.k[3] = round_up(ew_c); q.k[4] = round_up(ew_w);
+      const double alpha = 6.0 * u * KAn * isigA;
+      ew_w += scale * 16.0 * u * isigA * KAn * 0.25;
+      ew_c += scale * 16.0 * u * isigA * Tn;
+      // R2c, R2w, R2r
+      objk[0] = 0.25 + scale * (28.0 * u * Tn + alpha); objk[1] = scale * 7.0 * u * KAn; objk[2] = scale * (64.0 * u + 4.0 * alpha);
+      q.k[0] = round_up(objk[0]); q.k[1] = round_up(objk[1]); q.k[2] = round_up(objk[2]);
     } else {
-      // k = hc.xyz, hw.xyz, Ew_c, Ew_w
+      // hc.xyz, hw.xyz
       for (int r = 0; r < 3; r++) {
-        q.k[r] = round_up(0.5 + scale * u * (32.0 * q.T[r] + 16.0));
-        q.k[3 + r] = round_up(scale * 13.2 * u * q.KA[r]);
+        objk[r] = 0.5 + scale * u * (32.0 * q.T[r] + 16.0);
+        objk[3 + r] = scale * 13.2 * u * q.KA[r];
+        q.k[r] = round_up(objk[r]); q.k[3 + r] = round_up(objk[3 + r]);
       }
-      q.k[6] = round_up(ew_c); q.k[7] = round_up(ew_w);
     }
+    q.ew_c = round_up(ew_c); q.ew_w = round_up(ew_w);
+    // ---- world-space classes: c = the world point that A maps to the object origin ----
+    q.cls = g.type == 0 ? 1 : 3;
+    if (inv3(A3, Ai)) {
+      double cw[3], dc = 0.0;
+      for (int r = 0; r < 3; r++) {
+        cw[r] = -(Ai[r][0] * A[3] + Ai[r][1] * A[7] + Ai[r][2] * A[11]);
+        q.c[r] = (float)cw[r];
+        dc = fmax(dc, fabs(cw[r] - (double)q.c[r]) + u * fabs(cw[r]));  // rounding of c to binary32 (+ its use)
+      }
+      const bool finite = std::isfinite(cw[0]) && std::isfinite(cw[1]) && std::isfinite(cw[2]);
+      if (g.type == 0 && finite && lmin > 0 && (lmax - lmin) <= 1e-5 * lmax) {
+        // |A x|^2 >= lmin |x|^2: a line within R_obj of the object origin is within R_obj / sqrt(lmin) of c;
+        // |ro|^2 <= lmax |o - c|^2
+        const double rad = 0.5 / sqrt(lmin);
+        q.wk[0] = round_up(objk[0] / lmin + 4.0 * rad * dc);
+        q.wk[1] = round_up(objk[1] / lmin);
+        q.wk[2] = round_up(objk[2] * (lmax / lmin) + scale * 32.0 * u);
+        q.cls = 0;
+      } else if (g.type == 1 && finite) {
+        // world AABB of the inflated cube { x : |A (x - c)|_j <= h_j }: half extents sum_j |Ai_ij| h_j
+        bool tight = true;
+        for (int r = 0; r < 3; r++) {
+          double dom = 0.0, sum = 0.0;
+          for (int j = 0; j < 3; j++) { dom = fmax(dom, fabs(Ai[r][j])); sum += fabs(Ai[r][j]); }
+          if (!((sum - dom) <= 1e-4 * dom)) tight = false;  // the AABB must hug the cube, else near misses fall back
+          q.wk[r] = round_up(fabs(Ai[r][0]) * objk[0] + fabs(Ai[r][1]) * objk[1] + fabs(Ai[r][2]) * objk[2] + 2.0 * dc);
+          q.wk[3 + r] = round_up(fabs(Ai[r][0]) * objk[3] + fabs(Ai[r][1]) * objk[4] + fabs(Ai[r][2]) * objk[5] + scale * 16.0 * u);
+        }
+        if (tight) q.cls = 2;
+      }
+    }
+    per.push_back(q);
   }
-  // pairs of one type; an odd geom out is paired with a copy of itself that can never be a candidate (-inf bounds)
-  std::vector<int> pa, pb;
-  auto make_pairs = [&](int first, int count) {
-    for (int k = 0; k < count; k += 2) { pa.push_back(first + k); pb.push_back(k + 1 < count ? first + k + 1 : -1); }
-  };
-  make_pairs(0, n_spheres);
-  F.n_sphere_pairs = (int)pa.size();
-  make_pairs(n_spheres, n - n_spheres);
-  F.n_pairs = (int)pa.size();
-  const int np = F.n_pairs ? F.n_pairs : 1;
-  F.rows.assign((size_t)kFiltRows * np, make_float4(0, 0, 0, 0));
-  F.ids.assign(np, make_int2(0, 0));
+  // pairs of one class; an odd geom out is paired with a copy of itself that can never be a candidate (-inf bounds)
   const float ninf = -INFINITY;
-  for (int p = 0; p < F.n_pairs; p++) {
-    const int ka = pa[p], kb = pb[p] < 0 ? pa[p] : pb[p];
-    const bool dummy = pb[p] < 0;
-    const pt_static_geom& ga = geoms[order[ka]];
-    const pt_static_geom& gb = geoms[order[kb]];
-    const float* A = ga.inverseTransform;
-    const float* B = gb.inverseTransform;
-    for (int r = 0; r < 3; r++) {
-      F.rows[(size_t)p * kFiltRows + 2 * r] = make_float4(A[4 * r], B[4 * r], A[4 * r + 1], B[4 * r + 1]);
-      F.rows[(size_t)p * kFiltRows + 2 * r + 1] = make_float4(A[4 * r + 2], B[4 * r + 2], A[4 * r + 3], B[4 * r + 3]);
+  for (int cls = 0; cls < kFiltClasses; cls++) {
+    std::vector<int> m;
+    for (int k = 0; k < (int)per.size(); k++) if (per[k].cls == cls) m.push_back(k);
+    for (size_t j = 0; j < m.size(); j += 2) {
+      const Per& x = per[m[j]];
+      const bool dummy = j + 1 >= m.size();
+      Per y = per[dummy ? m[j] : m[j + 1]];
+      if (dummy) {  // radius^2 / half extents -inf: discriminant -inf, tnear = +inf > tfar = -inf: proven miss
+        if (cls == 0) y.wk[0] = ninf;
+        if (cls == 1) y.k[0] = ninf;
+        if (cls == 2) y.wk[0] = y.wk[1] = y.wk[2] = ninf;
+        if (cls == 3) y.k[0] = y.k[1] = y.k[2] = ninf;
+      }
+      float4 r[kFiltRows];
+      for (int t = 0; t < kFiltRows; t++) r[t] = make_float4(0, 0, 0, 0);
+      if (cls == 0) {
+        r[0] = make_float4(x.c[0], y.c[0], x.c[1], y.c[1]);
+        r[1] = make_float4(x.c[2], y.c[2], x.wk[0], y.wk[0]);
+        r[2] = make_float4(x.wk[1], y.wk[1], x.wk[2], y.wk[2]);
+        r[3] = make_float4(x.ew_c, y.ew_c, x.ew_w, y.ew_w);
+      } else if (cls == 2) {
+        r[0] = make_float4(x.c[0], y.c[0], x.c[1], y.c[1]);
+        r[1] = make_float4(x.c[2], y.c[2], x.wk[0], y.wk[0]);
+        r[2] = make_float4(x.wk[1], y.wk[1], x.wk[2], y.wk[2]);
+        r[3] = make_float4(x.wk[3], y.wk[3], x.wk[4], y.wk[4]);
+        r[4] = make_float4(x.wk[5], y.wk[5], x.ew_c, y.ew_c);
+        r[5] = make_float4(x.ew_w, y.ew_w, 0, 0);
+      } else {
+        const float* A = geoms[x.geom].inverseTransform;
+        const float* B = geoms[y.geom].inverseTransform;
+        for (int t = 0; t < 3; t++) {
+          r[2 * t] = make_float4(A[4 * t], B[4 * t], A[4 * t + 1], B[4 * t + 1]);
+          r[2 * t + 1] = make_float4(A[4 * t + 2], B[4 * t + 2], A[4 * t + 3], B[4 * t + 3]);
+        }
+        if (cls == 1) {
+          r[6] = make_float4(x.k[0], y.k[0], x.k[1], y.k[1]);
+          r[7] = make_float4(x.k[2], y.k[2], x.ew_c, y.ew_c);
+          r[8] = make_float4(x.ew_w, y.ew_w, 0, 0);
+        } else {
+          r[6] = make_float4(x.k[0], y.k[0], x.k[1], y.k[1]);
+          r[7] = make_float4(x.k[2], y.k[2], x.k[3], y.k[3]);
+          r[8] = make_float4(x.k[4], y.k[4], x.k[5], y.k[5]);
+          r[9] = make_float4(x.ew_c, y.ew_c, x.ew_w, y.ew_w);
+        }
+      }
+      F.rows.insert(F.rows.end(), r, r + kFiltRows);
+      F.ids.push_back(make_int2(x.geom, y.geom));
     }
-    const float* x = per[ka].k;
-    float y[8];
-    for (int j = 0; j < 8; j++) y[j] = per[kb].k[j];
-    if (ga.type == 0) {
-      if (dummy) y[0] = ninf;  // radius^2 = -inf: the discriminant is -inf, a proven miss
-      F.rows[(size_t)p * kFiltRows + 6] = make_float4(x[0], y[0], x[1], y[1]);
-      F.rows[(size_t)p * kFiltRows + 7] = make_float4(x[2], y[2], x[3], y[3]);
-      F.rows[(size_t)p * kFiltRows + 8] = make_float4(x[4], y[4], 0, 0);
-    } else {
-      if (dummy) y[0] = y[1] = y[2] = ninf;  // half extents -inf: tnear = +inf > tfar = -inf, a proven miss
-      F.rows[(size_t)p * kFiltRows + 6] = make_float4(x[0], y[0], x[1], y[1]);
-      F.rows[(size_t)p * kFiltRows + 7] = make_float4(x[2], y[2], x[3], y[3]);
-      F.rows[(size_t)p * kFiltRows + 8] = make_float4(x[4], y[4], x[5], y[5]);
-      F.rows[(size_t)p * kFiltRows + 9] = make_float4(x[6], y[6], x[7], y[7]);
-    }
-    F.ids[p] = make_int2(order[ka], order[kb]);
+    F.end[cls] = (int)F.ids.size();
   }
+  if (F.ids.empty()) { F.rows.assign(kFiltRows, make_float4(0, 0, 0, 0)); F.ids.push_back(make_int2(0, 0)); }
   return F;
 }
 
@@ -296,7 +365,7 @@ static int setup_variant(pt_context* c, int slot) {
 
 static int upload_filter(pt_context* c) {
   const HostFilter F = build_filter(c->h_geoms.data(), (int)c->h_geoms.size(), (double)c->filter_scale);
-  if (F.n_pairs != c->filt.n_pairs || !c->d_filt) {
+  if (F.end[3] != c->filt.end[3] || !c->d_filt) {
     if (c->d_filt) CU(cudaFree(c->d_filt));
     if (c->d_filt_ids) CU(cudaFree(c->d_filt_ids));
     c->d_filt = nullptr; c->d_filt_ids = nullptr;
@@ -308,7 +377,8 @@ static int upload_filter(pt_context* c) {
   CU(cudaStreamSynchronize(c->stream));  // F dies at return
   c->filt.rows = c->d_filt;
   c->filt.ids = c->d_filt_ids;
-  c->filt.n_sphere_pairs = F.n_sphere_pairs; c->filt.n_pairs = F.n_pairs; c->filt.r_scene = F.r_scene;
+  for (int k = 0; k < kFiltClasses; k++) c->filt.end[k] = F.end[k];
+  c->filt.r_scene = F.r_scene;
   return PT_OK;
 }
 
@@ -372,11 +442,11 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
   c->g.meta = c->d_meta;
   c->cam = make_raygen(*cam, lens);
   c->W = (uint32_t)Wi; c->H = (uint32_t)Hi; c->npix = c->W * c->H;
-  const int cap = c->filt.n_pairs < 1 ? 1 : (c->filt.n_pairs < kMaxSmemPairs ? c->filt.n_pairs : kMaxSmemPairs);
-  if (cap != c->filt_cap || c->staged != (c->filt.n_pairs <= cap)) {
+  const int cap = c->filt.end[3] < 1 ? 1 : (c->filt.end[3] < kMaxSmemPairs ? c->filt.end[3] : kMaxSmemPairs);
+  if (cap != c->filt_cap || c->staged != (c->filt.end[3] <= cap)) {
     c->filt_cap = cap;
     c->geom_smem = filt_smem_bytes(cap);
-    c->staged = c->filt.n_pairs <= cap;
+    c->staged = c->filt.end[3] <= cap;
     c->smem_bytes = (c->staged ? c->geom_smem : 0) + stage_smem_bytes();  // k_bounce: filter geometry + survivor staging
     int rc;
     if ((rc = setup_variant<true, false>(c, 0))) return rc;

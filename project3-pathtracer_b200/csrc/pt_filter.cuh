@@ -34,24 +34,35 @@ namespace ptd {
 __device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// ---- filter geometry: PAIRS of geoms of one type, sphere pairs first, then cube pairs (MESH left out) ----
-// Blackwell's packed FFMA2 / FMUL2 / FADD2 execute two independent binary32 operations per issue slot, so the
+// ---- filter geometry: PAIRS of geoms of one class (MESH left out) ----
+// Blackwell's packed FFMA2 / FMUL2 / FADD2 take one issue slot for two independent binary32 operations, so the
 // filter tests two geoms at once: geom A in the low half, geom B in the high half of every float2.  An odd geom
 // out is paired with a copy of itself whose constants are -inf, which the tests below reject (proven miss).
-// 10 consecutive float4 per pair (every lane reads the same pair, so the shared-memory reads are broadcasts and one
-// pointer walks the whole list):
-//   q[2r]   = (A[r][0], B[r][0], A[r][1], B[r][1])    q[2r+1] = (A[r][2], B[r][2], A[r][3], B[r][3])   r = 0,1,2:
-//             rows x,y,z of inverseTransform, interleaved
-//   cube:   k0 = (hc.x | hc.y)  k1 = (hc.z | hw.x)  k2 = (hw.y | hw.z)  k3 = (Ew_c | Ew_w)   each "|" half = (A, B)
-//           half extent_i = hc_i + hw_i * w
-//   sphere: k0 = (R2c | R2w)    k1 = (R2r | Ew_c)   k2 = (Ew_w | -)                          radius^2 = R2c + R2w * w + R2r * |ro|^2
+//
+// Four classes, in this order; the first and third need no object-space transform at all:
+//   class 0  uniformly scaled spheres: the inflated unit sphere is a SPHERE in world space
+//            (centre c, radius^2 = Wc + Ww*w + Wr*|o-c|^2); 15 packed instructions per pair
+//   class 1  other spheres (ellipsoids): object-space test on (ro, rw) = inverseTransform * (o, d)
+//   class 2  cubes whose axes are the world axes (up to a slop far below the other slacks; rotations by multiples of
+//            90 degrees): slab test against the world AABB of the inflated cube (centre c, half extents Hc + Hw*w)
+//            with the ray's own 1/d, computed once per ray; 13 packed instructions per pair
+//   class 3  other cubes: object-space slab test
+// Records are 10 consecutive float4 per pair (every lane reads the same pair: shared-memory broadcasts, one pointer
+// walks the list).  "|" separates the two float2 halves of a float4, each half = (A, B):
+//   class 0: r0 = (c.x | c.y)  r1 = (c.z | Wc)  r2 = (Ww | Wr)  r3 = (Ew_c | Ew_w)
+//   class 2: r0 = (c.x | c.y)  r1 = (c.z | Hc.x)  r2 = (Hc.y | Hc.z)  r3 = (Hw.x | Hw.y)  r4 = (Hw.z | Ew_c)  r5 = (Ew_w | -)
+//   class 1, 3: r[2k] = (A[k][0], B[k][0], A[k][1], B[k][1])   r[2k+1] = (A[k][2], B[k][2], A[k][3], B[k][3])   k = 0,1,2:
+//               rows x,y,z of inverseTransform, interleaved; then
+//     class 3: r6 = (hc.x | hc.y)  r7 = (hc.z | hw.x)  r8 = (hw.y | hw.z)  r9 = (Ew_c | Ew_w)     half extent_i = hc_i + hw_i * w
+//     class 1: r6 = (R2c | R2w)    r7 = (R2r | Ew_c)   r8 = (Ew_w | -)                            radius^2 = R2c + R2w * w + R2r * |ro|^2
 //   world slack E_w = Ew_c + Ew_w * w
 constexpr int kFiltRows = 10;
+constexpr int kFiltClasses = 4;
 struct FiltSoA {  // in HBM
-  const float4* rows;  // [n_pairs][kFiltRows]
-  const int2* ids;     // pair -> (geom index of A, geom index of B)
-  int n_sphere_pairs, n_pairs;
-  float r_scene;       // bound on |p| over all surface points of the scene
+  const float4* rows;       // [n_pairs][kFiltRows]
+  const int2* ids;          // pair -> (geom index of A, geom index of B)
+  int end[kFiltClasses];    // end[k] = first pair index after class k (end[3] = number of pairs)
+  float r_scene;            // bound on |p| over all surface points of the scene
 };
 __host__ __device__ inline size_t filt_smem_bytes(int cap) { return (size_t)cap * kFiltRows * sizeof(float4); }
 // cooperative copy of pairs [first, first+count) into shared memory; caller synchronises
@@ -70,18 +81,24 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
 
 // per-ray constants of the scan
 struct ScanRay {
-  f2 ox, oy, oz, dx, dy, dz;  // the ray, broadcast to both halves
-  f2 w;                       // 4*max|o_j| + R_scene
-  float dl;                   // |d| rounded down (parameter -> world distance)
+  f3 o, d;       // the ray (each component is broadcast to both halves by the packed instructions)
+  float w;       // 4*max|o_j| + R_scene
+  float dl;      // |d| rounded down (parameter -> world distance)
+  float a;       // d.d
+  f3 id, od;     // 1/d (MUFU) and o/d: the ray's side of the world-space slab test (class 2)
 };
-__device__ __forceinline__ ScanRay make_scan_ray(f3 o, f3 d, float r_scene) {
+__device__ __forceinline__ ScanRay make_scan_ray(f3 o, f3 d, float r_scene, bool need_inverse) {
   ScanRay r;
-  r.ox = bc2(o.x); r.oy = bc2(o.y); r.oz = bc2(o.z);
-  r.dx = bc2(d.x); r.dy = bc2(d.y); r.dz = bc2(d.z);
+  r.o = o; r.d = d;
   const float omax = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
-  r.w = bc2(__fmaf_rn(4.0f, omax, r_scene));
-  const float d2 = __fmaf_rn(d.x, d.x, __fmaf_rn(d.y, d.y, d.z * d.z));
-  r.dl = mufu_sqrt(d2) * 0.99999905f;  // 1 - 2^-20: below |d| whatever the approximation error
+  r.w = __fmaf_rn(4.0f, omax, r_scene);
+  r.a = __fmaf_rn(d.x, d.x, __fmaf_rn(d.y, d.y, d.z * d.z));
+  r.dl = mufu_sqrt(r.a) * 0.99999905f;  // 1 - 2^-20: below |d| whatever the approximation error
+  r.id = mk(0, 0, 0); r.od = mk(0, 0, 0);
+  if (need_inverse) {
+    r.id = mk(mufu_rcp(d.x), mufu_rcp(d.y), mufu_rcp(d.z));
+    r.od = mk(o.x * r.id.x, o.y * r.id.y, o.z * r.id.z);
+  }
   return r;
 }
 
@@ -103,43 +120,82 @@ __device__ __forceinline__ void scan_take(ScanBest& b, float lo, int k) {
 // (ro, rw) is the parameter along the world ray
 #define PT_FILT_TRANSFORM(V, R)                                                                          \
   const float4 Q0 = (V)[0], Q1 = (V)[1], Q2 = (V)[2], Q3 = (V)[3], Q4 = (V)[4], Q5 = (V)[5];             \
-  const f2 rox = fma2(lo2(Q0), (R).ox, fma2(hi2(Q0), (R).oy, fma2(lo2(Q1), (R).oz, hi2(Q1))));           \
-  const f2 roy = fma2(lo2(Q2), (R).ox, fma2(hi2(Q2), (R).oy, fma2(lo2(Q3), (R).oz, hi2(Q3))));           \
-  const f2 roz = fma2(lo2(Q4), (R).ox, fma2(hi2(Q4), (R).oy, fma2(lo2(Q5), (R).oz, hi2(Q5))));           \
-  const f2 rwx = fma2(lo2(Q0), (R).dx, fma2(hi2(Q0), (R).dy, mul2(lo2(Q1), (R).dz)));                    \
-  const f2 rwy = fma2(lo2(Q2), (R).dx, fma2(hi2(Q2), (R).dy, mul2(lo2(Q3), (R).dz)));                    \
-  const f2 rwz = fma2(lo2(Q4), (R).dx, fma2(hi2(Q4), (R).dy, mul2(lo2(Q5), (R).dz)));
+  const f2 rox = fma2(lo2(Q0), bc2((R).o.x), fma2(hi2(Q0), bc2((R).o.y), fma2(lo2(Q1), bc2((R).o.z), hi2(Q1)))); \
+  const f2 roy = fma2(lo2(Q2), bc2((R).o.x), fma2(hi2(Q2), bc2((R).o.y), fma2(lo2(Q3), bc2((R).o.z), hi2(Q3)))); \
+  const f2 roz = fma2(lo2(Q4), bc2((R).o.x), fma2(hi2(Q4), bc2((R).o.y), fma2(lo2(Q5), bc2((R).o.z), hi2(Q5)))); \
+  const f2 rwx = fma2(lo2(Q0), bc2((R).d.x), fma2(hi2(Q0), bc2((R).d.y), mul2(lo2(Q1), bc2((R).d.z))));          \
+  const f2 rwy = fma2(lo2(Q2), bc2((R).d.x), fma2(hi2(Q2), bc2((R).d.y), mul2(lo2(Q3), bc2((R).d.z))));          \
+  const f2 rwz = fma2(lo2(Q4), bc2((R).d.x), fma2(hi2(Q4), bc2((R).d.y), mul2(lo2(Q5), bc2((R).d.z))));
 
-// Scan pairs [0, count) at `v` (pair indices base..base+count); the first n_sph of them are sphere pairs.
-// Every "miss" needs a comparison to come out TRUE, so a NaN anywhere keeps the geom as a candidate.
-__device__ __forceinline__ void filter_scan(const float4* v, int base, int n_sph, int count, const ScanRay& r,
-                                            ScanBest& best) {
-  int i = 0;
-  for (; i < n_sph; i++, v += kFiltRows) {
-    PT_FILT_TRANSFORM(v, r)
-    const float4 K0 = v[6], K1 = v[7];
-    const f2 a = fma2(rwx, rwx, fma2(rwy, rwy, mul2(rwz, rwz)));
-    const f2 b = fma2(rox, rwx, fma2(roy, rwy, mul2(roz, rwz)));
-    const f2 ro2 = fma2(rox, rox, fma2(roy, roy, mul2(roz, roz)));
-    const f2 R2 = fma2(lo2(K1), ro2, fma2(hi2(K0), r.w, lo2(K0)));
-    const f2 nc = __fadd2_rn(R2, neg2(ro2));      // -(|ro|^2 - R^2)
-    const f2 disc = fma2(a, nc, mul2(b, b));      // (ro.rw)^2 - |rw|^2 (|ro|^2 - R^2)
-    if (disc.x < 0.0f && disc.y < 0.0f) continue;  // both lines miss their inflated spheres
-    const f2 ew = fma2(lo2(v[8]), r.w, hi2(K1));
+// Scan pairs [first, last) (global pair indices); `v` points at the record of pair `first`; end[k] = first pair
+// index after class k.  Every "miss" needs a comparison to come out TRUE, so a NaN anywhere keeps the geom as a
+// candidate.
 #define PT_SPHERE_HALF(H, K)                                                                          \
   if (!(disc.H < 0.0f)) {                                                                             \
     const float sd = mufu_sqrt(disc.H), ia = mufu_rcp(a.H);                                           \
     if (!((sd - b.H) * ia < 0.0f)) /* else: the inflated sphere lies behind the origin */             \
       scan_take(best, __fmaf_rn((-b.H - sd) * ia, r.dl, -ew.H), K);                                   \
   }
-    PT_SPHERE_HALF(x, 2 * (base + i))
-    PT_SPHERE_HALF(y, 2 * (base + i) + 1)
-#undef PT_SPHERE_HALF
+#define PT_BOX_HALF(H, K)                                                                             \
+  {                                                                                                   \
+    const float tnear = fmaxf(fmaxf(nx.H, ny.H), nz.H), tfar = fminf(fminf(fx.H, fy.H), fz.H);        \
+    if (!(tnear > tfar || tfar < 0.0f)) /* else: misses the inflated box, or the box lies behind */   \
+      scan_take(best, __fmaf_rn(tnear, r.dl, -ew.H), K);                                              \
   }
-  for (; i < count; i++, v += kFiltRows) {
+__device__ __forceinline__ void filter_scan(const float4* v, int first, int last, const int end[kFiltClasses],
+                                            const ScanRay& r, ScanBest& best) {
+  int i = first;
+  const f2 w2 = bc2(r.w);
+  // ---- class 0: uniformly scaled spheres, world space ----
+  for (const int e = min(last, end[0]); i < e; i++, v += kFiltRows) {
+    const float4 C0 = v[0], C1 = v[1], C2 = v[2], C3 = v[3];
+    const f2 ocx = __fadd2_rn(bc2(r.o.x), neg2(lo2(C0))), ocy = __fadd2_rn(bc2(r.o.y), neg2(hi2(C0))),
+             ocz = __fadd2_rn(bc2(r.o.z), neg2(lo2(C1)));
+    const f2 b = fma2(ocx, bc2(r.d.x), fma2(ocy, bc2(r.d.y), mul2(ocz, bc2(r.d.z))));
+    const f2 oc2 = fma2(ocx, ocx, fma2(ocy, ocy, mul2(ocz, ocz)));
+    const f2 R2 = fma2(hi2(C2), oc2, fma2(lo2(C2), w2, hi2(C1)));
+    const f2 nc = __fadd2_rn(R2, neg2(oc2));              // -(|o-c|^2 - R^2)
+    const f2 disc = fma2(bc2(r.a), nc, mul2(b, b));       // (oc.d)^2 - |d|^2 (|oc|^2 - R^2)
+    if (disc.x < 0.0f && disc.y < 0.0f) continue;          // both lines miss their inflated spheres
+    const f2 ew = fma2(hi2(C3), w2, lo2(C3));
+    const f2 a = bc2(r.a);
+    PT_SPHERE_HALF(x, 2 * i)
+    PT_SPHERE_HALF(y, 2 * i + 1)
+  }
+  // ---- class 1: other spheres, object space ----
+  for (const int e = min(last, end[1]); i < e; i++, v += kFiltRows) {
+    PT_FILT_TRANSFORM(v, r)
+    const float4 K0 = v[6], K1 = v[7];
+    const f2 a = fma2(rwx, rwx, fma2(rwy, rwy, mul2(rwz, rwz)));
+    const f2 b = fma2(rox, rwx, fma2(roy, rwy, mul2(roz, rwz)));
+    const f2 ro2 = fma2(rox, rox, fma2(roy, roy, mul2(roz, roz)));
+    const f2 R2 = fma2(lo2(K1), ro2, fma2(hi2(K0), w2, lo2(K0)));
+    const f2 nc = __fadd2_rn(R2, neg2(ro2));      // -(|ro|^2 - R^2)
+    const f2 disc = fma2(a, nc, mul2(b, b));      // (ro.rw)^2 - |rw|^2 (|ro|^2 - R^2)
+    if (disc.x < 0.0f && disc.y < 0.0f) continue;  // both lines miss their inflated spheres
+    const f2 ew = fma2(lo2(v[8]), w2, hi2(K1));
+    PT_SPHERE_HALF(x, 2 * i)
+    PT_SPHERE_HALF(y, 2 * i + 1)
+  }
+  // ---- class 2: world-axis-aligned cubes, world space ----
+  for (const int e = min(last, end[2]); i < e; i++, v += kFiltRows) {
+    const float4 C0 = v[0], C1 = v[1], C2 = v[2], C3 = v[3], C4 = v[4];
+    // parameter of the slab centres, (c_i - o_i) / d_i, and half widths H_i / |d_i|
+    const f2 cx = fma2(lo2(C0), bc2(r.id.x), bc2(-r.od.x)), cy = fma2(hi2(C0), bc2(r.id.y), bc2(-r.od.y)),
+             cz = fma2(lo2(C1), bc2(r.id.z), bc2(-r.od.z));
+    const f2 hx = fma2(lo2(C3), w2, hi2(C1)), hy = fma2(hi2(C3), w2, lo2(C2)), hz = fma2(lo2(C4), w2, hi2(C2));
+    const f2 aix = bc2(fabsf(r.id.x)), aiy = bc2(fabsf(r.id.y)), aiz = bc2(fabsf(r.id.z));
+    const f2 nx = fma2(hx, neg2(aix), cx), ny = fma2(hy, neg2(aiy), cy), nz = fma2(hz, neg2(aiz), cz);
+    const f2 fx = fma2(hx, aix, cx), fy = fma2(hy, aiy, cy), fz = fma2(hz, aiz, cz);
+    const f2 ew = fma2(lo2(v[5]), w2, hi2(C4));
+    PT_BOX_HALF(x, 2 * i)
+    PT_BOX_HALF(y, 2 * i + 1)
+  }
+  // ---- class 3: other cubes, object space ----
+  for (const int e = min(last, end[3]); i < e; i++, v += kFiltRows) {
     PT_FILT_TRANSFORM(v, r)
     const float4 K0 = v[6], K1 = v[7], K2 = v[8], K3 = v[9];
-    const f2 hx = fma2(hi2(K1), r.w, lo2(K0)), hy = fma2(lo2(K2), r.w, hi2(K0)), hz = fma2(hi2(K2), r.w, lo2(K1));
+    const f2 hx = fma2(hi2(K1), w2, lo2(K0)), hy = fma2(lo2(K2), w2, hi2(K0)), hz = fma2(hi2(K2), w2, lo2(K1));
     const f2 ix = make_float2(mufu_rcp(rwx.x), mufu_rcp(rwx.y)), iy = make_float2(mufu_rcp(rwy.x), mufu_rcp(rwy.y)),
              iz = make_float2(mufu_rcp(rwz.x), mufu_rcp(rwz.y));
     const f2 cx = mul2(neg2(rox), ix), cy = mul2(neg2(roy), iy), cz = mul2(neg2(roz), iz);  // parameter of the slab centre
@@ -147,18 +203,13 @@ __device__ __forceinline__ void filter_scan(const float4* v, int base, int n_sph
     // fmaxf / fminf ignore: that slab then does not constrain (conservative)
     const f2 nx = fma2(hx, neg2(abs2(ix)), cx), ny = fma2(hy, neg2(abs2(iy)), cy), nz = fma2(hz, neg2(abs2(iz)), cz);
     const f2 fx = fma2(hx, abs2(ix), cx), fy = fma2(hy, abs2(iy), cy), fz = fma2(hz, abs2(iz), cz);
-    const f2 ew = fma2(hi2(K3), r.w, lo2(K3));
-#define PT_BOX_HALF(H, K)                                                                             \
-  {                                                                                                   \
-    const float tnear = fmaxf(fmaxf(nx.H, ny.H), nz.H), tfar = fminf(fminf(fx.H, fy.H), fz.H);        \
-    if (!(tnear > tfar || tfar < 0.0f)) /* else: misses the inflated box, or the box lies behind */   \
-      scan_take(best, __fmaf_rn(tnear, r.dl, -ew.H), K);                                              \
-  }
-    PT_BOX_HALF(x, 2 * (base + i))
-    PT_BOX_HALF(y, 2 * (base + i) + 1)
-#undef PT_BOX_HALF
+    const f2 ew = fma2(hi2(K3), w2, lo2(K3));
+    PT_BOX_HALF(x, 2 * i)
+    PT_BOX_HALF(y, 2 * i + 1)
   }
 }
+#undef PT_SPHERE_HALF
+#undef PT_BOX_HALF
 #undef PT_FILT_TRANSFORM
 
 // ---- the exact test of ONE geom: the reference's arithmetic, unfused, in its order (see pt_device.cuh) ----
@@ -232,7 +283,7 @@ __device__ __forceinline__ bool resolve_scan(const ScanBest& best, const FiltSoA
                                              f3 o, f3 d, Hit& h) {
   if (best.k1 < 0) return false;  // every geom is a proven miss
   const int gi = __ldg(reinterpret_cast<const int*>(f.ids) + best.k1);
-  const int type = best.k1 < 2 * f.n_sphere_pairs ? 0 : 1;
+  const int type = best.k1 < 2 * f.end[1] ? 0 : 1;
   float dist;
   f3 P;
   int ncode;

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const __grid_co
   // ---- filter geometry: staged once per CTA; scenes too large for shared memory are read through L1/L2 instead ----
   const float4* fs;
   if (STAGED) {
-    stage_filt(P.filt, 0, P.filt.n_pairs, reinterpret_cast<float4*>(smem_raw));
+    stage_filt(P.filt, 0, P.filt.end[3], reinterpret_cast<float4*>(smem_raw));
     fs = reinterpret_cast<const float4*>(smem_raw);
   } else {
     fs = P.filt.rows;
@@ -194,10 +194,10 @@ __global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const __grid_co
     Hit h;
     h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
     if (valid) {
-      const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene);
+      const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene, P.filt.end[2] > P.filt.end[1]);
       ScanBest best;
       scan_init(best);
-      filter_scan(fs, 0, P.filt.n_sphere_pairs, P.filt.n_pairs, ray, best);
+      filter_scan(fs, 0, P.filt.end[3], P.filt.end, ray, best);
       if (resolve_scan(best, P.filt, P.g, P.n_geoms, o, d, h)) atomicAdd(&P.ctrl->fallbacks, 1u);
     }
 
@@ -275,15 +275,15 @@ __global__ void __launch_bounds__(kTile) k_intersect_list(GeomSoA g, int n_geoms
     if (valid) closest_hit_exact(g, n_geoms, oo, dd, h);
   } else {
     const float4* fs = reinterpret_cast<const float4*>(smem_raw);
-    const ScanRay ray = make_scan_ray(oo, dd, filt.r_scene);
+    const ScanRay ray = make_scan_ray(oo, dd, filt.r_scene, filt.end[2] > filt.end[1]);
     ScanBest best;
     scan_init(best);
-    for (int c0 = 0; c0 < filt.n_pairs; c0 += filt_cap) {  // chunk loop: scenes larger than shared memory
-      const int cnt = min(filt_cap, filt.n_pairs - c0);
+    for (int c0 = 0; c0 < filt.end[3]; c0 += filt_cap) {  // chunk loop: scenes larger than shared memory
+      const int cnt = min(filt_cap, filt.end[3] - c0);
       __syncthreads();
       stage_filt(filt, c0, cnt, reinterpret_cast<float4*>(smem_raw));
       __syncthreads();
-      if (valid) filter_scan(fs, c0, max(0, min(cnt, filt.n_sphere_pairs - c0)), cnt, ray, best);
+      if (valid) filter_scan(fs, c0, c0 + cnt, filt.end, ray, best);
     }
     if (valid && resolve_scan(best, filt, g, n_geoms, oo, dd, h)) atomicAdd(fallbacks, 1ull);
   }

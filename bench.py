@@ -244,10 +244,15 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
-        traffic = None
+        n_bounce = max(1, (launches // args.steps) * DEPTH // (DEPTH + 1))  # launches per step = wavefronts * (DEPTH k_bounce + 1 k_accum_counts)
+        traffic, traffic_note = None, "no ncu capture on file"
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("k_bounce_dram_bytes_per_step")
+            tj = json.load(open(tpath))
+            # DRAM bytes of one average k_bounce launch = measured DRAM/algorithmic ratio of the captured launch x the
+            # algorithmic bytes of an average launch of this run
+            traffic = tj["dram_over_algorithmic"] * alg_bytes / n_bounce
+            traffic_note = "ncu dram read+write / algorithmic = %.3f on the captured launch (%s)" % (tj["dram_over_algorithmic"], tj["source"])
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -265,9 +270,12 @@ def main():
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_bounce",
-                         "algorithmic_bytes_per_step": alg_bytes,
-                         "note": "bytes = 96*(S-P) + 32*P over the %d k_bounce launches of a step" % (launches // args.steps)},
+                         "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "kernel": "k_bounce",
+                         "algorithmic_bytes_per_launch": alg_bytes / n_bounce, "launches_per_step": n_bounce,
+                         "avg_launch_us": 1e3 * ms_per_step / n_bounce,
+                         "note": "achieved = algorithmic bytes 96*(S-P) + 32*P of a step / CUDA-event time of the step; the step is "
+                                 "%d back-to-back k_bounce launches (99.9 %% of its GPU time, profiles/r01_launches_v9.csv), so this "
+                                 "is bytes per average launch / average launch duration" % n_bounce},
         }
         if world == 1 and not args.no_cpu_baseline:
             csegs, csecs, cthreads = cpu_oracle_rate()

@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <algorithm>
+#include <functional>
 #include <vector>
 
 using namespace ptd;
@@ -62,6 +64,10 @@ struct pt_context {
   int2* d_filt_ids = nullptr;
   FiltSoA filt{};
   int filt_cap = 0;
+  float4* d_bvh_nodes = nullptr;   // hierarchy over the filter tests (pt_bvh.cuh), scenes with >= kBvhMinGeoms geoms
+  float4* d_bvh_leaves = nullptr;
+  int2* d_bvh_meta = nullptr;
+  BvhSoA bvh{};
   float filter_scale = 1.0f;  // multiplies every error-model term of the filter (test hook; 1 = the shipped bounds)
   std::vector<pt_static_geom> h_geoms;  // host copy, to rebuild the filter when the scale changes
   GeomSoA g{};
@@ -81,13 +87,13 @@ struct pt_context {
   float* d_rgb = nullptr;      // staging for packed RGB
   uchar4* d_rgba8 = nullptr;   // staging for the 8-bit resolve
   int grid_blocks[4] = {0, 0, 0, 0};  // persistent grid per (FIRST,LAST) variant
-  bool staged = true;                 // filter geometry fits in shared memory
+  int mode = -1;                      // 0: linear scan over pairs staged in shared memory, 1: hierarchy (pt_bvh.cuh)
   size_t smem_bytes = 0;   // k_bounce: geometry + survivor staging
   size_t geom_smem = 0;    // filter geometry only (k_intersect_list)
 };
 
 static const uint64_t kDefaultWavefrontPaths = 16ull << 20;
-static const int kMaxSmemPairs = 256;   // 40 KB of shared memory for filter geometry at most; larger scenes are read through L1/L2
+static const int kMaxSmemPairs = 64;    // the linear scan serves scenes below kBvhMinGeoms geoms: at most 16 + 3 pairs, 3 KB of shared memory
 
 // ---------------------------------------------------------------- filter constants (pt_filter.cuh, DESIGN.md "filter")
 // largest eigenvalue of the symmetric 3x3 matrix S (cyclic Jacobi, binary64)
@@ -125,7 +131,12 @@ struct HostFilter {
   std::vector<int2> ids;     // per pair: geom index of half A, half B
   int end[kFiltClasses] = {0, 0, 0, 0};
   float r_scene = 0.0f;
+  // hierarchy (pt_bvh.cuh); empty when the scene is small enough for the pair scan
+  std::vector<float4> nodes, leaves;
+  std::vector<int2> leaf_meta;
+  float ew_c_max = 0.0f, ew_w_max = 0.0f;
 };
+static const int kBvhMinGeoms = 33;  // scenes with fewer geoms use the linear pair scan (shared memory, packed)
 static bool inv3(const double a[3][3], double r[3][3]) {
   const double c00 = a[1][1] * a[2][2] - a[1][2] * a[2][1], c01 = a[1][2] * a[2][0] - a[1][0] * a[2][2],
                c02 = a[1][0] * a[2][1] - a[1][1] * a[2][0];
@@ -150,6 +161,7 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
     float c[3];      // world point that inverseTransform maps to the object origin (classes 0, 2)
     float wk[6];     // class 0: Wc, Ww, Wr;  class 2: Hc.xyz, Hw.xyz
     float ew_c, ew_w;
+    double bc[3], bh[3], p1, p2;  // world AABB (centre, half extents) of the inflated shape at w = 0; pad coefficients
   };
   std::vector<Per> per;
   // pass 1: scene bound
@@ -243,6 +255,24 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
         dc = fmax(dc, fabs(cw[r] - (double)q.c[r]) + u * fabs(cw[r]));  // rounding of c to binary32 (+ its use)
       }
       const bool finite = std::isfinite(cw[0]) && std::isfinite(cw[1]) && std::isfinite(cw[2]);
+      // world AABB of the inflated shape { x : A (x - c) in inflated unit shape }, split into its value at w = 0 and
+      // the pad coefficients of P1*w + P2*D^2 (pt_bvh.cuh)
+      q.p1 = q.p2 = 0.0;
+      for (int r = 0; r < 3; r++) {
+        q.bc[r] = cw[r];
+        if (g.type == 1) {
+          q.bh[r] = fabs(Ai[r][0]) * objk[0] + fabs(Ai[r][1]) * objk[1] + fabs(Ai[r][2]) * objk[2] + 2.0 * dc;
+          q.p1 = fmax(q.p1, fabs(Ai[r][0]) * objk[3] + fabs(Ai[r][1]) * objk[4] + fabs(Ai[r][2]) * objk[5]);
+        } else {
+          // |x - c|_r <= |row r of A^-1| * sqrt(R2),  sqrt(R2) <= sqrt(R2c) + R2w w + R2r |ro|^2,  |ro|^2 <= lmax D^2
+          const double rown = sqrt(Ai[r][0] * Ai[r][0] + Ai[r][1] * Ai[r][1] + Ai[r][2] * Ai[r][2]);
+          q.bh[r] = sqrt(objk[0]) * rown * 1.000001 + 2.0 * dc;
+          q.p1 = fmax(q.p1, objk[1] * rown);
+          q.p2 = fmax(q.p2, objk[2] * lmax * rown * 1.001);
+        }
+      }
+      q.p1 += scale * 16.0 * u;  // rounding of the node slab test itself, in units of w
+      if (!finite) { q.bh[0] = q.bh[1] = q.bh[2] = INFINITY; q.bc[0] = q.bc[1] = q.bc[2] = 0.0; }
       if (g.type == 0 && finite && lmin > 0 && (lmax - lmin) <= 1e-5 * lmax) {
         // |A x|^2 >= lmin |x|^2: a line within R_obj of the object origin is within R_obj / sqrt(lmin) of c;
         // |ro|^2 <= lmax |o - c|^2
@@ -263,6 +293,9 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
         }
         if (tight) q.cls = 2;
       }
+    }
+    else {  // singular inverseTransform: cannot be bounded, always visited
+      q.bc[0] = q.bc[1] = q.bc[2] = 0.0; q.bh[0] = q.bh[1] = q.bh[2] = INFINITY; q.p1 = q.p2 = 0.0;
     }
     per.push_back(q);
   }
@@ -319,6 +352,81 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
     F.end[cls] = (int)F.ids.size();
   }
   if (F.ids.empty()) { F.rows.assign(kFiltRows, make_float4(0, 0, 0, 0)); F.ids.push_back(make_int2(0, 0)); }
+
+  // ---- hierarchy for scenes with many geoms: median split of the centroids along the widest axis, one geom per leaf ----
+  const int n = (int)per.size();
+  if (n >= kBvhMinGeoms) {
+    F.leaves.assign((size_t)n * kBvhLeafRows, make_float4(0, 0, 0, 0));
+    F.leaf_meta.resize(n);
+    for (int k = 0; k < n; k++) {
+      const Per& x = per[k];
+      float4* L = &F.leaves[(size_t)k * kBvhLeafRows];
+      const float* A = geoms[x.geom].inverseTransform;
+      if (x.cls == 0) {
+        L[0] = make_float4(x.c[0], x.c[1], x.c[2], x.wk[0]);
+        L[1] = make_float4(x.wk[1], x.wk[2], x.ew_c, x.ew_w);
+      } else if (x.cls == 2) {
+        L[0] = make_float4(x.c[0], x.c[1], x.c[2], x.ew_c);
+        L[1] = make_float4(x.wk[0], x.wk[1], x.wk[2], x.ew_w);
+        L[2] = make_float4(x.wk[3], x.wk[4], x.wk[5], 0);
+      } else {
+        for (int t = 0; t < 3; t++) L[t] = make_float4(A[4 * t], A[4 * t + 1], A[4 * t + 2], A[4 * t + 3]);
+        if (x.cls == 1) { L[3] = make_float4(x.k[0], x.k[1], x.k[2], x.ew_c); L[4] = make_float4(x.ew_w, 0, 0, 0); }
+        else { L[3] = make_float4(x.k[0], x.k[1], x.k[2], x.ew_c); L[4] = make_float4(x.k[3], x.k[4], x.k[5], x.ew_w); }
+      }
+      F.leaf_meta[k] = make_int2(x.cls, x.geom);
+      F.ew_c_max = fmaxf(F.ew_c_max, x.ew_c);
+      F.ew_w_max = fmaxf(F.ew_w_max, x.ew_w);
+    }
+    struct Box { double lo[3], hi[3], p1, p2; };
+    auto leaf_box = [&](int k) {
+      Box b;
+      for (int r = 0; r < 3; r++) { b.lo[r] = per[k].bc[r] - per[k].bh[r]; b.hi[r] = per[k].bc[r] + per[k].bh[r]; }
+      b.p1 = per[k].p1; b.p2 = per[k].p2;
+      return b;
+    };
+    auto merge = [](const Box& a, const Box& b) {
+      Box m;
+      for (int r = 0; r < 3; r++) { m.lo[r] = fmin(a.lo[r], b.lo[r]); m.hi[r] = fmax(a.hi[r], b.hi[r]); }
+      m.p1 = fmax(a.p1, b.p1); m.p2 = fmax(a.p2, b.p2);
+      return m;
+    };
+    auto down = [](double x) { float f = (float)x; if ((double)f > x) f = nextafterf(f, -INFINITY); return nextafterf(f, -INFINITY); };
+    auto up = [](double x) { float f = (float)x; if ((double)f < x) f = nextafterf(f, INFINITY); return nextafterf(f, INFINITY); };
+    std::vector<int> idx(n);
+    for (int k = 0; k < n; k++) idx[k] = k;
+    F.nodes.assign((size_t)(n - 1) * kBvhNodeRows, make_float4(0, 0, 0, 0));
+    int next_node = 0;
+    // returns the child reference (node index, or ~leaf) and the box of idx[first, last)
+    std::function<int(int, int, Box&)> build = [&](int first, int last, Box& box) -> int {
+      if (last - first == 1) { box = leaf_box(idx[first]); return ~idx[first]; }
+      double clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+      for (int i = first; i < last; i++)
+        for (int r = 0; r < 3; r++) { clo[r] = fmin(clo[r], per[idx[i]].bc[r]); chi[r] = fmax(chi[r], per[idx[i]].bc[r]); }
+      int axis = 0;
+      if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
+      if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
+      const int mid = first + (last - first) / 2;  // median split: depth = ceil(log2 n) <= kBvhStack
+      std::nth_element(idx.begin() + first, idx.begin() + mid, idx.begin() + last,
+                       [&](int a, int b) { return per[a].bc[axis] < per[b].bc[axis]; });
+      const int me = next_node++;
+      Box b0, b1;
+      const int c0 = build(first, mid, b0), c1 = build(mid, last, b1);
+      float4* N = &F.nodes[(size_t)me * kBvhNodeRows];
+      N[0] = make_float4(down(b0.lo[0]), down(b0.lo[1]), down(b0.lo[2]), up(b0.hi[0]));
+      N[1] = make_float4(up(b0.hi[1]), up(b0.hi[2]), down(b1.lo[0]), down(b1.lo[1]));
+      N[2] = make_float4(down(b1.lo[2]), up(b1.hi[0]), up(b1.hi[1]), up(b1.hi[2]));
+      N[3] = make_float4(up(b0.p1), up(b0.p2), up(b1.p1), up(b1.p2));
+      int ci[2] = {c0, c1};
+      float cf[2];
+      memcpy(cf, ci, sizeof(cf));
+      N[4] = make_float4(cf[0], cf[1], 0, 0);
+      box = merge(b0, b1);
+      return me;
+    };
+    Box root;
+    build(0, n, root);
+  }
   return F;
 }
 
@@ -349,18 +457,18 @@ static RaygenConsts make_raygen(const pt_camera_data& c, const pt_lens* lens) {
   return R;
 }
 
-template <bool F, bool L, bool S>
+template <bool F, bool L, bool B>
 static int setup_variant1(pt_context* c, int slot) {
-  CU(cudaFuncSetAttribute(k_bounce<F, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  CU(cudaFuncSetAttribute(k_bounce<F, L, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce<F, L, S>, kTile, c->smem_bytes));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce<F, L, B>, kTile, c->smem_bytes));
   if (per_sm < 1) { pt_set_error_("k_bounce does not fit on an SM"); return PT_ERR_CUDA; }
   c->grid_blocks[slot] = per_sm * c->sm_count;
   return PT_OK;
 }
 template <bool F, bool L>
 static int setup_variant(pt_context* c, int slot) {
-  return c->staged ? setup_variant1<F, L, true>(c, slot) : setup_variant1<F, L, false>(c, slot);
+  return c->mode ? setup_variant1<F, L, true>(c, slot) : setup_variant1<F, L, false>(c, slot);
 }
 
 static int upload_filter(pt_context* c) {
@@ -379,6 +487,22 @@ static int upload_filter(pt_context* c) {
   c->filt.ids = c->d_filt_ids;
   for (int k = 0; k < kFiltClasses; k++) c->filt.end[k] = F.end[k];
   c->filt.r_scene = F.r_scene;
+  // hierarchy
+  if (c->d_bvh_nodes) CU(cudaFree(c->d_bvh_nodes));
+  if (c->d_bvh_leaves) CU(cudaFree(c->d_bvh_leaves));
+  if (c->d_bvh_meta) CU(cudaFree(c->d_bvh_meta));
+  c->d_bvh_nodes = nullptr; c->d_bvh_leaves = nullptr; c->d_bvh_meta = nullptr;
+  c->bvh = BvhSoA{};
+  if (!F.leaf_meta.empty()) {
+    CU(cudaMalloc(&c->d_bvh_nodes, F.nodes.size() * sizeof(float4)));
+    CU(cudaMalloc(&c->d_bvh_leaves, F.leaves.size() * sizeof(float4)));
+    CU(cudaMalloc(&c->d_bvh_meta, F.leaf_meta.size() * sizeof(int2)));
+    CU(cudaMemcpy(c->d_bvh_nodes, F.nodes.data(), F.nodes.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_bvh_leaves, F.leaves.data(), F.leaves.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_bvh_meta, F.leaf_meta.data(), F.leaf_meta.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    c->bvh.nodes = c->d_bvh_nodes; c->bvh.leaves = c->d_bvh_leaves; c->bvh.leaf_meta = c->d_bvh_meta;
+    c->bvh.n_leaves = (int)F.leaf_meta.size(); c->bvh.ew_c_max = F.ew_c_max; c->bvh.ew_w_max = F.ew_w_max;
+  }
   return PT_OK;
 }
 
@@ -443,11 +567,12 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
   c->cam = make_raygen(*cam, lens);
   c->W = (uint32_t)Wi; c->H = (uint32_t)Hi; c->npix = c->W * c->H;
   const int cap = c->filt.end[3] < 1 ? 1 : (c->filt.end[3] < kMaxSmemPairs ? c->filt.end[3] : kMaxSmemPairs);
-  if (cap != c->filt_cap || c->staged != (c->filt.end[3] <= cap)) {
+  const int mode = c->bvh.n_leaves > 0 ? 1 : 0;  // fewer than kBvhMinGeoms geoms always fit: at most 16 pairs per class
+  if (cap != c->filt_cap || mode != c->mode) {
     c->filt_cap = cap;
     c->geom_smem = filt_smem_bytes(cap);
-    c->staged = c->filt.end[3] <= cap;
-    c->smem_bytes = (c->staged ? c->geom_smem : 0) + stage_smem_bytes();  // k_bounce: filter geometry + survivor staging
+    c->mode = mode;
+    c->smem_bytes = mode == 0 ? c->geom_smem : 0;  // k_bounce: filter geometry
     int rc;
     if ((rc = setup_variant<true, false>(c, 0))) return rc;
     if ((rc = setup_variant<true, true>(c, 1))) return rc;
@@ -480,7 +605,7 @@ extern "C" int pt_context_destroy(pt_context* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->d_rows); cudaFree(c->d_meta); cudaFree(c->d_mats); cudaFree(c->d_state); cudaFree(c->d_status);
-  cudaFree(c->d_filt); cudaFree(c->d_filt_ids);
+  cudaFree(c->d_filt); cudaFree(c->d_filt_ids); cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_leaves); cudaFree(c->d_bvh_meta);
   cudaFree(c->d_ctrl); cudaFree(c->d_live); cudaFree(c->d_accum); cudaFree(c->d_rgb); cudaFree(c->d_rgba8);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -565,7 +690,7 @@ static cudaError_t launch_bounce(pt_context* c, int slot, const BounceParams& P,
   uint32_t ctas = (n_upper + kTile - 1) / kTile;  // one unit per warp at least
   uint32_t grid = (uint32_t)c->grid_blocks[slot];
   if (ctas < grid) grid = ctas ? ctas : 1;
-  if (c->staged) k_bounce<F, L, true><<<grid, kTile, c->smem_bytes, c->stream>>>(P);
+  if (c->mode) k_bounce<F, L, true><<<grid, kTile, c->smem_bytes, c->stream>>>(P);
   else k_bounce<F, L, false><<<grid, kTile, c->smem_bytes, c->stream>>>(P);
   c->launches++;
   return cudaGetLastError();
@@ -591,6 +716,7 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
       P.accum = c->d_accum;
       P.g = c->g; P.n_geoms = c->n_geoms;
       P.filt = c->filt; P.filt_cap = c->filt_cap;
+      P.bvh = c->bvh;
       P.mats = c->d_mats;
       P.cam = c->cam;
       P.ctrl = c->d_ctrl;
@@ -742,7 +868,7 @@ extern "C" int pt_intersect_ex(pt_context* c, int mode, int n, const float* orig
   CU(cudaMemcpyAsync(ddr.p, direction, v * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemsetAsync(dfb.p, 0, sizeof(unsigned long long), c->stream));
   k_intersect_list<<<(n + kTile - 1) / kTile, kTile, c->geom_smem, c->stream>>>(
-      c->g, c->n_geoms, c->filt, c->filt_cap, mode, n, dor.p, ddr.p, did.p, dt.p, dpnt.p, dn.p, dfb.p);
+      c->g, c->n_geoms, c->filt, c->filt_cap, c->bvh, mode, n, dor.p, ddr.p, did.p, dt.p, dpnt.p, dn.p, dfb.p);
   c->launches++;
   CU(cudaGetLastError());
   unsigned long long fb = 0;

@@ -16,6 +16,7 @@
 #pragma once
 #include "pt_device.cuh"
 #include "pt_filter.cuh"
+#include "pt_bvh.cuh"
 
 namespace ptd {
 
@@ -114,8 +115,9 @@ struct BounceParams {
   float4* accum;                     // per-pixel radiance sums
   GeomSoA g;                         // per-geom rows in HBM (winner's normal / material lookup)
   int n_geoms;
-  FiltSoA filt;                      // filter geometry (pt_filter.cuh): sphere pairs first, then cube pairs
+  FiltSoA filt;                      // filter geometry (pt_filter.cuh): pairs of geoms, four classes
   int filt_cap;                      // pairs that fit in shared memory
+  BvhSoA bvh;                        // hierarchy over the same filter tests for scenes with many geoms (pt_bvh.cuh)
   const float4* mats;                // 4 float4 per material
   RaygenConsts cam;
   WfCtrl* ctrl;
@@ -147,19 +149,18 @@ __device__ __forceinline__ uint32_t atom_add_u32(uint32_t* p, uint32_t v) {  // 
   return old;
 }
 
-template <bool FIRST, bool LAST, bool STAGED>
-__global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const __grid_constant__ BounceParams P) {
+// BVH = false: few geoms (every BASELINE config but the 10k one): linear scan over the filter pairs staged in shared
+//              memory;  BVH = true: the hierarchy of pt_bvh.cuh, read through L1/L2
+template <bool FIRST, bool LAST, bool BVH>
+__global__ void __launch_bounds__(kTile, BVH ? 3 : PT_MIN_BLOCKS) k_bounce(const __grid_constant__ BounceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  // ---- filter geometry: staged once per CTA; scenes too large for shared memory are read through L1/L2 instead ----
-  const float4* fs;
-  if (STAGED) {
+  // ---- filter geometry: staged once per CTA (scenes with many geoms use the hierarchy instead) ----
+  const float4* const fs = reinterpret_cast<const float4*>(smem_raw);
+  if (!BVH) {
     stage_filt(P.filt, 0, P.filt.end[3], reinterpret_cast<float4*>(smem_raw));
-    fs = reinterpret_cast<const float4*>(smem_raw);
-  } else {
-    fs = P.filt.rows;
+    __syncthreads();  // the only CTA-wide barrier
   }
-  if (STAGED) __syncthreads();  // the only CTA-wide barrier
 
   const uint32_t n_in = FIRST ? P.n_first : P.ctrl->count[P.depth];
   if (FIRST && blockIdx.x == 0 && threadIdx.x == 0) P.ctrl->count[0] = n_in;
@@ -194,11 +195,19 @@ __global__ void __launch_bounds__(kTile, PT_MIN_BLOCKS) k_bounce(const __grid_co
     Hit h;
     h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
     if (valid) {
-      const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene, P.filt.end[2] > P.filt.end[1]);
       ScanBest best;
       scan_init(best);
-      filter_scan(fs, 0, P.filt.end[3], P.filt.end, ray, best);
-      if (resolve_scan(best, P.filt, P.g, P.n_geoms, o, d, h)) atomicAdd(&P.ctrl->fallbacks, 1u);
+      bool fell_back;
+      if (BVH) {
+        const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene, true);
+        bvh_traverse<false>(P.bvh, P.g, ray, o, d, best, h);
+        fell_back = resolve_bvh(best, P.bvh, P.g, P.filt.r_scene, o, d, h);
+      } else {
+        const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene, P.filt.end[2] > P.filt.end[1]);
+        filter_scan(fs, 0, P.filt.end[3], P.filt.end, ray, best);
+        fell_back = resolve_scan(best, P.filt, P.g, P.n_geoms, o, d, h);
+      }
+      if (fell_back) atomicAdd(&P.ctrl->fallbacks, 1u);
     }
 
     // a path survives this segment unless it left the scene or reached a light; the slot of the unit's survivors
@@ -261,7 +270,7 @@ __global__ void k_raygen_list(RaygenConsts C, uint64_t seed, int n, const uint32
   d[3 * i] = dd.x; d[3 * i + 1] = dd.y; d[3 * i + 2] = dd.z;
 }
 
-__global__ void __launch_bounds__(kTile) k_intersect_list(GeomSoA g, int n_geoms, FiltSoA filt, int filt_cap, int mode, int n,
+__global__ void __launch_bounds__(kTile) k_intersect_list(GeomSoA g, int n_geoms, FiltSoA filt, int filt_cap, BvhSoA bvh, int mode, int n,
                                                           const float* o, const float* d, int* id, float* t, float* p,
                                                           float* nrm, unsigned long long* fallbacks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -273,18 +282,22 @@ __global__ void __launch_bounds__(kTile) k_intersect_list(GeomSoA g, int n_geoms
   h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
   if (mode == 1) {  // the exact scan on its own (the specification; what the filtered path must reproduce)
     if (valid) closest_hit_exact(g, n_geoms, oo, dd, h);
+  } else if (bvh.n_leaves > 0) {  // many geoms: the hierarchy
+    if (valid) {
+      const ScanRay ray = make_scan_ray(oo, dd, filt.r_scene, true);
+      ScanBest best;
+      scan_init(best);
+      bvh_traverse<false>(bvh, g, ray, oo, dd, best, h);
+      if (resolve_bvh(best, bvh, g, filt.r_scene, oo, dd, h)) atomicAdd(fallbacks, 1ull);
+    }
   } else {
     const float4* fs = reinterpret_cast<const float4*>(smem_raw);
     const ScanRay ray = make_scan_ray(oo, dd, filt.r_scene, filt.end[2] > filt.end[1]);
     ScanBest best;
     scan_init(best);
-    for (int c0 = 0; c0 < filt.end[3]; c0 += filt_cap) {  // chunk loop: scenes larger than shared memory
-      const int cnt = min(filt_cap, filt.end[3] - c0);
-      __syncthreads();
-      stage_filt(filt, c0, cnt, reinterpret_cast<float4*>(smem_raw));
-      __syncthreads();
-      if (valid) filter_scan(fs, c0, c0 + cnt, filt.end, ray, best);
-    }
+    stage_filt(filt, 0, filt.end[3], reinterpret_cast<float4*>(smem_raw));
+    __syncthreads();
+    if (valid) filter_scan(fs, 0, filt.end[3], filt.end, ray, best);
     if (valid && resolve_scan(best, filt, g, n_geoms, oo, dd, h)) atomicAdd(fallbacks, 1ull);
   }
   if (!valid) return;

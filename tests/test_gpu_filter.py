@@ -53,3 +53,38 @@ def test_fallback_is_rare_on_the_sample_scene(pt, sample_scene):
         _, segs, _ = ctx.counters()
         fb = ctx.filter_stats()
     assert segs > 0 and fb / segs < 0.01, (fb, segs)
+
+
+@pytest.mark.parametrize("n_geoms,n_rays", [(200, 200_000), (10_000, 60_000)])
+def test_hierarchy_equals_exact_scan(pt, sample_scene, n_geoms, n_rays):
+    """scenes with many geoms go through the hierarchy (csrc/pt_bvh.cuh): same answers as the exact scan, bit for bit"""
+    from scenes_for_tests import random_scene
+    g = random_scene(pt, n_geoms, 21, extent=12.0, smin=0.05, smax=0.6)
+    with pt.Context(g, sample_scene["materials"], sample_scene["camera"]) as ctx:
+        for rname, (o, d) in ray_sets(pt, ctx, g, n_rays).items():
+            want = ctx.intersect(o, d, mode=pt.HIT_EXACT_SCAN)
+            for scale in (1.0, 0.25):
+                ctx.set_filter_scale(scale)
+                got = ctx.intersect(o, d, with_stats=True)
+                assert _same(got, want), (n_geoms, rname, scale)
+            ctx.set_filter_scale(1.0)
+
+
+def test_hierarchy_render_matches_oracle(pt, oracle, sample_scene):
+    """a whole render of a 600-geom scene (BASELINE config 3 in small): image and live counts identical to the oracle"""
+    from conftest import with_resolution
+    from scenes_for_tests import random_scene
+    g = random_scene(pt, 600, 33, extent=6.0, smin=0.2, smax=0.9)
+    rng = np.random.default_rng(5)
+    g["materialid"] = rng.integers(0, len(sample_scene["materials"]), len(g))
+    g["translation"] += np.float32(0)  # keep transforms as built
+    cam = with_resolution(sample_scene["camera"], 64, 64)
+    g = np.concatenate([g, sample_scene["geoms"]])  # walls and the light around the cloud
+    scn = oracle.make_scene(g, sample_scene["materials"], cam)
+    want_sum, want_live, _ = oracle.render(scn, 0, 2, 6, 9)
+    with pt.Context(g, sample_scene["materials"], cam) as c:
+        c.render(0, 2, 6, 9)
+        got = c.download_sum()
+        _, _, live = c.counters()
+    assert live[:6].tolist() == want_live.tolist()
+    assert (got.view(np.uint32) == want_sum.view(np.uint32)).all()

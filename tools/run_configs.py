@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Measure the BASELINE.json configs other than the headline on one GPU (device-timed, CUDA events on the render
+stream) and write one JSON line per config.  Scene files come from scenes/gen_scenes.py (reference text format) and
+go through the product's own loader (pt_scene_load).
+
+usage: python tools/run_configs.py [--frac F] [--out profiles/r01_configs.jsonl] [--png-dir gpurun_out]
+  --frac   fraction of each config's sample count to render (1 = the config as stated)"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pt = importlib.import_module("project3-pathtracer_b200")
+
+CONFIGS = [
+    # name, scene file (generated if missing), spp, depth, wavefront spp
+    ("config2_cornell_glass_dof_1080p", "scenes/cornell_glass_dof.txt", 4096, 12, 8),
+    ("config3_procedural_10k_1080p", "procedural:10000", 1024, 8, 8),
+    ("config4_sample_4k", "scenes/sample_4k.txt", 16384, 8, 4),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frac", type=float, default=1.0)
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_configs.jsonl"))
+    ap.add_argument("--png-dir", default=os.path.join(ROOT, "gpurun_out"))
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    lines = []
+    for name, path, spp_full, depth, wf_spp in CONFIGS:
+        if args.only and args.only not in name:
+            continue
+        if path.startswith("procedural:"):
+            n = int(path.split(":")[1])
+            tmp = os.path.join(tempfile.gettempdir(), "procedural_%d.txt" % n)
+            subprocess.check_call([sys.executable, os.path.join(ROOT, "scenes", "gen_scenes.py"), "--procedural", str(n), tmp])
+            path = tmp
+        else:
+            path = os.path.join(ROOT, path)
+        t0 = time.perf_counter()
+        sc = pt.Scene(path)
+        g, m, cam, lens = sc.frame(0)
+        t_load = time.perf_counter() - t0
+        spp = max(1, int(round(spp_full * args.frac)))
+        t0 = time.perf_counter()
+        with pt.Context(g, m, cam, lens=lens if lens[0] > 0 else None) as ctx:
+            t_ctx = time.perf_counter() - t0
+            ctx.set_wavefront_paths(sc.width * sc.height * wf_spp)
+            ctx.render(0, min(spp, wf_spp), depth, 565)  # warm-up
+            ctx.sync()
+            ctx.clear()
+            ctx.render(0, spp, depth, 565)
+            ms = ctx.last_render_ms()
+            paths, segs, live = ctx.counters()
+            fb = ctx.filter_stats()
+            img = ctx.download_mean(spp)
+        out_png = pt.save_image(img, sc.width, sc.height, os.path.join(args.png_dir, name + ".png"), 0, True)
+        line = {"config": name, "scene": os.path.basename(path), "geoms": int(sc.n_geoms), "resolution": [sc.width, sc.height],
+                "spp": spp, "spp_of_config": spp_full, "depth": depth, "paths": int(paths), "segments": int(segs),
+                "render_ms": ms, "Mseg_per_s": segs / ms / 1e3, "spp_per_s": spp / (ms * 1e-3),
+                "live_per_depth": [int(x) for x in live[:depth]], "exact_scan_fallbacks": int(fb),
+                "fallback_fraction": fb / max(1, segs), "scene_load_s": t_load, "context_create_s": t_ctx,
+                "mean_luminance": float(img.mean()), "image": os.path.basename(out_png)}
+        print(json.dumps(line), flush=True)
+        lines.append(line)
+    with open(args.out, "w") as f:
+        for ln in lines:
+            f.write(json.dumps(ln) + "\n")
+
+
+if __name__ == "__main__":
+    main()

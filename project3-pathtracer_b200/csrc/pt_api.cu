@@ -461,7 +461,7 @@ template <bool F, bool L, bool B>
 static int setup_variant1(pt_context* c, int slot) {
   CU(cudaFuncSetAttribute(k_bounce<F, L, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce<F, L, B>, kTile, c->smem_bytes));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce<F, L, B>, kBounceThreads, c->smem_bytes));
   if (per_sm < 1) { pt_set_error_("k_bounce does not fit on an SM"); return PT_ERR_CUDA; }
   c->grid_blocks[slot] = per_sm * c->sm_count;
   return PT_OK;
@@ -687,11 +687,11 @@ extern "C" int pt_clear(pt_context* c) {
 
 template <bool F, bool L>
 static cudaError_t launch_bounce(pt_context* c, int slot, const BounceParams& P, uint32_t n_upper) {
-  uint32_t ctas = (n_upper + kTile - 1) / kTile;  // one unit per warp at least
+  uint32_t ctas = (n_upper + kBounceThreads - 1) / kBounceThreads;  // one unit per warp at least
   uint32_t grid = (uint32_t)c->grid_blocks[slot];
   if (ctas < grid) grid = ctas ? ctas : 1;
-  if (c->mode) k_bounce<F, L, true><<<grid, kTile, c->smem_bytes, c->stream>>>(P);
-  else k_bounce<F, L, false><<<grid, kTile, c->smem_bytes, c->stream>>>(P);
+  if (c->mode) k_bounce<F, L, true><<<grid, kBounceThreads, c->smem_bytes, c->stream>>>(P);
+  else k_bounce<F, L, false><<<grid, kBounceThreads, c->smem_bytes, c->stream>>>(P);
   c->launches++;
   return cudaGetLastError();
 }

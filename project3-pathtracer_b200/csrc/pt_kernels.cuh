@@ -21,7 +21,11 @@
 namespace ptd {
 
 constexpr int kMaxDepth = 64;
-constexpr int kTile = 256;  // paths per tile = threads per CTA
+constexpr int kTile = 256;  // paths per tile = threads per CTA (list kernels, k_compact_u32)
+#ifndef PT_BOUNCE_THREADS
+#define PT_BOUNCE_THREADS 256  // threads per CTA of k_bounce (tuning knob together with PT_MIN_BLOCKS, see profiles/)
+#endif
+constexpr int kBounceThreads = PT_BOUNCE_THREADS;
 #ifndef PT_MIN_BLOCKS
 #define PT_MIN_BLOCKS 4  // resident CTAs per SM the register allocation aims for (tuning knob, see profiles/)
 #endif
@@ -152,7 +156,7 @@ __device__ __forceinline__ uint32_t atom_add_u32(uint32_t* p, uint32_t v) {  // 
 // BVH = false: few geoms (every BASELINE config but the 10k one): linear scan over the filter pairs staged in shared
 //              memory;  BVH = true: the hierarchy of pt_bvh.cuh, read through L1/L2
 template <bool FIRST, bool LAST, bool BVH>
-__global__ void __launch_bounds__(kTile, BVH ? 3 : PT_MIN_BLOCKS) k_bounce(const __grid_constant__ BounceParams P) {
+__global__ void __launch_bounds__(kBounceThreads, BVH ? (3 * 256 / kBounceThreads) : PT_MIN_BLOCKS) k_bounce(const __grid_constant__ BounceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   // ---- filter geometry: staged once per CTA (scenes with many geoms use the hierarchy instead) ----

@@ -76,10 +76,8 @@ struct pt_context {
   // wavefront
   uint64_t wf_capacity = 0;  // paths
   float4* d_state = nullptr; // 6 arrays of wf_capacity float4: o0 d0 t0 o1 d1 t1
-  uint64_t* d_status = nullptr;
   WfCtrl* d_ctrl = nullptr;
   unsigned long long* d_live = nullptr;  // kMaxDepth totals
-  uint32_t epoch = 0;
   uint64_t paths_total = 0;
   uint64_t launches = 0;     // kernels of this library launched on behalf of this context
   // image
@@ -590,12 +588,8 @@ static int alloc_wavefront(pt_context* c, uint64_t max_paths) {
   if (cap > 0xFFFFFF00ull) { pt_set_error_("wavefront of %llu paths exceeds 2^32", (unsigned long long)cap); return PT_ERR_INVALID; }
   if (cap == c->wf_capacity) return PT_OK;
   if (c->d_state) CU(cudaFree(c->d_state));
-  if (c->d_status) CU(cudaFree(c->d_status));
-  c->d_state = nullptr; c->d_status = nullptr; c->wf_capacity = 0;
+  c->d_state = nullptr; c->wf_capacity = 0;
   CU(cudaMalloc(&c->d_state, 6 * cap * sizeof(float4)));
-  const uint64_t tiles = (cap + kUnit - 1) / kUnit;  // one status word per 32-path unit
-  CU(cudaMalloc(&c->d_status, tiles * sizeof(uint64_t)));
-  CU(cudaMemsetAsync(c->d_status, 0, tiles * sizeof(uint64_t), c->stream));
   c->wf_capacity = cap;
   return PT_OK;
 }
@@ -604,7 +598,7 @@ extern "C" int pt_context_destroy(pt_context* c) {
   if (!c) return PT_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_rows); cudaFree(c->d_meta); cudaFree(c->d_mats); cudaFree(c->d_state); cudaFree(c->d_status);
+  cudaFree(c->d_rows); cudaFree(c->d_meta); cudaFree(c->d_mats); cudaFree(c->d_state);
   cudaFree(c->d_filt); cudaFree(c->d_filt_ids); cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_leaves); cudaFree(c->d_bvh_meta);
   cudaFree(c->d_ctrl); cudaFree(c->d_live); cudaFree(c->d_accum); cudaFree(c->d_rgb); cudaFree(c->d_rgba8);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -720,9 +714,6 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
       P.mats = c->d_mats;
       P.cam = c->cam;
       P.ctrl = c->d_ctrl;
-      P.status = c->d_status;
-      P.epoch = (++c->epoch) & 0x3FFFFFFFu;
-      if (P.epoch == 0) P.epoch = (++c->epoch) & 0x3FFFFFFFu;
       P.depth = (uint32_t)depth;
       P.seed = seed;
       P.first_sample = first_sample + s0;

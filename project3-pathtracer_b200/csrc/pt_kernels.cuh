@@ -125,8 +125,7 @@ struct BounceParams {
   const float4* mats;                // 4 float4 per material
   RaygenConsts cam;
   WfCtrl* ctrl;
-  uint64_t* status;
-  uint32_t epoch, depth;
+  uint32_t depth;
   uint64_t seed;
   uint32_t first_sample, n_first;    // FIRST only: paths to generate = npix * samples in this wavefront
 };
@@ -153,6 +152,13 @@ __device__ __forceinline__ uint32_t atom_add_u32(uint32_t* p, uint32_t v) {  // 
   return old;
 }
 
+// A ticket is kTicketUnits consecutive units: the ticket counter sees one atomic per 128 paths (atomics on one address
+// serialise in L2 at about one per clock; a ticket per unit put the counter at a third of that limit).
+#ifndef PT_TICKET_UNITS
+#define PT_TICKET_UNITS 4
+#endif
+constexpr uint32_t kTicketUnits = PT_TICKET_UNITS;
+
 // BVH = false: few geoms (every BASELINE config but the 10k one): linear scan over the filter pairs staged in shared
 //              memory;  BVH = true: the hierarchy of pt_bvh.cuh, read through L1/L2
 template <bool FIRST, bool LAST, bool BVH>
@@ -175,9 +181,11 @@ __global__ void __launch_bounds__(kBounceThreads, BVH ? (3 * 256 / kBounceThread
   if (lane == 0) next_raw = atom_add_u32(ticket, 1u);
 
   for (;;) {
-    const uint32_t unit = __shfl_sync(0xffffffffu, next_raw, 0);
-    if (unit >= n_units) break;
-    if (lane == 0) next_raw = atom_add_u32(ticket, 1u);  // consumed in the next iteration: its latency is hidden
+    const uint32_t unit0 = __shfl_sync(0xffffffffu, next_raw, 0) * kTicketUnits;
+    if (unit0 >= n_units) break;
+    if (lane == 0) next_raw = atom_add_u32(ticket, 1u);  // consumed after this ticket's units: its latency is hidden
+#pragma unroll 1
+    for (uint32_t unit = unit0; unit < min(unit0 + kTicketUnits, n_units); unit++) {
     const uint32_t idx = unit * kUnit + lane;
     const bool valid = idx < n_in;
 
@@ -252,6 +260,7 @@ __global__ void __launch_bounds__(kBounceThreads, BVH ? (3 * 256 / kBounceThread
         __stcs(P.out_d + slot, make_float4(d.x, d.y, d.z, __uint_as_float(sample)));
         __stcs(P.out_t + slot, make_float4(thr.x, thr.y, thr.z, 0.0f));
       }
+    }
     }
   }
 }

@@ -103,9 +103,11 @@ __device__ __forceinline__ float child_entry(float3 bmin, float3 bmax, float p1,
   const float mz = fmaxf(fabsf(bmin.z - r.o.z), fabsf(bmax.z - r.o.z));
   const float D2 = __fmaf_rn(mx, mx, __fmaf_rn(my, my, mz * mz)) * 1.000001f;
   const float pad = __fmaf_rn(p2, D2, p1 * r.w);
-  const float ax = __fmaf_rn(bmin.x - pad, r.id.x, -r.od.x), bx = __fmaf_rn(bmax.x + pad, r.id.x, -r.od.x);
-  const float ay = __fmaf_rn(bmin.y - pad, r.id.y, -r.od.y), by = __fmaf_rn(bmax.y + pad, r.id.y, -r.od.y);
-  const float az = __fmaf_rn(bmin.z - pad, r.id.z, -r.od.z), bz = __fmaf_rn(bmax.z + pad, r.id.z, -r.od.z);
+  // (b - o) * (1/d), subtraction first: with d_i = 0 the two planes give -inf / +inf (origin inside the slab: no
+  // constraint) or the same infinity twice (outside: miss); b/d - o/d would turn the first case into inf - inf
+  const float ax = ((bmin.x - pad) - r.o.x) * r.id.x, bx = ((bmax.x + pad) - r.o.x) * r.id.x;
+  const float ay = ((bmin.y - pad) - r.o.y) * r.id.y, by = ((bmax.y + pad) - r.o.y) * r.id.y;
+  const float az = ((bmin.z - pad) - r.o.z) * r.id.z, bz = ((bmax.z + pad) - r.o.z) * r.id.z;
   // rounding of the six parameters (a few ulp of |box - o| / |d|) is covered by the 16u*w in P1
   const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
   const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));

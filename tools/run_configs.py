@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_configs.jsonl"))
     ap.add_argument("--png-dir", default=os.path.join(ROOT, "gpurun_out"))
     ap.add_argument("--only", default="")
+    ap.add_argument("--filter-scale", type=float, default=1.0, help="experiment: scale of the filter's rounding-error bounds")
     args = ap.parse_args()
     lines = []
     for name, path, spp_full, depth, wf_spp in CONFIGS:
@@ -55,6 +56,8 @@ def main():
         with pt.Context(g, m, cam, lens=lens if lens[0] > 0 else None) as ctx:
             t_ctx = time.perf_counter() - t0
             ctx.set_wavefront_paths(sc.width * sc.height * wf_spp)
+            if args.filter_scale != 1.0:
+                ctx.set_filter_scale(args.filter_scale)
             ctx.render(0, min(spp, wf_spp), depth, 565)  # warm-up
             ctx.sync()
             ctx.clear()

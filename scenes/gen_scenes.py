@@ -116,6 +116,22 @@ def cornell_glass_dof():
     return scene_text(mats, cam, objs, lens=(0.12, 13.0))
 
 
+def sample_animated(n_frames=3, res=(800, 800), iterations=5000):
+    """the sample scene with a bouncing sphere, a sliding camera and one per-frame array for every object
+    (the reference's loader reads `frame k` blocks into per-frame arrays, src/scene.cpp:82-128, and its main loop
+    advances through them, src/main.cpp:147-157)"""
+    objs = []
+    for i, (t, m, tr, ro, sc) in enumerate(SAMPLE_OBJECTS):
+        frames = []
+        for k in range(n_frames):
+            tk = tr if i != 5 else (tr[0] + 0.5 * k, tr[1] + 1.2 * k, tr[2])   # object 5: the big sphere moves
+            frames.append((tk, ro, sc))
+        objs.append((t, m, frames))
+    cam = dict(SAMPLE_CAMERA, res=res, iterations=iterations,
+               frames=[((0.4 * k, 4.5, 12), (-0.03 * k, 0, -1), (0, 1, 0)) for k in range(n_frames)])
+    return scene_text(SAMPLE_MATERIALS, cam, objs)
+
+
 def procedural(n, seed=565, res=(1920, 1080), iterations=1024):
     rng = np.random.default_rng(seed)
     colours = [(.8, .8, .8), (.63, .06, .04), (.15, .48, .09), (.2, .3, .8), (.8, .7, .2), (.6, .2, .7)]

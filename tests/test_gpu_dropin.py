@@ -104,3 +104,30 @@ def test_cornell_scene_file_end_to_end(pt, oracle):
         _, segs, glive = c.counters()
     assert glive[:12].tolist() == live.tolist() and same_bits(got, want)
     assert live[11] > 0.05 * live[0], "closed box: paths stay alive"
+
+
+def test_headless_driver_renders_every_frame_of_an_animation(pt, oracle, tmp_path):
+    """no frame= token: the driver walks all frames (src/main.cpp:147-157), re-uploading the per-frame transforms and
+    camera and clearing the image in between; every saved frame equals the oracle's render of that frame"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "scenes"))
+    import gen_scenes
+    p = tmp_path / "anim.txt"
+    p.write_text(gen_scenes.sample_animated(3, (96, 64), 2))
+    out = subprocess.check_output([os.path.join(ROOT, "project3-pathtracer_b200", "pt_render"), "scene=%s" % p,
+                                   "depth=5", "seed=3", "out=%s" % (tmp_path / "a.png"), "json=1"], text=True)
+    infos = [json.loads(x) for x in out.strip().splitlines()]
+    assert [i["frame"] for i in infos] == [0, 1, 2]
+    s = pt.Scene(p)
+    assert s.n_frames == 3
+    imgs = []
+    for k, info in enumerate(infos):
+        assert info["file"].endswith("a.%d.png" % k)
+        g, m, cam, lens = s.frame(k)
+        want_sum, live, _ = oracle.render(oracle.make_scene(g, m, cam, lens), 0, 2, 5, 3)
+        assert info["segments"] == int(live.sum())
+        want8 = pt.image_to_rgb8(want_sum / np.float32(2), 96, 64)
+        got8 = np.asarray(Image.open(info["file"]).convert("RGB"))
+        assert (got8 == want8).all()  # two samples per pixel: the sum is order-independent, so bits match
+        imgs.append(got8)
+    assert (imgs[0] != imgs[1]).any() and (imgs[1] != imgs[2]).any()

@@ -110,3 +110,25 @@ def test_tiny_wavefront_and_deep_paths(pt, oracle, sample_scene):
         _, _, live = ctx.counters()
     assert live[:40].tolist() == want_live.tolist()
     assert (_bits(got) == _bits(want)).all()
+
+
+def test_update_scene_switches_between_pair_scan_and_hierarchy(pt, sample_scene):
+    """pt_update_scene (next animation frame) may change the number of geoms across the hierarchy threshold"""
+    cam = with_resolution(sample_scene["camera"], 64, 64)
+    small = sample_scene["geoms"]
+    big = np.concatenate([random_scene(pt, 80, 77, extent=4.0, smin=0.3, smax=1.0), small])
+    big["materialid"][:80] = 1
+
+    def fresh(g):
+        with pt.Context(g, sample_scene["materials"], cam) as c:
+            c.render(0, 2, 6, 13)
+            return c.download_sum(), c.counters()[2][:6].tolist()
+
+    want_small, want_big = fresh(small), fresh(big)
+    with pt.Context(small, sample_scene["materials"], cam) as ctx:
+        for g, want in ((big, want_big), (small, want_small), (big, want_big)):
+            ctx.update_scene(g, sample_scene["materials"], cam)
+            ctx.clear()
+            ctx.render(0, 2, 6, 13)
+            assert ctx.counters()[2][:6].tolist() == want[1]
+            assert (_bits(ctx.download_sum()) == _bits(want[0])).all()

@@ -36,7 +36,7 @@ import numpy as np  # noqa: E402
 METRIC = "path segments per second, reference sample scene 800x800, 5000 spp, 8 bounces"
 UNIT = "Mseg/s"
 RES, SPP, DEPTH, SEED = 800, 5000, 8, 565
-CPU_SPP = 16  # bounded CPU sample: 16 spp of the 800x800 frame (about 20 s of CPU work)
+CPU_SPP = 32  # bounded CPU sample: 32 spp of the 800x800 frame (about 20 s of CPU work over the host cores)
 WF_SPP = 50  # samples of the frame per wavefront: 32 M paths, 3.07 GB of path state (>> 126 MB L2); 100 wavefronts per step
 
 

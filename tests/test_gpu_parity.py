@@ -211,3 +211,33 @@ def test_compaction_is_a_stable_partition(pt, n):
 def test_single_guard_ieee_math_exhaustive(pt):
     """sqrt_ieee / rcp_ieee / inv_sqrt_ieee (csrc/pt_device.cuh) equal sqrtf, 1/x, 1/sqrtf(x) on all 2^32 inputs"""
     assert pt.selftest_math() == (0, 0, 0)
+
+
+def test_full_size_config_properties(pt, oracle, sample_scene):
+    """BASELINE configs[1] at FULL size (800x800, 5000 spp, 8 bounces) through size-independent properties:
+    splitting the samples in two renders adds up (live counts exactly, image up to float summation order), the
+    wavefront size does not matter, paths only ever die, and no pixel exceeds the light's radiance"""
+    g, m, cam = sample_scene["geoms"], sample_scene["materials"], sample_scene["camera"]
+    spp, depth, seed = 5000, 8, 565
+    with pt.Context(g, m, cam) as ctx:
+        ctx.set_wavefront_paths(800 * 800 * 50)
+        ctx.render(0, spp, depth, seed)
+        whole = ctx.download_sum()
+        paths, segs, live = ctx.counters()
+        assert paths == 800 * 800 * spp and segs == int(live[:depth].sum())
+        assert all(live[i + 1] <= live[i] for i in range(depth - 1)) and live[depth] == 0
+        ctx.clear()
+        ctx.set_wavefront_paths(800 * 800 * 16)  # another wavefront size, and the samples in two calls
+        ctx.render(0, 2000, depth, seed)
+        _, _, live_a = ctx.counters()
+        ctx.render(2000, 3000, depth, seed)
+        parts = ctx.download_sum()
+        _, _, live_ab = ctx.counters()
+    assert live_ab[:depth].tolist() == live[:depth].tolist() and (live_a[:depth] < live[:depth]).all()
+    assert np.allclose(parts, whole, rtol=2e-5, atol=1e-3)  # same samples, different atomic summation order
+    mean = whole / np.float32(spp)
+    assert mean.max() <= 15.0 * 1.0001 and mean.min() >= 0.0  # the only emitter has emittance 15, albedos <= 1
+    # mean luminance against the CPU oracle on the same frame (8 of the 5000 samples per pixel: 5.1 M paths, whose
+    # mean is within a few 1e-3 of the converged one)
+    want8, _, _ = oracle.render(oracle.make_scene(g, m, cam), 0, 8, depth, seed)
+    assert abs(float(mean.mean()) - float(want8.mean()) / 8.0) < 0.01 * float(mean.mean())

@@ -59,6 +59,7 @@ struct pt_context {
   int n_geoms = 0, n_mats = 0;
   float4* d_rows = nullptr;  // 6 arrays of n_geoms float4
   int2* d_meta = nullptr;
+  float4* d_normals = nullptr;  // kNormalRows float4 per geom: face normals + sphere centre (k_normal_table)
   float4* d_mats = nullptr;
   float4* d_filt = nullptr;   // kFiltRows arrays of n_pairs float4: filter geometry (pt_filter.cuh)
   int2* d_filt_ids = nullptr;
@@ -543,9 +544,11 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
   if (n_geoms != c->n_geoms) {
     if (c->d_rows) CU(cudaFree(c->d_rows));
     if (c->d_meta) CU(cudaFree(c->d_meta));
-    c->d_rows = nullptr; c->d_meta = nullptr;
+    if (c->d_normals) CU(cudaFree(c->d_normals));
+    c->d_rows = nullptr; c->d_meta = nullptr; c->d_normals = nullptr;
     CU(cudaMalloc(&c->d_rows, rows.size() * sizeof(float4)));
     CU(cudaMalloc(&c->d_meta, meta.size() * sizeof(int2)));
+    CU(cudaMalloc(&c->d_normals, (size_t)n_geoms * kNormalRows * sizeof(float4)));
   }
   if (n_mats != c->n_mats) {
     if (c->d_mats) CU(cudaFree(c->d_mats));
@@ -562,6 +565,8 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
   c->g.fwd0 = c->d_rows + 3 * (size_t)n_geoms; c->g.fwd1 = c->d_rows + 4 * (size_t)n_geoms;
   c->g.fwd2 = c->d_rows + 5 * (size_t)n_geoms;
   c->g.meta = c->d_meta;
+  k_normal_table<<<(n_geoms + 127) / 128, 128, 0, c->stream>>>(c->g, n_geoms, c->d_normals);
+  CU(cudaGetLastError());
   c->cam = make_raygen(*cam, lens);
   c->W = (uint32_t)Wi; c->H = (uint32_t)Hi; c->npix = c->W * c->H;
   const int cap = c->filt.end[3] < 1 ? 1 : (c->filt.end[3] < kMaxSmemPairs ? c->filt.end[3] : kMaxSmemPairs);
@@ -598,7 +603,7 @@ extern "C" int pt_context_destroy(pt_context* c) {
   if (!c) return PT_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_rows); cudaFree(c->d_meta); cudaFree(c->d_mats); cudaFree(c->d_state);
+  cudaFree(c->d_rows); cudaFree(c->d_meta); cudaFree(c->d_normals); cudaFree(c->d_mats); cudaFree(c->d_state);
   cudaFree(c->d_filt); cudaFree(c->d_filt_ids); cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_leaves); cudaFree(c->d_bvh_meta);
   cudaFree(c->d_ctrl); cudaFree(c->d_live); cudaFree(c->d_accum); cudaFree(c->d_rgb); cudaFree(c->d_rgba8);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -709,6 +714,7 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
       P.out_o = S + (3 * outb + 0) * cap; P.out_d = S + (3 * outb + 1) * cap; P.out_t = S + (3 * outb + 2) * cap;
       P.accum = c->d_accum;
       P.g = c->g; P.n_geoms = c->n_geoms;
+      P.normals = c->d_normals;
       P.filt = c->filt; P.filt_cap = c->filt_cap;
       P.bvh = c->bvh;
       P.mats = c->d_mats;
@@ -859,7 +865,8 @@ extern "C" int pt_intersect_ex(pt_context* c, int mode, int n, const float* orig
   CU(cudaMemcpyAsync(ddr.p, direction, v * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemsetAsync(dfb.p, 0, sizeof(unsigned long long), c->stream));
   k_intersect_list<<<(n + kTile - 1) / kTile, kTile, c->geom_smem, c->stream>>>(
-      c->g, c->n_geoms, c->filt, c->filt_cap, c->bvh, mode, n, dor.p, ddr.p, did.p, dt.p, dpnt.p, dn.p, dfb.p);
+      c->g, c->n_geoms, c->filt, c->filt_cap, c->bvh, mode == PT_HIT_FILTERED ? c->d_normals : nullptr, mode, n, dor.p, ddr.p,
+      did.p, dt.p, dpnt.p, dn.p, dfb.p);
   c->launches++;
   CU(cudaGetLastError());
   unsigned long long fb = 0;

@@ -117,7 +117,8 @@ struct BounceParams {
   const float4 *in_o, *in_d, *in_t;  // path state in:  (origin.xyz, pixel) (direction.xyz, sample) (throughput.xyz, -)
   float4 *out_o, *out_d, *out_t;     // survivors out, compacted
   float4* accum;                     // per-pixel radiance sums
-  GeomSoA g;                         // per-geom rows in HBM (winner's normal / material lookup)
+  GeomSoA g;                         // per-geom rows in HBM (the winner's exact test / material lookup)
+  const float4* normals;             // per-geom table of face normals and sphere centres (k_normal_table)
   int n_geoms;
   FiltSoA filt;                      // filter geometry (pt_filter.cuh): pairs of geoms, four classes
   int filt_cap;                      // pairs that fit in shared memory
@@ -164,7 +165,7 @@ constexpr uint32_t kTicketUnits = PT_TICKET_UNITS;
 template <bool FIRST, bool LAST, bool BVH>
 __global__ void __launch_bounds__(kBounceThreads, BVH ? (3 * 256 / kBounceThreads) : PT_MIN_BLOCKS) k_bounce(const __grid_constant__ BounceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
   // ---- filter geometry: staged once per CTA (scenes with many geoms use the hierarchy instead) ----
   const float4* const fs = reinterpret_cast<const float4*>(smem_raw);
   if (!BVH) {
@@ -239,9 +240,7 @@ __global__ void __launch_bounds__(kBounceThreads, BVH ? (3 * 256 / kBounceThread
     }
     if (hit) {
       const int gi = h.id;
-      // the winner's own rows: from HBM through L1 (a handful of distinct addresses per warp)
-      const float4 f0 = __ldg(P.g.fwd0 + gi), f1 = __ldg(P.g.fwd1 + gi), f2 = __ldg(P.g.fwd2 + gi);
-      const f3 n = hit_normal(f0, f1, f2, h);
+      const f3 n = hit_normal_table(P.normals, h);
       MatRows m;
       m.a = __ldg(P.mats + 4 * mat); m.b = __ldg(P.mats + 4 * mat + 1); m.c = __ldg(P.mats + 4 * mat + 2); m.d = md;
       f3 L;
@@ -272,6 +271,23 @@ __global__ void k_accum_counts(const WfCtrl* ctrl, unsigned long long* live_tota
   if (d == 0) live_total[kMaxDepth] += ctrl->fallbacks;
 }
 
+// the ray-independent part of hit_normal, once per scene: identical instructions, so identical bits
+__global__ void k_normal_table(GeomSoA g, int n_geoms, float4* tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_geoms) return;
+  const float4 f0 = g.fwd0[i], f1 = g.fwd1[i], f2 = g.fwd2[i];
+  Hit h;
+  h.t = 0.0f; h.id = i; h.p = mk(0, 0, 0);
+  for (int face = 0; face < 6; face++) {
+    h.ncode = (face % 3) | (face >= 3 ? 4 : 0);
+    const f3 n = hit_normal(f0, f1, f2, h);
+    tab[(size_t)i * kNormalRows + face] = make_float4(n.x, n.y, n.z, 0.0f);
+  }
+  const f3 c = mulMV(f0, f1, f2, 0.0f, 0.0f, 0.0f, 1.0f);  // intersections.h:111: transform * (0,0,0,1)
+  tab[(size_t)i * kNormalRows + 6] = make_float4(c.x, c.y, c.z, 0.0f);
+  tab[(size_t)i * kNormalRows + 7] = make_float4(0, 0, 0, 0);
+}
+
 // ---- parity entry points ----
 __global__ void k_raygen_list(RaygenConsts C, uint64_t seed, int n, const uint32_t* pixel, const uint32_t* sample,
                               float* o, float* d) {
@@ -283,7 +299,7 @@ __global__ void k_raygen_list(RaygenConsts C, uint64_t seed, int n, const uint32
   d[3 * i] = dd.x; d[3 * i + 1] = dd.y; d[3 * i + 2] = dd.z;
 }
 
-__global__ void __launch_bounds__(kTile) k_intersect_list(GeomSoA g, int n_geoms, FiltSoA filt, int filt_cap, BvhSoA bvh, int mode, int n,
+__global__ void __launch_bounds__(kTile) k_intersect_list(GeomSoA g, int n_geoms, FiltSoA filt, int filt_cap, BvhSoA bvh, const float4* normals, int mode, int n,
                                                           const float* o, const float* d, int* id, float* t, float* p,
                                                           float* nrm, unsigned long long* fallbacks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -315,7 +331,7 @@ __global__ void __launch_bounds__(kTile) k_intersect_list(GeomSoA g, int n_geoms
   }
   if (!valid) return;
   f3 nn = mk(0, 0, 0);
-  if (h.id >= 0) nn = hit_normal(__ldg(g.fwd0 + h.id), __ldg(g.fwd1 + h.id), __ldg(g.fwd2 + h.id), h);
+  if (h.id >= 0) nn = normals ? hit_normal_table(normals, h) : hit_normal(__ldg(g.fwd0 + h.id), __ldg(g.fwd1 + h.id), __ldg(g.fwd2 + h.id), h);
   id[i] = h.id;
   t[i] = h.id >= 0 ? h.t : -1.0f;
   p[3 * i] = h.p.x; p[3 * i + 1] = h.p.y; p[3 * i + 2] = h.p.z;

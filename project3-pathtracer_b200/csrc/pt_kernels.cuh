@@ -182,11 +182,12 @@ __global__ void __launch_bounds__(kBounceThreads, BVH ? (3 * 256 / kBounceThread
   if (lane == 0) next_raw = atom_add_u32(ticket, 1u);
 
   for (;;) {
-    const uint32_t unit0 = __shfl_sync(0xffffffffu, next_raw, 0) * kTicketUnits;
+    constexpr uint32_t kTU = BVH ? 1u : kTicketUnits;  // traversal times vary too much for multi-unit tickets
+    const uint32_t unit0 = __shfl_sync(0xffffffffu, next_raw, 0) * kTU;
     if (unit0 >= n_units) break;
     if (lane == 0) next_raw = atom_add_u32(ticket, 1u);  // consumed after this ticket's units: its latency is hidden
 #pragma unroll 1
-    for (uint32_t unit = unit0; unit < min(unit0 + kTicketUnits, n_units); unit++) {
+    for (uint32_t unit = unit0; unit < min(unit0 + kTU, n_units); unit++) {
     const uint32_t idx = unit * kUnit + lane;
     const bool valid = idx < n_in;
 
@@ -240,7 +241,9 @@ __global__ void __launch_bounds__(kBounceThreads, BVH ? (3 * 256 / kBounceThread
     }
     if (hit) {
       const int gi = h.id;
-      const f3 n = hit_normal_table(P.normals, h);
+      // few geoms: the per-geom table (L1-resident); many geoms: from the winner's rows, which the exact test just loaded
+      const f3 n = BVH ? hit_normal(__ldg(P.g.fwd0 + gi), __ldg(P.g.fwd1 + gi), __ldg(P.g.fwd2 + gi), h)
+                       : hit_normal_table(P.normals, h);
       MatRows m;
       m.a = __ldg(P.mats + 4 * mat); m.b = __ldg(P.mats + 4 * mat + 1); m.c = __ldg(P.mats + 4 * mat + 2); m.d = md;
       f3 L;

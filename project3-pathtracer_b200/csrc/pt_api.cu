@@ -87,7 +87,7 @@ struct pt_context {
   uchar4* d_rgba8 = nullptr;   // staging for the 8-bit resolve
   int grid_blocks[4] = {0, 0, 0, 0};  // persistent grid per (FIRST,LAST) variant
   int mode = -1;                      // 0: linear scan over pairs staged in shared memory, 1: hierarchy (pt_bvh.cuh)
-  size_t smem_bytes = 0;   // k_bounce: geometry + survivor staging
+  size_t smem_bytes = 0;   // k_bounce: filter geometry
   size_t geom_smem = 0;    // filter geometry only (k_intersect_list)
 };
 

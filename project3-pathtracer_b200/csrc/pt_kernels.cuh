@@ -145,7 +145,6 @@ struct BounceParams {
 // as k_compact_u32 / pt_compact_u32.  Results do not depend on the slot order (RNG streams are keyed by pixel and
 // sample, radiance goes through atomics).
 constexpr int kUnit = 32;  // paths per unit = one warp
-__host__ __device__ inline size_t stage_smem_bytes() { return 0; }
 
 __device__ __forceinline__ uint32_t atom_add_u32(uint32_t* p, uint32_t v) {  // plain ATOMG, no warp-aggregation code
   uint32_t old;

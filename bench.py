@@ -245,7 +245,7 @@ def main():
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
         n_bounce = max(1, (launches // args.steps) * DEPTH // (DEPTH + 1))  # launches per step = wavefronts * (DEPTH k_bounce + 1 k_accum_counts)
-        traffic, traffic_note = None, "no ncu capture on file"
+        traffic, traffic_note, pipes = None, "no ncu capture on file", None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
@@ -253,6 +253,7 @@ def main():
             # algorithmic bytes of an average launch of this run
             traffic = tj["dram_over_algorithmic"] * alg_bytes / n_bounce
             traffic_note = "ncu dram read+write / algorithmic = %.3f on the captured launch (%s)" % (tj["dram_over_algorithmic"], tj["source"])
+            pipes = tj.get("pipes_pct_of_peak")  # FP32 pipe utilisation next to the HBM fraction (same capture)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -270,7 +271,9 @@ def main():
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_of_nominal_8000": achieved / 8000.0,
                          "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "kernel": "k_bounce",
+                         "ncu_pipes_pct_of_peak": pipes,
                          "algorithmic_bytes_per_launch": alg_bytes / n_bounce, "launches_per_step": n_bounce,
                          "avg_launch_us": 1e3 * ms_per_step / n_bounce,
                          "note": "achieved = algorithmic bytes 96*(S-P) + 32*P of a step / CUDA-event time of the step; the step is "
@@ -282,6 +285,9 @@ def main():
             out["cpu_baseline"] = {"value": csegs / csecs / 1e6, "unit": UNIT, "cores": cthreads, "kind": "port",
                                    "sample": "BASELINE configs[0] x %d: sample scene 800x800, %d spp, 8 bounces (%d segments, %.2f s)"
                                              % (CPU_SPP, CPU_SPP, csegs, csecs)}
+            s1, t1, _ = cpu_oracle_rate(threads=1, spp=2)  # the same oracle on ONE core
+            out["cpu_baseline_1core"] = {"value": s1 / t1 / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+                                         "sample": "sample scene 800x800, 2 spp, 8 bounces (%d segments, %.2f s)" % (s1, t1)}
         print(json.dumps(out))
     ctx.close()
     if world > 1:

@@ -76,8 +76,13 @@ struct pt_context {
   uint32_t W = 0, H = 0, npix = 0;
   // wavefront
   uint64_t wf_capacity = 0;  // paths
-  float4* d_state = nullptr; // 6 arrays of wf_capacity float4: o0 d0 t0 o1 d1 t1
-  WfCtrl* d_ctrl = nullptr;
+  // Two wavefronts are in flight at a time, each on its own internal stream with its own path-state buffers and control
+  // block: the tail of one wavefront's launch (its last units) overlaps the head of the other's instead of idling SMs.
+  static const int kSlots = 2;
+  float4* d_state = nullptr; // per slot: 6 arrays of wf_capacity float4: o0 d0 t0 o1 d1 t1
+  WfCtrl* d_ctrl = nullptr;  // per slot
+  cudaStream_t wf_stream[kSlots] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {nullptr, nullptr};
   unsigned long long* d_live = nullptr;  // kMaxDepth totals
   uint64_t paths_total = 0;
   uint64_t launches = 0;     // kernels of this library launched on behalf of this context
@@ -594,7 +599,7 @@ static int alloc_wavefront(pt_context* c, uint64_t max_paths) {
   if (cap == c->wf_capacity) return PT_OK;
   if (c->d_state) CU(cudaFree(c->d_state));
   c->d_state = nullptr; c->wf_capacity = 0;
-  CU(cudaMalloc(&c->d_state, 6 * cap * sizeof(float4)));
+  CU(cudaMalloc(&c->d_state, (size_t)pt_context::kSlots * 6 * cap * sizeof(float4)));
   c->wf_capacity = cap;
   return PT_OK;
 }
@@ -606,6 +611,11 @@ extern "C" int pt_context_destroy(pt_context* c) {
   cudaFree(c->d_rows); cudaFree(c->d_meta); cudaFree(c->d_normals); cudaFree(c->d_mats); cudaFree(c->d_state);
   cudaFree(c->d_filt); cudaFree(c->d_filt_ids); cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_leaves); cudaFree(c->d_bvh_meta);
   cudaFree(c->d_ctrl); cudaFree(c->d_live); cudaFree(c->d_accum); cudaFree(c->d_rgb); cudaFree(c->d_rgba8);
+  for (int i = 0; i < pt_context::kSlots; i++) {
+    if (c->wf_stream[i]) { cudaStreamSynchronize(c->wf_stream[i]); cudaStreamDestroy(c->wf_stream[i]); }
+    if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -629,7 +639,11 @@ extern "C" int pt_context_create(const pt_static_geom* geoms, int n_geoms, const
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { pt_set_error_("cudaGetDeviceProperties failed"); return fail(PT_ERR_CUDA); }
   c->sm_count = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+  bool ok = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < pt_context::kSlots; i++)
+    ok = ok && cudaStreamCreateWithFlags(&c->wf_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
     pt_set_error_("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     return fail(PT_ERR_CUDA);
@@ -639,7 +653,7 @@ extern "C" int pt_context_create(const pt_static_geom* geoms, int n_geoms, const
   if (cudaMalloc(&c->d_accum, (size_t)c->npix * sizeof(float4)) != cudaSuccess ||
       cudaMalloc(&c->d_rgb, (size_t)c->npix * 3 * sizeof(float)) != cudaSuccess ||
       cudaMalloc(&c->d_rgba8, (size_t)c->npix * sizeof(uchar4)) != cudaSuccess ||
-      cudaMalloc(&c->d_ctrl, sizeof(WfCtrl)) != cudaSuccess ||
+      cudaMalloc(&c->d_ctrl, pt_context::kSlots * sizeof(WfCtrl)) != cudaSuccess ||
       cudaMalloc(&c->d_live, (kMaxDepth + 1) * sizeof(unsigned long long)) != cudaSuccess) {
     pt_set_error_("cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     return fail(PT_ERR_CUDA);
@@ -685,12 +699,12 @@ extern "C" int pt_clear(pt_context* c) {
 }
 
 template <bool F, bool L>
-static cudaError_t launch_bounce(pt_context* c, int slot, const BounceParams& P, uint32_t n_upper) {
+static cudaError_t launch_bounce(pt_context* c, int slot, const BounceParams& P, uint32_t n_upper, cudaStream_t st) {
   uint32_t ctas = (n_upper + kBounceThreads - 1) / kBounceThreads;  // one unit per warp at least
   uint32_t grid = (uint32_t)c->grid_blocks[slot];
   if (ctas < grid) grid = ctas ? ctas : 1;
-  if (c->mode) k_bounce<F, L, true><<<grid, kBounceThreads, c->smem_bytes, c->stream>>>(P);
-  else k_bounce<F, L, false><<<grid, kBounceThreads, c->smem_bytes, c->stream>>>(P);
+  if (c->mode) k_bounce<F, L, true><<<grid, kBounceThreads, c->smem_bytes, st>>>(P);
+  else k_bounce<F, L, false><<<grid, kBounceThreads, c->smem_bytes, st>>>(P);
   c->launches++;
   return cudaGetLastError();
 }
@@ -701,12 +715,24 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
   if ((uint64_t)first_sample + n_samples > 0xFFFFFFFFull) { pt_set_error_("sample index overflow"); return PT_ERR_INVALID; }
   CU(cudaEventRecord(c->ev0, c->stream));
   const uint32_t spp_wf = (uint32_t)(c->wf_capacity / c->npix);
-  float4* S = c->d_state;
   const uint64_t cap = c->wf_capacity;
-  for (uint32_t s0 = 0; s0 < n_samples; s0 += spp_wf) {
+  // fork: wavefront i runs on internal stream i % kSlots, after everything queued on the caller's stream so far
+  // ... as long as the accumulation image leaves room in the 126 MB L2 for two wavefronts' streams: at 3840x2160 (133 MB
+  // of float4 sums) a second concurrent sweep over the image costs more in missed RED atomics than the overlap gains
+  const int n_wf = (int)((n_samples + spp_wf - 1) / spp_wf);
+  const int max_slots = (size_t)c->npix * sizeof(float4) <= ((size_t)48 << 20) ? pt_context::kSlots : 1;
+  const int slots_used = n_wf < max_slots ? n_wf : max_slots;
+  CU(cudaEventRecord(c->ev_fork, c->stream));
+  for (int i = 0; i < slots_used; i++) CU(cudaStreamWaitEvent(c->wf_stream[i], c->ev_fork, 0));
+  int wf = 0;
+  for (uint32_t s0 = 0; s0 < n_samples; s0 += spp_wf, wf++) {
+    const int sl = wf % slots_used;
+    cudaStream_t st = c->wf_stream[sl];
+    float4* S = c->d_state + (size_t)sl * 6 * cap;
+    WfCtrl* ctrl = c->d_ctrl + sl;
     const uint32_t ns = (n_samples - s0 < spp_wf) ? (n_samples - s0) : spp_wf;
     const uint32_t n_first = ns * c->npix;
-    CU(cudaMemsetAsync(c->d_ctrl, 0, sizeof(WfCtrl), c->stream));
+    CU(cudaMemsetAsync(ctrl, 0, sizeof(WfCtrl), st));
     for (int depth = 0; depth < max_depth; depth++) {
       BounceParams P;
       const int in = depth & 1, outb = in ^ 1;
@@ -719,23 +745,28 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
       P.bvh = c->bvh;
       P.mats = c->d_mats;
       P.cam = c->cam;
-      P.ctrl = c->d_ctrl;
+      P.ctrl = ctrl;
       P.depth = (uint32_t)depth;
       P.seed = seed;
       P.first_sample = first_sample + s0;
       P.n_first = n_first;
       const bool first = depth == 0, last = depth == max_depth - 1;
       cudaError_t e;
-      if (first && last) e = launch_bounce<true, true>(c, 1, P, n_first);
-      else if (first) e = launch_bounce<true, false>(c, 0, P, n_first);
-      else if (last) e = launch_bounce<false, true>(c, 3, P, n_first);
-      else e = launch_bounce<false, false>(c, 2, P, n_first);
+      if (first && last) e = launch_bounce<true, true>(c, 1, P, n_first, st);
+      else if (first) e = launch_bounce<true, false>(c, 0, P, n_first, st);
+      else if (last) e = launch_bounce<false, true>(c, 3, P, n_first, st);
+      else e = launch_bounce<false, false>(c, 2, P, n_first, st);
       if (e != cudaSuccess) { pt_set_error_("k_bounce launch failed: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
     }
-    k_accum_counts<<<1, kMaxDepth, 0, c->stream>>>(c->d_ctrl, c->d_live, max_depth);
+    k_accum_counts<<<1, kMaxDepth, 0, st>>>(ctrl, c->d_live, max_depth);
     c->launches++;
     CU(cudaGetLastError());
     c->paths_total += n_first;
+  }
+  // join: the caller's stream continues when both internal streams are done
+  for (int i = 0; i < slots_used; i++) {
+    CU(cudaEventRecord(c->ev_join[i], c->wf_stream[i]));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
   }
   CU(cudaEventRecord(c->ev1, c->stream));
   c->timed = true;

@@ -269,8 +269,9 @@ __global__ void __launch_bounds__(kBounceThreads, BVH ? (3 * 256 / kBounceThread
 // live_total[d] += count[d]; one tiny launch per wavefront
 __global__ void k_accum_counts(const WfCtrl* ctrl, unsigned long long* live_total, int max_depth) {
   int d = threadIdx.x;
-  if (d < max_depth) live_total[d] += ctrl->count[d];
-  if (d == 0) live_total[kMaxDepth] += ctrl->fallbacks;
+  // atomics: the two wavefront slots run on different streams and may fold their counts at the same time
+  if (d < max_depth) atomicAdd(live_total + d, (unsigned long long)ctrl->count[d]);
+  if (d == 0) atomicAdd(live_total + kMaxDepth, (unsigned long long)ctrl->fallbacks);
 }
 
 // the ray-independent part of hit_normal, once per scene: identical instructions, so identical bits

@@ -146,6 +146,9 @@ int pt_intersect(pt_context* ctx, int n, const float* origin, const float* direc
  * preserved; out must have room for n entries */
 int pt_compact_u32(int device, const uint32_t* values, const uint8_t* flags, uint64_t n, uint32_t* out,
                    uint64_t* n_out);
+/* the same, and the kernel alone timed on the device (CUDA events, mean of `iters` launches after one warm-up) */
+int pt_compact_u32_timed(int device, const uint32_t* values, const uint8_t* flags, uint64_t n, uint32_t* out,
+                         uint64_t* n_out, int iters, float* kernel_ms);
 
 /* Closest hit runs as a conservative filter over all geoms followed by the reference-exact test of the best
  * candidate, falling back to the exact scan of every geom when the filter cannot separate two surfaces

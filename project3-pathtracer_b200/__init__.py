@@ -222,6 +222,17 @@ def compact_u32(values, flags, device=0):
     return out[: n_out.value].copy()
 
 
+def compact_u32_timed(values, flags, iters=10, device=0):
+    """pt_compact_u32_timed: (compacted values, kernel milliseconds per launch on the device)"""
+    v, f = _arr(values, np.uint32).ravel(), _arr(flags, np.uint8).ravel()
+    assert v.shape == f.shape
+    out = np.empty(max(v.shape[0], 1), np.uint32)
+    n_out, ms = C.c_uint64(), C.c_float()
+    _check(lib().pt_compact_u32_timed(C.c_int(device), _p(v), _p(f), C.c_uint64(v.shape[0]), _p(out), C.byref(n_out),
+                                      C.c_int(iters), C.byref(ms)))
+    return out[: n_out.value].copy(), ms.value
+
+
 class Scene:
     """scene::scene(string) of the reference (src/scene.cpp:11-35) through pt_scene_load."""
 

@@ -933,10 +933,11 @@ extern "C" int pt_filter_stats(pt_context* c, uint64_t* fallbacks) {
   return PT_OK;
 }
 
-extern "C" int pt_compact_u32(int device, const uint32_t* values, const uint8_t* flags, uint64_t n, uint32_t* out,
-                              uint64_t* n_out) {
+static int compact_impl(int device, const uint32_t* values, const uint8_t* flags, uint64_t n, uint32_t* out,
+                        uint64_t* n_out, int timed_iters, float* kernel_ms) {
   if (!n_out || (n > 0 && (!values || !flags || !out))) { pt_set_error_("bad arguments"); return PT_ERR_INVALID; }
   *n_out = 0;
+  if (kernel_ms) *kernel_ms = 0.0f;
   if (n == 0) return PT_OK;
   if (n > 0xFFFFFF00ull) { pt_set_error_("n too large"); return PT_ERR_INVALID; }
   int ndev = 0;
@@ -948,23 +949,47 @@ extern "C" int pt_compact_u32(int device, const uint32_t* values, const uint8_t*
   DevBuf<uint32_t> dv, dout, dctl;
   DevBuf<uint8_t> df;
   DevBuf<uint64_t> dst;
-  const uint64_t tiles = (n + kTile - 1) / kTile;
+  const uint64_t tiles = (n + kCompactTile - 1) / kCompactTile;
   CU(dv.alloc(n)); CU(dout.alloc(n)); CU(dctl.alloc(2)); CU(df.alloc(n)); CU(dst.alloc(tiles));
   CU(cudaMemcpy(dv.p, values, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(df.p, flags, n, cudaMemcpyHostToDevice));
-  CU(cudaMemset(dctl.p, 0, 2 * sizeof(uint32_t)));
   CU(cudaMemset(dst.p, 0, tiles * sizeof(uint64_t)));
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_compact_u32, kTile, 0));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_compact_u32, kCompactThreads, 0));
   uint64_t grid = (uint64_t)per_sm * prop.multiProcessorCount;
   if (tiles < grid) grid = tiles;
-  k_compact_u32<<<(unsigned)grid, kTile>>>(dv.p, df.p, (uint32_t)n, dout.p, dctl.p + 1, dctl.p, dst.p, 1u);
-  CU(cudaGetLastError());
+  // the status words carry the launch epoch, so repeated launches need no clearing in between
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timed_iters > 0) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); }
+  const int launches = timed_iters > 0 ? timed_iters + 1 : 1;  // one warm-up launch before the timed ones
+  for (int it = 0; it < launches; it++) {
+    CU(cudaMemsetAsync(dctl.p, 0, 2 * sizeof(uint32_t), 0));
+    if (timed_iters > 0 && it == 1) CU(cudaEventRecord(e0, 0));
+    k_compact_u32<<<(unsigned)grid, kCompactThreads>>>(dv.p, df.p, (uint32_t)n, dout.p, dctl.p + 1, dctl.p, dst.p, (uint32_t)(it + 1));
+    CU(cudaGetLastError());
+  }
+  if (timed_iters > 0) {
+    CU(cudaEventRecord(e1, 0));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (kernel_ms) *kernel_ms = ms / timed_iters;  // includes one 8-byte memset per launch
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
   uint32_t cnt = 0;
   CU(cudaMemcpy(&cnt, dctl.p + 1, sizeof(cnt), cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(out, dout.p, (size_t)cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   *n_out = cnt;
   return PT_OK;
+}
+extern "C" int pt_compact_u32(int device, const uint32_t* values, const uint8_t* flags, uint64_t n, uint32_t* out,
+                              uint64_t* n_out) {
+  return compact_impl(device, values, flags, n, out, n_out, 0, nullptr);
+}
+extern "C" int pt_compact_u32_timed(int device, const uint32_t* values, const uint8_t* flags, uint64_t n, uint32_t* out,
+                                    uint64_t* n_out, int iters, float* kernel_ms) {
+  if (iters < 1 || !kernel_ms) { pt_set_error_("bad arguments"); return PT_ERR_INVALID; }
+  return compact_impl(device, values, flags, n, out, n_out, iters, kernel_ms);
 }
 
 extern "C" int pt_selftest_math(int device, uint64_t bad[3]) {

@@ -55,6 +55,9 @@ __device__ __forceinline__ uint64_t st_load(const uint64_t* p) {
 
 // Called by ONE full warp of the CTA that owns `tile`.  aggregate = number of survivors in this tile.
 // Returns the number of survivors in all earlier tiles (exclusive prefix) to every lane.
+// (Inspecting 128 instead of 32 predecessors per look-back step -- four independent loads per lane -- was tried for
+// k_compact_u32 and did not help: tiles do not wait for the prefix wave but for the slowest load among ALL their
+// predecessors, see profiles/r01_compact_u32.txt.)
 __device__ __forceinline__ uint32_t lookback_exclusive(uint64_t* status, uint32_t tile, uint32_t epoch,
                                                        uint32_t aggregate) {
   const uint32_t lane = threadIdx.x & 31u;
@@ -82,35 +85,6 @@ __device__ __forceinline__ uint32_t lookback_exclusive(uint64_t* status, uint32_
   }
   if (lane == 0) st_store(status + tile, st_pack(epoch, kStPrefix, exclusive + aggregate));
   return exclusive;
-}
-
-// Block-level part shared by k_bounce and k_compact_u32: every thread passes its flag, gets its output slot.
-// s_warp (>= 8 words) and s_base are shared scratch.  All threads of the CTA must call.
-// Returns the global slot of this thread's item (meaningful if keep) and the tile's inclusive total via *incl.
-__device__ __forceinline__ uint32_t compact_slot(bool keep, uint64_t* status, uint32_t tile, uint32_t epoch,
-                                                 uint32_t* s_warp, uint32_t* s_base, uint32_t* incl) {
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
-  const uint32_t lane_off = __popc(ballot & ((1u << lane) - 1u));
-  if (lane == 0) s_warp[warp] = __popc(ballot);
-  __syncthreads();
-  if (warp == 0) {
-    const uint32_t nw = blockDim.x >> 5;
-    uint32_t c = lane < nw ? s_warp[lane] : 0u;
-    uint32_t incl_w = c;  // inclusive scan over the warps' counts
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t v = __shfl_up_sync(0xffffffffu, incl_w, o);
-      if ((int)lane >= o) incl_w += v;
-    }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl_w, 31);
-    const uint32_t excl = lookback_exclusive(status, tile, epoch, total);
-    if (lane < nw) s_warp[lane] = incl_w - c;  // exclusive offset of each warp within the tile
-    if (lane == 0) { s_base[0] = excl; s_base[1] = excl + total; }
-  }
-  __syncthreads();
-  *incl = s_base[1];
-  return s_base[0] + s_warp[warp] + lane_off;
 }
 
 struct BounceParams {
@@ -341,26 +315,102 @@ __global__ void __launch_bounds__(kTile) k_intersect_list(GeomSoA g, int n_geoms
   nrm[3 * i] = nn.x; nrm[3 * i + 1] = nn.y; nrm[3 * i + 2] = nn.z;
 }
 
-// stream compaction on its own: same ballot / block scan / look-back code as k_bounce
-__global__ void __launch_bounds__(kTile) k_compact_u32(const uint32_t* values, const uint8_t* flags, uint32_t n,
-                                                       uint32_t* out, uint32_t* n_out, uint32_t* ticket,
-                                                       uint64_t* status, uint32_t epoch) {
+// ---- stream compaction on its own (README.md:63-70): stable, single pass, decoupled look-back ----
+// A tile is 256 threads x 16 elements = 4096 consecutive elements.  Each WARP owns 512 consecutive elements and loads
+// them warp-striped -- lane l, step j reads the uint4 (and the 4 flag bytes) at element (j*32 + l)*4 of the warp's chunk
+// -- so every load instruction covers 512 contiguous bytes.  Ranks in index order:
+//   inside a lane's uint4      prefix of its 4 flags
+//   across the lanes of a step  counts 0..4 per lane -> three ballots (one per bit of the count) + popc of the lanes below
+//   across the 4 steps / 8 warps running sums; the warps' totals go through shared memory (block scan)
+//   across tiles               64-bit status word per tile (epoch | state | value): the tile's aggregate is published as
+//                               soon as it is known, warp 0 looks back over 32 predecessors per step until it meets an
+//                               inclusive prefix, then publishes its own.  Tiles come from a ticket counter, so every
+//                               predecessor is resident and the look-back cannot deadlock; the epoch tag makes clearing
+//                               the status words between launches unnecessary.
+// Kept elements are written straight to out[prefix + rank]: a lane's (up to 4) elements are adjacent and the lanes'
+// ranges abut, so the sectors are filled within the warp.  HBM-bound: 5 B read per element + 4 B written per kept one.
+#ifndef PT_COMPACT_THREADS
+#define PT_COMPACT_THREADS 256
+#endif
+constexpr int kCompactThreads = PT_COMPACT_THREADS;
+constexpr int kCompactItems = 16;                                // elements per thread
+constexpr int kCompactTile = kCompactThreads * kCompactItems;    // 4096 elements per tile
+#ifndef PT_COMPACT_BLOCKS
+#define PT_COMPACT_BLOCKS (2048 / PT_COMPACT_THREADS)  // resident CTAs per SM: the kernel is latency-bound (one HBM and one L2 round trip per tile)
+#endif
+__global__ void __launch_bounds__(kCompactThreads, PT_COMPACT_BLOCKS) k_compact_u32(const uint32_t* __restrict__ values, const uint8_t* __restrict__ flags,
+                                                       uint32_t n, uint32_t* __restrict__ out, uint32_t* n_out,
+                                                       uint32_t* ticket, uint64_t* status, uint32_t epoch) {
   __shared__ uint32_t s_tile;
-  __shared__ uint32_t s_warp[kTile / 32];
-  __shared__ uint32_t s_base[2];
-  const uint32_t n_tiles = (n + kTile - 1) / kTile;
+  __shared__ uint32_t s_warp[kCompactThreads / 32];  // per-warp totals, then exclusive offsets inside the tile
+  __shared__ uint32_t s_base;              // exclusive prefix of the tile
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t n_tiles = (n + kCompactTile - 1) / kCompactTile;
+  const bool aligned = (reinterpret_cast<uintptr_t>(values) & 15u) == 0 && (reinterpret_cast<uintptr_t>(flags) & 3u) == 0;
   for (;;) {
-    __syncthreads();
+    __syncthreads();  // s_tile / s_warp / s_base of the previous tile are no longer read
+    // (a ticket taken ahead of time would delay that tile's aggregate by a whole tile and stall every successor: measured -30 %)
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
     if (tile >= n_tiles) break;
-    const uint32_t idx = tile * kTile + threadIdx.x;
-    const bool keep = idx < n && flags[idx] != 0;
-    uint32_t incl;
-    const uint32_t slot = compact_slot(keep, status, tile, epoch, s_warp, s_base, &incl);
-    if (keep) out[slot] = values[idx];
-    if (tile == n_tiles - 1 && threadIdx.x == 0) *n_out = incl;
+    const uint32_t chunk = tile * kCompactTile + warp * (32 * kCompactItems);  // first element of this warp's 512
+    uint4 v[4];
+    uint32_t f[4];       // 4 flag bytes per step, normalised to 0 / 1 per byte
+    uint32_t cnt[4];     // kept elements of this lane in step j
+    uint32_t before[4];  // kept elements of the warp before this lane's uint4 of step j
+    uint32_t run = 0;    // running total of the warp over the steps
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t e = chunk + (j * 32 + lane) * 4;  // first of this lane's 4 elements
+      uint32_t fb = 0;
+      if (e + 4 <= n && aligned) {
+        v[j] = __ldcs(reinterpret_cast<const uint4*>(values + e));
+        fb = __ldcs(reinterpret_cast<const uint32_t*>(flags + e));
+      } else {  // the ragged end of the input (or unaligned pointers): element by element
+        uint32_t t[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (e + k < n) { t[k] = values[e + k]; fb |= (uint32_t)flags[e + k] << (8 * k); }
+        v[j] = make_uint4(t[0], t[1], t[2], t[3]);
+      }
+      // byte != 0 -> 1, per byte (no carries across bytes: 0x7f + 0x7f < 0x100)
+      f[j] = ((((fb & 0x7f7f7f7fu) + 0x7f7f7f7fu) | fb) & 0x80808080u) >> 7;
+      cnt[j] = (f[j] * 0x01010101u) >> 24;  // sum of the four bytes
+      const uint32_t b0 = __ballot_sync(0xffffffffu, cnt[j] & 1u), b1 = __ballot_sync(0xffffffffu, cnt[j] & 2u),
+                     b2 = __ballot_sync(0xffffffffu, cnt[j] & 4u);
+      before[j] = run + __popc(b0 & lt) + 2u * __popc(b1 & lt) + 4u * __popc(b2 & lt);
+      run += __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+    }
+    if (lane == 0) s_warp[warp] = run;
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t c = lane < kCompactThreads / 32 ? s_warp[lane] : 0u;
+      uint32_t incl = c;  // inclusive scan over the warps' totals
+#pragma unroll
+      for (int o = 1; o < kCompactThreads / 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, kCompactThreads / 32 - 1);
+      const uint32_t excl = lookback_exclusive(status, tile, epoch, total);
+      if (lane < kCompactThreads / 32) s_warp[lane] = incl - c;
+      if (lane == 0) {
+        s_base = excl;
+        if (tile == n_tiles - 1) *n_out = excl + total;
+      }
+    }
+    __syncthreads();
+    const uint32_t base = s_base + s_warp[warp];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint32_t pos = base + before[j];
+      if (f[j] & 0x00000001u) out[pos++] = v[j].x;
+      if (f[j] & 0x00000100u) out[pos++] = v[j].y;
+      if (f[j] & 0x00010000u) out[pos++] = v[j].z;
+      if (f[j] & 0x01000000u) out[pos++] = v[j].w;
+    }
   }
 }
 

@@ -8,6 +8,8 @@
 #include "../../include/pt_b200.h"
 #include "../../include/pt_compat.h"
 
+#include <cuda_runtime_api.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -28,6 +30,8 @@ struct Cache {
   const camera* last_cam = nullptr;
   int last_frame = -1, last_iter = 0;
   std::vector<float> scaled;
+  void* pinned = nullptr;  // renderCam->image, page-locked in place while calls keep arriving for it
+  void* pin_failed = nullptr;  // ... or the buffer that could not be locked (not retried on every call)
 } g;
 int g_depth = 8;
 unsigned long long g_seed = 0;
@@ -60,7 +64,22 @@ extern "C" int pt_compat_set_lens(float aperture, float focal_distance) {
 }
 extern "C" int pt_compat_set_exit_on_error(int on) { g_exit_on_error = on; return PT_OK; }
 extern "C" int pt_compat_last_status(void) { return g_status; }
+// The caller reads renderCam->image after every call (src/main.cpp:118-131), so its D2H copy cannot go away; but a
+// pageable destination makes it a staged ~10 GB/s copy.  Page-locking the caller's buffer in place (it lives as long as
+// the scene, src/scene.cpp:207-214) turns it into one DMA.  Failure to lock is harmless: the copy stays pageable.
+static void unpin() {
+  if (g.pinned) { cudaHostUnregister(g.pinned); cudaGetLastError(); g.pinned = nullptr; }
+}
+static void pin(void* image, size_t bytes) {
+  if (g.pinned == image || g.pin_failed == image) return;
+  unpin();
+  const cudaError_t e = cudaHostRegister(image, bytes, cudaHostRegisterDefault);
+  if (e == cudaSuccess) { g.pinned = image; g.pin_failed = nullptr; }
+  else { cudaGetLastError(); g.pin_failed = image; }
+  if (getenv("PT_COMPAT_DEBUG")) fprintf(stderr, "pt_compat: cudaHostRegister(%p, %zu) -> %s\n", image, bytes, cudaGetErrorString(e));
+}
 extern "C" void pt_compat_reset(void) {
+  unpin();
   if (g.ctx) pt_context_destroy(g.ctx);
   g = Cache();
 }
@@ -131,6 +150,7 @@ void cudaRaytraceCore(uchar4* PBOpos, camera* renderCam, int frame, int iteratio
     for (size_t i = 0; i < npix * 3; i++) g.scaled[i] = im[i] * k1;
     if ((rc = pt_upload_sum(g.ctx, g.scaled.data()))) return fail(rc);
   }
+  if (in_sequence || iterations == 1) pin(renderCam->image, npix * 3 * sizeof(float));  // a render loop, not a one-off call
   if ((rc = pt_render(g.ctx, (uint32_t)(iterations - 1), 1, g_depth, g_seed))) return fail(rc);
   if (PBOpos && (rc = pt_resolve_rgba8(g.ctx, (uint32_t)iterations, nullptr, PBOpos))) return fail(rc);
   if ((rc = pt_download_mean(g.ctx, reinterpret_cast<float*>(renderCam->image), (uint32_t)iterations))) return fail(rc);

@@ -81,6 +81,7 @@ struct pt_context {
   static const int kSlots = 2;
   float4* d_state = nullptr; // per slot: 6 arrays of wf_capacity float4: o0 d0 t0 o1 d1 t1
   WfCtrl* d_ctrl = nullptr;  // per slot
+  int n_slots = kSlots;      // slots in use (1 for frames whose accumulation image alone fills the L2)
   cudaStream_t wf_stream[kSlots] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {nullptr, nullptr};
   unsigned long long* d_live = nullptr;  // kMaxDepth totals
@@ -599,7 +600,20 @@ static int alloc_wavefront(pt_context* c, uint64_t max_paths) {
   if (cap == c->wf_capacity) return PT_OK;
   if (c->d_state) CU(cudaFree(c->d_state));
   c->d_state = nullptr; c->wf_capacity = 0;
-  CU(cudaMalloc(&c->d_state, (size_t)pt_context::kSlots * 6 * cap * sizeof(float4)));
+  // ... as long as the accumulation image leaves room in the 126 MB L2 for two wavefronts' streams: at 3840x2160 (133 MB
+  // of float4 sums) a second concurrent sweep over the image costs more in missed RED atomics than the overlap gains
+  c->n_slots = (size_t)c->npix * sizeof(float4) <= ((size_t)48 << 20) ? pt_context::kSlots : 1;
+  if (const char* env = getenv("PT_B200_SLOTS")) c->n_slots = atoi(env) >= 2 ? pt_context::kSlots : 1;  // developer knob
+  // the internal streams exist only when they are used: merely creating extra streams in the process slowed the
+  // single-stream 4K render by 12 % (profiles/r01_two_wavefronts.txt)
+  if (c->n_slots > 1 && !c->wf_stream[0]) {
+    CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < pt_context::kSlots; i++) {
+      CU(cudaStreamCreateWithFlags(&c->wf_stream[i], cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
+  }
+  CU(cudaMalloc(&c->d_state, (size_t)c->n_slots * 6 * cap * sizeof(float4)));
   c->wf_capacity = cap;
   return PT_OK;
 }
@@ -639,11 +653,7 @@ extern "C" int pt_context_create(const pt_static_geom* geoms, int n_geoms, const
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { pt_set_error_("cudaGetDeviceProperties failed"); return fail(PT_ERR_CUDA); }
   c->sm_count = prop.multiProcessorCount;
-  bool ok = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-  for (int i = 0; i < pt_context::kSlots; i++)
-    ok = ok && cudaStreamCreateWithFlags(&c->wf_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
-         cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
-  if (!ok || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
     pt_set_error_("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     return fail(PT_ERR_CUDA);
@@ -717,17 +727,17 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
   const uint32_t spp_wf = (uint32_t)(c->wf_capacity / c->npix);
   const uint64_t cap = c->wf_capacity;
   // fork: wavefront i runs on internal stream i % kSlots, after everything queued on the caller's stream so far
-  // ... as long as the accumulation image leaves room in the 126 MB L2 for two wavefronts' streams: at 3840x2160 (133 MB
-  // of float4 sums) a second concurrent sweep over the image costs more in missed RED atomics than the overlap gains
   const int n_wf = (int)((n_samples + spp_wf - 1) / spp_wf);
-  const int max_slots = (size_t)c->npix * sizeof(float4) <= ((size_t)48 << 20) ? pt_context::kSlots : 1;
-  const int slots_used = n_wf < max_slots ? n_wf : max_slots;
-  CU(cudaEventRecord(c->ev_fork, c->stream));
-  for (int i = 0; i < slots_used; i++) CU(cudaStreamWaitEvent(c->wf_stream[i], c->ev_fork, 0));
+  const int slots_used = n_wf < c->n_slots ? n_wf : c->n_slots;
+  const bool forked = slots_used > 1;  // a single wavefront in flight simply runs on the caller's stream
+  if (forked) {
+    CU(cudaEventRecord(c->ev_fork, c->stream));
+    for (int i = 0; i < slots_used; i++) CU(cudaStreamWaitEvent(c->wf_stream[i], c->ev_fork, 0));
+  }
   int wf = 0;
   for (uint32_t s0 = 0; s0 < n_samples; s0 += spp_wf, wf++) {
     const int sl = wf % slots_used;
-    cudaStream_t st = c->wf_stream[sl];
+    cudaStream_t st = forked ? c->wf_stream[sl] : c->stream;
     float4* S = c->d_state + (size_t)sl * 6 * cap;
     WfCtrl* ctrl = c->d_ctrl + sl;
     const uint32_t ns = (n_samples - s0 < spp_wf) ? (n_samples - s0) : spp_wf;
@@ -764,7 +774,7 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
     c->paths_total += n_first;
   }
   // join: the caller's stream continues when both internal streams are done
-  for (int i = 0; i < slots_used; i++) {
+  for (int i = 0; forked && i < slots_used; i++) {
     CU(cudaEventRecord(c->ev_join[i], c->wf_stream[i]));
     CU(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
   }

@@ -604,8 +604,7 @@ static int alloc_wavefront(pt_context* c, uint64_t max_paths) {
   // of float4 sums) a second concurrent sweep over the image costs more in missed RED atomics than the overlap gains
   c->n_slots = (size_t)c->npix * sizeof(float4) <= ((size_t)48 << 20) ? pt_context::kSlots : 1;
   if (const char* env = getenv("PT_B200_SLOTS")) c->n_slots = atoi(env) >= 2 ? pt_context::kSlots : 1;  // developer knob
-  // the internal streams exist only when they are used: merely creating extra streams in the process slowed the
-  // single-stream 4K render by 12 % (profiles/r01_two_wavefronts.txt)
+  // the internal streams exist only when they are used
   if (c->n_slots > 1 && !c->wf_stream[0]) {
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     for (int i = 0; i < pt_context::kSlots; i++) {

@@ -358,7 +358,7 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
   }
   if (F.ids.empty()) { F.rows.assign(kFiltRows, make_float4(0, 0, 0, 0)); F.ids.push_back(make_int2(0, 0)); }
 
-  // ---- hierarchy for scenes with many geoms: median split of the centroids along the widest axis, one geom per leaf ----
+  // ---- hierarchy for scenes with many geoms: surface-area heuristic, one geom per leaf ----
   const int n = (int)per.size();
   if (n >= kBvhMinGeoms) {
     F.leaves.assign((size_t)n * kBvhLeafRows, make_float4(0, 0, 0, 0));
@@ -398,39 +398,98 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
     };
     auto down = [](double x) { float f = (float)x; if ((double)f > x) f = nextafterf(f, -INFINITY); return nextafterf(f, -INFINITY); };
     auto up = [](double x) { float f = (float)x; if ((double)f < x) f = nextafterf(f, INFINITY); return nextafterf(f, INFINITY); };
+    auto area = [](const Box& b) {  // half the surface area; +inf for an unbounded box
+      const double x = b.hi[0] - b.lo[0], y = b.hi[1] - b.lo[1], z = b.hi[2] - b.lo[2];
+      const double a = x * y + y * z + z * x;
+      return std::isfinite(a) ? a : INFINITY;
+    };
     std::vector<int> idx(n);
     for (int k = 0; k < n; k++) idx[k] = k;
+    std::vector<Box> lbox(n);
+    for (int k = 0; k < n; k++) lbox[k] = leaf_box(k);
+    std::vector<double> suffix(n);
     F.nodes.assign((size_t)(n - 1) * kBvhNodeRows, make_float4(0, 0, 0, 0));
     int next_node = 0;
-    // returns the child reference (node index, or ~leaf) and the box of idx[first, last)
-    std::function<int(int, int, Box&)> build = [&](int first, int last, Box& box) -> int {
-      if (last - first == 1) { box = leaf_box(idx[first]); return ~idx[first]; }
-      double clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
-      for (int i = first; i < last; i++)
-        for (int r = 0; r < 3; r++) { clo[r] = fmin(clo[r], per[idx[i]].bc[r]); chi[r] = fmax(chi[r], per[idx[i]].bc[r]); }
-      int axis = 0;
-      if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
-      if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
-      const int mid = first + (last - first) / 2;  // median split: depth = ceil(log2 n) <= kBvhStack
-      std::nth_element(idx.begin() + first, idx.begin() + mid, idx.begin() + last,
-                       [&](int a, int b) { return per[a].bc[axis] < per[b].bc[axis]; });
+    // Returns the child reference (node index, or ~leaf) and the box of idx[first, last).  Split rule: the cheapest, by
+    // the surface-area heuristic (area x count of each side), of
+    //   * the largest geom on its own (a ground slab among pebbles: whatever group it stayed in would inherit its
+    //     extent, level after level; a sweep over centroids cannot single it out),
+    //   * every split position of the centroids sorted along x, y and z;
+    // the median along the widest axis when the levels left are only just enough to finish by halving (the traversal
+    // stack holds one entry per level: depth <= kBvhStack) or when nothing has a finite cost.
+    const bool median_only = getenv("PT_B200_BVH_MEDIAN") != nullptr;  // measurement knob: the plain median-split tree
+    std::function<int(int, int, int, Box&)> build = [&](int first, int last, int depth, Box& box) -> int {
+      const int cnt = last - first;
+      if (cnt == 1) { box = lbox[idx[first]]; return ~idx[first]; }
+      int levels = 0;
+      while ((1 << levels) < cnt) levels++;
+      const bool must_halve = depth + levels + 2 >= kBvhStack || median_only;
+      int mid = -1;
+      if (!must_halve && cnt > 2) {
+        int big = first;
+        for (int i = first + 1; i < last; i++)
+          if (area(lbox[idx[i]]) > area(lbox[idx[big]])) big = i;
+        std::swap(idx[first], idx[big]);
+        Box rest = lbox[idx[first + 1]];
+        for (int i = first + 2; i < last; i++) rest = merge(rest, lbox[idx[i]]);
+        double best_cost = area(lbox[idx[first]]) + area(rest) * (cnt - 1);  // the largest geom on its own
+        int best_axis = -1, best_mid = first + 1;
+        if (std::isfinite(area(lbox[idx[first]]))) {
+          for (int axis = 0; axis < 3; axis++) {
+            std::sort(idx.begin() + first, idx.begin() + last, [&](int a, int b) { return per[a].bc[axis] < per[b].bc[axis]; });
+            Box acc = lbox[idx[last - 1]];
+            suffix[last - 1] = area(acc);
+            for (int i = last - 2; i > first; i--) { acc = merge(acc, lbox[idx[i]]); suffix[i] = area(acc); }
+            acc = lbox[idx[first]];
+            for (int i = first + 1; i < last; i++) {  // left = [first, i), right = [i, last)
+              const double cost = area(acc) * (i - first) + suffix[i] * (last - i);
+              if (cost < best_cost) { best_cost = cost; best_axis = axis; best_mid = i; }
+              acc = merge(acc, lbox[idx[i]]);
+            }
+          }
+        }
+        if (best_axis >= 0) {
+          if (best_axis != 2)
+            std::sort(idx.begin() + first, idx.begin() + last, [&](int a, int b) { return per[a].bc[best_axis] < per[b].bc[best_axis]; });
+          mid = best_mid;
+        } else if (std::isfinite(best_cost) || !std::isfinite(area(lbox[idx[big]]))) {
+          // (the sorts moved the largest geom: bring it back to the front)
+          big = first;
+          for (int i = first + 1; i < last; i++)
+            if (area(lbox[idx[i]]) > area(lbox[idx[big]])) big = i;
+          std::swap(idx[first], idx[big]);
+          mid = first + 1;
+        }
+      }
+      if (mid < 0) {
+        double clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int i = first; i < last; i++)
+          for (int r = 0; r < 3; r++) { clo[r] = fmin(clo[r], per[idx[i]].bc[r]); chi[r] = fmax(chi[r], per[idx[i]].bc[r]); }
+        int axis = 0;
+        if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
+        if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
+        mid = first + cnt / 2;
+        std::nth_element(idx.begin() + first, idx.begin() + mid, idx.begin() + last,
+                         [&](int a, int b) { return per[a].bc[axis] < per[b].bc[axis]; });
+      }
       const int me = next_node++;
       Box b0, b1;
-      const int c0 = build(first, mid, b0), c1 = build(mid, last, b1);
+      const int c0 = build(first, mid, depth + 1, b0), c1 = build(mid, last, depth + 1, b1);
       float4* N = &F.nodes[(size_t)me * kBvhNodeRows];
-      N[0] = make_float4(down(b0.lo[0]), down(b0.lo[1]), down(b0.lo[2]), up(b0.hi[0]));
-      N[1] = make_float4(up(b0.hi[1]), up(b0.hi[2]), down(b1.lo[0]), down(b1.lo[1]));
-      N[2] = make_float4(down(b1.lo[2]), up(b1.hi[0]), up(b1.hi[1]), up(b1.hi[2]));
-      N[3] = make_float4(up(b0.p1), up(b0.p2), up(b1.p1), up(b1.p2));
+      N[0] = make_float4(down(b0.lo[0]), down(b1.lo[0]), down(b0.lo[1]), down(b1.lo[1]));
+      N[1] = make_float4(down(b0.lo[2]), down(b1.lo[2]), up(b0.hi[0]), up(b1.hi[0]));
+      N[2] = make_float4(up(b0.hi[1]), up(b1.hi[1]), up(b0.hi[2]), up(b1.hi[2]));
       int ci[2] = {c0, c1};
       float cf[2];
       memcpy(cf, ci, sizeof(cf));
+      // x 1.000002: rounding of D^2 in child_entries (pt_bvh.cuh)
+      N[3] = make_float4(up(b0.p1), up(b1.p1), up(b0.p2 * 1.000002), up(b1.p2 * 1.000002));
       N[4] = make_float4(cf[0], cf[1], 0, 0);
       box = merge(b0, b1);
       return me;
     };
     Box root;
-    build(0, n, root);
+    build(0, n, 0, root);
   }
   return F;
 }
@@ -462,18 +521,19 @@ static RaygenConsts make_raygen(const pt_camera_data& c, const pt_lens* lens) {
   return R;
 }
 
-template <bool F, bool L, bool B>
-static int setup_variant1(pt_context* c, int slot) {
-  CU(cudaFuncSetAttribute(k_bounce<F, L, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+template <bool F, bool L>
+static int setup_variant(pt_context* c, int slot) {
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce<F, L, B>, kBounceThreads, c->smem_bytes));
+  if (c->mode) {
+    CU(cudaFuncSetAttribute(k_bounce_bvh<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce_bvh<F, L>, kBvhThreads, c->smem_bytes));
+  } else {
+    CU(cudaFuncSetAttribute(k_bounce<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce<F, L>, kBounceThreads, c->smem_bytes));
+  }
   if (per_sm < 1) { pt_set_error_("k_bounce does not fit on an SM"); return PT_ERR_CUDA; }
   c->grid_blocks[slot] = per_sm * c->sm_count;
   return PT_OK;
-}
-template <bool F, bool L>
-static int setup_variant(pt_context* c, int slot) {
-  return c->mode ? setup_variant1<F, L, true>(c, slot) : setup_variant1<F, L, false>(c, slot);
 }
 
 static int upload_filter(pt_context* c) {
@@ -581,7 +641,7 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
     c->filt_cap = cap;
     c->geom_smem = filt_smem_bytes(cap);
     c->mode = mode;
-    c->smem_bytes = mode == 0 ? c->geom_smem : 0;  // k_bounce: filter geometry
+    c->smem_bytes = mode == 0 ? c->geom_smem : kBvhSmemBytes;  // k_bounce: filter geometry; k_bounce_bvh: the warps' ray pools
     int rc;
     if ((rc = setup_variant<true, false>(c, 0))) return rc;
     if ((rc = setup_variant<true, true>(c, 1))) return rc;
@@ -709,11 +769,16 @@ extern "C" int pt_clear(pt_context* c) {
 
 template <bool F, bool L>
 static cudaError_t launch_bounce(pt_context* c, int slot, const BounceParams& P, uint32_t n_upper, cudaStream_t st) {
-  uint32_t ctas = (n_upper + kBounceThreads - 1) / kBounceThreads;  // one unit per warp at least
   uint32_t grid = (uint32_t)c->grid_blocks[slot];
-  if (ctas < grid) grid = ctas ? ctas : 1;
-  if (c->mode) k_bounce<F, L, true><<<grid, kBounceThreads, c->smem_bytes, st>>>(P);
-  else k_bounce<F, L, false><<<grid, kBounceThreads, c->smem_bytes, st>>>(P);
+  if (c->mode) {
+    const uint32_t ctas = (n_upper + kPool * (kBvhThreads / 32) - 1) / (kPool * (kBvhThreads / 32));  // one pool per warp at least
+    if (ctas < grid) grid = ctas ? ctas : 1;
+    k_bounce_bvh<F, L><<<grid, kBvhThreads, c->smem_bytes, st>>>(P);
+  } else {
+    const uint32_t ctas = (n_upper + kBounceThreads - 1) / kBounceThreads;  // one unit per warp at least
+    if (ctas < grid) grid = ctas ? ctas : 1;
+    k_bounce<F, L><<<grid, kBounceThreads, c->smem_bytes, st>>>(P);
+  }
   c->launches++;
   return cudaGetLastError();
 }

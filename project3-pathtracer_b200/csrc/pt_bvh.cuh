@@ -12,18 +12,22 @@
 //   * Pass 1 (bvh_scan) computes the same (lo1, k1, lo2) as the linear scan would over the geoms it visits; a child is
 //     skipped if its box's entry distance minus the largest world slack is >= lo2 -- nothing below it can change k1
 //     or lower lo2.  The exact test of k1 then decides as usual (resolve in pt_kernels.cuh).
-//   * Pass 2 (bvh_exact, the fallback; rare) is the exact scan restricted to the filter's candidates: every candidate
-//     leaf whose bound does not exceed the best exact distance so far goes through exact_hit; smaller distance wins,
-//     ties go to the lower geom index (the index-order rule of the specification, applied explicitly because the
-//     traversal order is not the index order).
-// Built on the host (pt_api.cu: build_bvh): median split of the centroids along the widest axis, one geom per leaf.
+//   * Pass 2 (the fallback, a few per cent of the rays) is the exact scan restricted to the filter's candidates: every
+//     candidate leaf whose bound does not exceed the best exact distance so far goes through exact_hit; smaller
+//     distance wins, ties go to the lower geom index (the index-order rule of the specification, applied explicitly
+//     because the traversal order is not the index order).  k_bounce_bvh collects the rays that need it and runs them
+//     32 at a time (pt_kernels.cuh); the list kernel runs it on the spot (bvh_exact).
+// Built on the host (pt_api.cu: build_filter): surface-area heuristic, one geom per leaf.
 #pragma once
 #include "pt_filter.cuh"
 
 namespace ptd {
 
-// node = 5 float4:  n0 = (min0.xyz, max0.x)  n1 = (max0.yz, min1.xy)  n2 = (min1.z, max1.xyz)
-//                   n3 = (P1_0, P2_0, P1_1, P2_1)  n4 = int bits (child0, child1, -, -); child >= 0: node, < 0: leaf ~child
+// node = 5 float4, the two children side by side (child 0 in the low half of each float2, child 1 in the high half):
+//   n0 = (min0.x, min1.x | min0.y, min1.y)  n1 = (min0.z, min1.z | max0.x, max1.x)  n2 = (max0.y, max1.y | max0.z, max1.z)
+//   n3 = (P1_0, P1_1 | P2_0, P2_1)  n4 = int bits (child0, child1, -, -); child >= 0: node, < 0: leaf ~child
+// (a 64-byte node -- one P1, P2 per node, the children in n3 -- read 18 % fewer sectors and still ran 12 % slower:
+// profiles/r01_bvh_v2_notes.txt)
 // leaf = 5 float4 (scalar filter record) + int2 (class, geom index):
 //   class 0: l0 = (c.xyz, Wc)  l1 = (Ww, Wr, Ew_c, Ew_w)
 //   class 2: l0 = (c.xyz, Ew_c)  l1 = (Hc.xyz, Ew_w)  l2 = (Hw.xyz, -)
@@ -94,82 +98,117 @@ __device__ __forceinline__ bool leaf_filter(int cls, const float4* __restrict__ 
   return true;
 }
 
-// Entry parameter of the ray into a child's padded box, or +inf if the ray provably misses it.
+// Entry parameters of the ray into the two children's padded boxes (+inf = the ray provably misses the box), both
+// children at once: a node stores its children side by side, so every add / multiply is one packed f32x2
+// instruction (FADD2 / FMUL2 / FFMA2; min / max have no packed form and stay scalar).
 // A NaN (0 * inf) is ignored by fminf / fmaxf, so the affected slab does not constrain: conservative.
-__device__ __forceinline__ float child_entry(float3 bmin, float3 bmax, float p1, float p2, const ScanRay& r) {
-  // D = largest distance from the origin to a point of the box (bounds |o - c| of every geom inside)
-  const float mx = fmaxf(fabsf(bmin.x - r.o.x), fabsf(bmax.x - r.o.x));
-  const float my = fmaxf(fabsf(bmin.y - r.o.y), fabsf(bmax.y - r.o.y));
-  const float mz = fmaxf(fabsf(bmin.z - r.o.z), fabsf(bmax.z - r.o.z));
-  const float D2 = __fmaf_rn(mx, mx, __fmaf_rn(my, my, mz * mz)) * 1.000001f;
-  const float pad = __fmaf_rn(p2, D2, p1 * r.w);
-  // (b - o) * (1/d), subtraction first: with d_i = 0 the two planes give -inf / +inf (origin inside the slab: no
-  // constraint) or the same infinity twice (outside: miss); b/d - o/d would turn the first case into inf - inf
-  const float ax = ((bmin.x - pad) - r.o.x) * r.id.x, bx = ((bmax.x + pad) - r.o.x) * r.id.x;
-  const float ay = ((bmin.y - pad) - r.o.y) * r.id.y, by = ((bmax.y + pad) - r.o.y) * r.id.y;
-  const float az = ((bmin.z - pad) - r.o.z) * r.id.z, bz = ((bmax.z + pad) - r.o.z) * r.id.z;
+__device__ __forceinline__ void child_entries(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const ScanRay& r,
+                                              float& e0, float& e1) {
+  // box planes relative to the origin, subtraction first: with d_i = 0 the two planes of a slab give -inf / +inf
+  // (origin inside the slab: no constraint) or the same infinity twice (outside: miss); b/d - o/d would turn the
+  // first case into inf - inf
+  const f2 nox = bc2(-r.o.x), noy = bc2(-r.o.y), noz = bc2(-r.o.z);
+  const f2 lx = __fadd2_rn(lo2(n0), nox), ly = __fadd2_rn(hi2(n0), noy), lz = __fadd2_rn(lo2(n1), noz);
+  const f2 hx = __fadd2_rn(hi2(n1), nox), hy = __fadd2_rn(lo2(n2), noy), hz = __fadd2_rn(hi2(n2), noz);
+  // D = largest distance from the origin to a point of the box (bounds |o - c| of every geom inside); the rounding
+  // of these few operations is part of P2 (x 1.000002 on the host)
+  const f2 mx = make_float2(fmaxf(fabsf(lx.x), fabsf(hx.x)), fmaxf(fabsf(lx.y), fabsf(hx.y)));
+  const f2 my = make_float2(fmaxf(fabsf(ly.x), fabsf(hy.x)), fmaxf(fabsf(ly.y), fabsf(hy.y)));
+  const f2 mz = make_float2(fmaxf(fabsf(lz.x), fabsf(hz.x)), fmaxf(fabsf(lz.y), fabsf(hz.y)));
+  const f2 D2 = fma2(mx, mx, fma2(my, my, mul2(mz, mz)));
+  const f2 pad = fma2(hi2(n3), D2, mul2(lo2(n3), bc2(r.w)));
+  const f2 npad = neg2(pad), idx = bc2(r.id.x), idy = bc2(r.id.y), idz = bc2(r.id.z);
+  const f2 ax = mul2(__fadd2_rn(lx, npad), idx), bx = mul2(__fadd2_rn(hx, pad), idx);
+  const f2 ay = mul2(__fadd2_rn(ly, npad), idy), by = mul2(__fadd2_rn(hy, pad), idy);
+  const f2 az = mul2(__fadd2_rn(lz, npad), idz), bz = mul2(__fadd2_rn(hz, pad), idz);
   // rounding of the six parameters (a few ulp of |box - o| / |d|) is covered by the 16u*w in P1
-  const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-  const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-  if (tn > tf || tf < 0.0f) return INFINITY;
-  return fmaxf(tn, 0.0f);  // NaN -> 0: "may be entered at once"
+  const float tn0 = fmaxf(fmaxf(fminf(ax.x, bx.x), fminf(ay.x, by.x)), fminf(az.x, bz.x));
+  const float tf0 = fminf(fminf(fmaxf(ax.x, bx.x), fmaxf(ay.x, by.x)), fmaxf(az.x, bz.x));
+  const float tn1 = fmaxf(fmaxf(fminf(ax.y, bx.y), fminf(ay.y, by.y)), fminf(az.y, bz.y));
+  const float tf1 = fminf(fminf(fmaxf(ax.y, bx.y), fmaxf(ay.y, by.y)), fmaxf(az.y, bz.y));
+  e0 = (tn0 > tf0 || tf0 < 0.0f) ? INFINITY : fmaxf(tn0, 0.0f);  // NaN -> 0: "may be entered at once"
+  e1 = (tn1 > tf1 || tf1 < 0.0f) ? INFINITY : fmaxf(tn1, 0.0f);
 }
 
-// One traversal serves both passes.  EXACT = false: filter scan, result in `best` (k1 = leaf index).
+// per-ray constants of a traversal
+struct TravRay {
+  float ewmax;  // largest world slack of any geom, plus room for the rounding differences between a node's slab
+                // parameters and a leaf's own entry parameter (a few ulp of w)
+  float dls;    // |d|, rounded down a little further
+};
+__device__ __forceinline__ TravRay make_trav_ray(const BvhSoA& B, const ScanRay& r) {
+  TravRay t;
+  t.ewmax = __fmaf_rn(B.ew_w_max, r.w, B.ew_c_max) + 1e-6f * r.w;
+  t.dls = r.dl * 0.999996f;
+  return t;
+}
+__device__ __forceinline__ int bvh_root(const BvhSoA& B) { return B.n_leaves == 1 ? ~0 : 0; }  // a single geom: the root is leaf 0
+
+// One step of a traversal: test the leaf `cur` (< 0) or the two children of the node `cur`, then move on.  Returns
+// false when the traversal is finished.  EXACT = false: filter scan, result in `best` (k1 = leaf index).
 // EXACT = true: exact test of every candidate leaf that can still matter, result in `h`.
+// The stack holds at most one entry per level: depth <= kBvhStack by construction (build_bvh).
 template <bool EXACT>
-__device__ __forceinline__ void bvh_traverse(const BvhSoA& B, const GeomSoA& g, const ScanRay& r, f3 o, f3 d, ScanBest& best, Hit& h) {
-  if (B.n_leaves <= 0) return;
-  // largest world slack of any geom, plus room for the rounding differences between a node's slab parameters and a
-  // leaf's own entry parameter (a few ulp of w)
-  const float ewmax = __fmaf_rn(B.ew_w_max, r.w, B.ew_c_max) + 1e-6f * r.w;
-  const float dls = r.dl * 0.999996f;
-  int stack[kBvhStack];
-  int sp = 0;
-  int cur = B.n_leaves == 1 ? ~0 : 0;  // a single geom: the root is leaf 0
-  for (;;) {
-    if (cur < 0) {
-      const int leaf = ~cur;
-      const int2 meta = __ldg(B.leaf_meta + leaf);
-      float lo;
-      if (leaf_filter(meta.x, B.leaves + (size_t)leaf * kBvhLeafRows, r, lo)) {
-        lo = fmaxf(lo, 0.0f);
-        if (!EXACT) {
-          scan_take(best, lo, leaf);
-        } else if (!(lo > h.t)) {
-          const int gi = meta.y;
-          float dist;
-          f3 P;
-          int ncode;
-          if (exact_hit(meta.x < 2 ? 0 : 1, __ldg(g.inv0 + gi), __ldg(g.inv1 + gi), __ldg(g.inv2 + gi), __ldg(g.fwd0 + gi),
-                        __ldg(g.fwd1 + gi), __ldg(g.fwd2 + gi), o, d, dist, P, ncode)) {
-            // specification: scan in index order, keep the strictly smaller positive distance
-            if (dist > 0 && (dist < h.t || (dist == h.t && gi < h.id))) { h.t = dist; h.id = gi; h.p = P; h.ncode = ncode; }
-          }
+__device__ __forceinline__ bool trav_step(const BvhSoA& B, const GeomSoA& g, const ScanRay& r, const TravRay& tr, ScanBest& best, Hit& h,
+                                          int& cur, int& sp, int* stack) {
+  if (cur < 0) {
+    const int leaf = ~cur;
+    const int2 meta = __ldg(B.leaf_meta + leaf);
+    float lo;
+    if (leaf_filter(meta.x, B.leaves + (size_t)leaf * kBvhLeafRows, r, lo)) {
+      lo = fmaxf(lo, 0.0f);
+      if (!EXACT) {
+        scan_take(best, lo, leaf);
+      } else if (!(lo > h.t)) {
+        const int gi = meta.y;
+        float dist;
+        f3 P;
+        int ncode;
+        if (exact_hit(meta.x < 2 ? 0 : 1, __ldg(g.inv0 + gi), __ldg(g.inv1 + gi), __ldg(g.inv2 + gi), __ldg(g.fwd0 + gi),
+                      __ldg(g.fwd1 + gi), __ldg(g.fwd2 + gi), r.o, r.d, dist, P, ncode)) {
+          // specification: scan in index order, keep the strictly smaller positive distance
+          if (dist > 0 && (dist < h.t || (dist == h.t && gi < h.id))) { h.t = dist; h.id = gi; h.p = P; h.ncode = ncode; }
         }
       }
-    } else {
-      const float4* N = B.nodes + (size_t)cur * kBvhNodeRows;
-      const float4 n0 = __ldg(N), n1 = __ldg(N + 1), n2 = __ldg(N + 2), n3 = __ldg(N + 3), n4 = __ldg(N + 4);
-      float e0 = child_entry(make_float3(n0.x, n0.y, n0.z), make_float3(n0.w, n1.x, n1.y), n3.x, n3.y, r);
-      float e1 = child_entry(make_float3(n1.z, n1.w, n2.x), make_float3(n2.y, n2.z, n2.w), n3.z, n3.w, r);
-      // a child whose best possible bound cannot beat the current limit is skipped:
-      //   filter pass: bound >= lo2 changes neither k1 nor lo2;  exact pass: bound > best exact distance (ties may still win)
-      const float b0 = __fmaf_rn(e0, dls, -ewmax), b1 = __fmaf_rn(e1, dls, -ewmax);
-      const bool v0 = e0 < INFINITY && (EXACT ? !(b0 > h.t) : (b0 < best.lo2));
-      const bool v1 = e1 < INFINITY && (EXACT ? !(b1 > h.t) : (b1 < best.lo2));
-      int c0 = __float_as_int(n4.x), c1 = __float_as_int(n4.y);
-      if (v0 && v1) {
-        if (e1 < e0) { const int t = c0; c0 = c1; c1 = t; }  // nearer child first
-        stack[sp++] = c1;  // depth <= ceil(log2 n) <= 32 < kBvhStack by construction (median split)
-        cur = c0;
-        continue;
-      }
-      if (v0 || v1) { cur = v0 ? c0 : c1; continue; }
     }
-    if (sp == 0) break;
-    cur = stack[--sp];
+  } else {
+    const float4* N = B.nodes + (size_t)cur * kBvhNodeRows;
+    const float4 n0 = __ldg(N), n1 = __ldg(N + 1), n2 = __ldg(N + 2), n3 = __ldg(N + 3);
+    const int2 ch = __ldg(reinterpret_cast<const int2*>(N + 4));
+    float e0, e1;
+    child_entries(n0, n1, n2, n3, r, e0, e1);
+    // a child whose best possible bound cannot beat the current limit is skipped:
+    //   filter pass: bound >= lo2 changes neither k1 nor lo2 (a missed box has bound +inf);
+    //   exact pass: bound > best exact distance (ties may still win)
+    const float b0 = __fmaf_rn(e0, tr.dls, -tr.ewmax), b1 = __fmaf_rn(e1, tr.dls, -tr.ewmax);
+    const bool v0 = EXACT ? (e0 < INFINITY && !(b0 > h.t)) : (b0 < best.lo2);
+    const bool v1 = EXACT ? (e1 < INFINITY && !(b1 > h.t)) : (b1 < best.lo2);
+    if (v0 || v1) {
+      const bool second = !v0 || (v1 && e1 < e0);  // nearer (or only) child first
+      const int near_child = second ? ch.y : ch.x, far_child = second ? ch.x : ch.y;
+      if (v0 && v1) {
+        stack[sp++] = far_child;
+#ifdef PT_BVH_PREFETCH
+        if (far_child >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(B.nodes + (size_t)far_child * kBvhNodeRows));
+#endif
+      }
+      cur = near_child;
+      return true;
+    }
   }
+  if (sp == 0) return false;
+  cur = stack[--sp];
+  return true;
+}
+
+// a whole traversal by one lane (parity entry points, the deferred exact pass)
+template <bool EXACT>
+__device__ __forceinline__ void bvh_traverse(const BvhSoA& B, const GeomSoA& g, const ScanRay& r, ScanBest& best, Hit& h) {
+  if (B.n_leaves <= 0) return;
+  const TravRay tr = make_trav_ray(B, r);
+  int stack[kBvhStack];
+  int sp = 0, cur = bvh_root(B);
+  while (trav_step<EXACT>(B, g, r, tr, best, h, cur, sp, stack)) {}
 }
 
 // the exact pass on its own (fallback of resolve_bvh; rare, so not inlined)
@@ -177,24 +216,29 @@ __device__ __noinline__ void bvh_exact(const BvhSoA B, const GeomSoA g, f3 o, f3
   const ScanRay r = make_scan_ray(o, d, r_scene, true);
   ScanBest unused;
   scan_init(unused);
-  bvh_traverse<true>(B, g, r, o, d, unused, h);
+  bvh_traverse<true>(B, g, r, unused, h);
 }
 
-// Resolve a finished BVH filter pass: exact test of the best candidate leaf, accepted if it is a hit closer than
-// every other geom's lower bound; otherwise the exact pass.  Returns true if the fallback ran (statistics only).
-__device__ __forceinline__ bool resolve_bvh(const ScanBest& best, const BvhSoA& B, const GeomSoA& g, float r_scene, f3 o, f3 d, Hit& h) {
-  if (best.k1 < 0) return false;  // every geom is a proven miss
-  const int2 meta = __ldg(B.leaf_meta + best.k1);
+// The exact test of the filter pass's best candidate leaf k1: confirmed (h filled in) if it is a hit closer than every
+// other geom's lower bound lo2.
+__device__ __forceinline__ bool confirm_candidate(int k1, float lo2, const BvhSoA& B, const GeomSoA& g, f3 o, f3 d, Hit& h) {
+  const int2 meta = __ldg(B.leaf_meta + k1);
   const int gi = meta.y;
   float dist;
   f3 P;
   int ncode;
   const bool hit = exact_hit(meta.x < 2 ? 0 : 1, __ldg(g.inv0 + gi), __ldg(g.inv1 + gi), __ldg(g.inv2 + gi), __ldg(g.fwd0 + gi),
                              __ldg(g.fwd1 + gi), __ldg(g.fwd2 + gi), o, d, dist, P, ncode);
-  if (hit && dist > 0 && dist < best.lo2) {
-    h.t = dist; h.id = gi; h.p = P; h.ncode = ncode;
-    return false;
-  }
+  if (!(hit && dist > 0 && dist < lo2)) return false;
+  h.t = dist; h.id = gi; h.p = P; h.ncode = ncode;
+  return true;
+}
+
+// Resolve a finished BVH filter pass on the spot (parity entry point; k_bounce_bvh defers the fallback instead):
+// the confirmed candidate, otherwise the exact pass.  Returns true if the fallback ran (statistics only).
+__device__ __forceinline__ bool resolve_bvh(const ScanBest& best, const BvhSoA& B, const GeomSoA& g, float r_scene, f3 o, f3 d, Hit& h) {
+  if (best.k1 < 0) return false;  // every geom is a proven miss
+  if (confirm_candidate(best.k1, best.lo2, B, g, o, d, h)) return false;
   bvh_exact(B, g, o, d, r_scene, h);
   return true;
 }

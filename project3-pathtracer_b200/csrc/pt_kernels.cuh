@@ -1,6 +1,6 @@
 // pt_kernels.cuh -- the wavefront kernels (sm_100a).
 //
-//   k_bounce<FIRST,LAST>  one path segment for every live path of the wavefront, fused:
+//   k_bounce<FIRST,LAST>  (k_bounce_bvh for scenes with many geoms) one path segment for every live path of the wavefront, fused:
 //                           [FIRST: raygen + depth of field]  (raycastFromCameraKernel, src/raytraceKernel.cu:40-45)
 //                           closest hit over SoA geometry staged in shared memory (src/intersections.h:74-117)
 //                           BSDF sampling with Philox (calculateBSDF, src/interactions.h:99-104)
@@ -133,18 +133,60 @@ __device__ __forceinline__ uint32_t atom_add_u32(uint32_t* p, uint32_t v) {  // 
 #endif
 constexpr uint32_t kTicketUnits = PT_TICKET_UNITS;
 
-// BVH = false: few geoms (every BASELINE config but the 10k one): linear scan over the filter pairs staged in shared
-//              memory;  BVH = true: the hierarchy of pt_bvh.cuh, read through L1/L2
-template <bool FIRST, bool LAST, bool BVH>
-__global__ void __launch_bounds__(kBounceThreads, BVH ? (3 * 256 / kBounceThreads) : PT_MIN_BLOCKS) k_bounce(const __grid_constant__ BounceParams P) {
+// The second half of a segment, by a whole warp: material lookup, reservation of the unit's output slots, BSDF
+// sampling, radiance of finished paths, survivors written to base + rank.  `hit` lanes carry a closest hit in h.
+// TABLE: normals from the per-geom table (few geoms, L1-resident) or from the winner's own rows (many geoms).
+template <bool LAST, bool TABLE>
+__device__ __forceinline__ void shade_and_compact(const BounceParams& P, uint32_t lane, bool hit, const Hit& h, f3 o, f3 d, f3 thr,
+                                                  uint32_t pixel, uint32_t sample) {
+  // a path survives this segment unless it left the scene or reached a light; the slot of the unit's survivors
+  // is reserved before shading so that the atomic's latency hides behind it
+  int mat = 0;
+  float4 md = make_float4(0, 0, 0, 0);  // (absorption.yz, reducedScatter, emittance)
+  if (hit) {
+    mat = __ldg(P.g.meta + h.id).y;
+    md = __ldg(P.mats + 4 * mat + 3);
+  }
+  const bool alive = hit && !(md.w > 0);
+  uint32_t base_raw = 0, ballot = 0;
+  if (!LAST) {
+    ballot = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0 && ballot) base_raw = atom_add_u32(&P.ctrl->count[P.depth + 1], (uint32_t)__popc(ballot));
+  }
+  if (hit) {
+    const int gi = h.id;
+    const f3 n = TABLE ? hit_normal_table(P.normals, h)
+                       : hit_normal(__ldg(P.g.fwd0 + gi), __ldg(P.g.fwd1 + gi), __ldg(P.g.fwd2 + gi), h);
+    MatRows m;
+    m.a = __ldg(P.mats + 4 * mat); m.b = __ldg(P.mats + 4 * mat + 1); m.c = __ldg(P.mats + 4 * mat + 2); m.d = md;
+    f3 L;
+    const int kind = shade(m, P.g, gi, h.p, n, P.seed, pixel, sample, P.depth, o, d, thr, L);
+    if (kind == 3) {
+      float* px = reinterpret_cast<float*>(P.accum + pixel);
+      atomicAdd(px + 0, L.x);
+      atomicAdd(px + 1, L.y);
+      atomicAdd(px + 2, L.z);
+    }
+  }
+  if (!LAST) {
+    const uint32_t slot = __shfl_sync(0xffffffffu, base_raw, 0) + __popc(ballot & ((1u << lane) - 1u));
+    if (alive) {
+      __stcs(P.out_o + slot, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
+      __stcs(P.out_d + slot, make_float4(d.x, d.y, d.z, __uint_as_float(sample)));
+      __stcs(P.out_t + slot, make_float4(thr.x, thr.y, thr.z, 0.0f));
+    }
+  }
+}
+
+// Few geoms (every BASELINE config but the 10k one): linear scan over the filter pairs staged in shared memory.
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_bounce(const __grid_constant__ BounceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31u;
-  // ---- filter geometry: staged once per CTA (scenes with many geoms use the hierarchy instead) ----
+  // ---- filter geometry: staged once per CTA ----
   const float4* const fs = reinterpret_cast<const float4*>(smem_raw);
-  if (!BVH) {
-    stage_filt(P.filt, 0, P.filt.end[3], reinterpret_cast<float4*>(smem_raw));
-    __syncthreads();  // the only CTA-wide barrier
-  }
+  stage_filt(P.filt, 0, P.filt.end[3], reinterpret_cast<float4*>(smem_raw));
+  __syncthreads();  // the only CTA-wide barrier
 
   const uint32_t n_in = FIRST ? P.n_first : P.ctrl->count[P.depth];
   if (FIRST && blockIdx.x == 0 && threadIdx.x == 0) P.ctrl->count[0] = n_in;
@@ -155,12 +197,11 @@ __global__ void __launch_bounds__(kBounceThreads, BVH ? (3 * 256 / kBounceThread
   if (lane == 0) next_raw = atom_add_u32(ticket, 1u);
 
   for (;;) {
-    constexpr uint32_t kTU = BVH ? 1u : kTicketUnits;  // traversal times vary too much for multi-unit tickets
-    const uint32_t unit0 = __shfl_sync(0xffffffffu, next_raw, 0) * kTU;
+    const uint32_t unit0 = __shfl_sync(0xffffffffu, next_raw, 0) * kTicketUnits;
     if (unit0 >= n_units) break;
     if (lane == 0) next_raw = atom_add_u32(ticket, 1u);  // consumed after this ticket's units: its latency is hidden
 #pragma unroll 1
-    for (uint32_t unit = unit0; unit < min(unit0 + kTU, n_units); unit++) {
+    for (uint32_t unit = unit0; unit < min(unit0 + kTicketUnits, n_units); unit++) {
     const uint32_t idx = unit * kUnit + lane;
     const bool valid = idx < n_in;
 
@@ -184,59 +225,193 @@ __global__ void __launch_bounds__(kBounceThreads, BVH ? (3 * 256 / kBounceThread
     if (valid) {
       ScanBest best;
       scan_init(best);
-      bool fell_back;
-      if (BVH) {
-        const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene, true);
-        bvh_traverse<false>(P.bvh, P.g, ray, o, d, best, h);
-        fell_back = resolve_bvh(best, P.bvh, P.g, P.filt.r_scene, o, d, h);
-      } else {
-        const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene, P.filt.end[2] > P.filt.end[1]);
-        filter_scan(fs, 0, P.filt.end[3], P.filt.end, ray, best);
-        fell_back = resolve_scan(best, P.filt, P.g, P.n_geoms, o, d, h);
-      }
-      if (fell_back) atomicAdd(&P.ctrl->fallbacks, 1u);
+      const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene, P.filt.end[2] > P.filt.end[1]);
+      filter_scan(fs, 0, P.filt.end[3], P.filt.end, ray, best);
+      if (resolve_scan(best, P.filt, P.g, P.n_geoms, o, d, h)) atomicAdd(&P.ctrl->fallbacks, 1u);
     }
 
-    // a path survives this segment unless it left the scene or reached a light; the slot of the unit's survivors
-    // is reserved before shading so that the atomic's latency hides behind it
-    const bool hit = valid && h.id >= 0;
-    int mat = 0;
-    float4 md = make_float4(0, 0, 0, 0);  // (absorption.yz, reducedScatter, emittance)
-    if (hit) {
-      mat = __ldg(P.g.meta + h.id).y;
-      md = __ldg(P.mats + 4 * mat + 3);
+    shade_and_compact<LAST, true>(P, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample);
     }
-    const bool alive = hit && !(md.w > 0);
-    uint32_t base_raw = 0, ballot = 0;
-    if (!LAST) {
-      ballot = __ballot_sync(0xffffffffu, alive);
-      if (lane == 0 && ballot) base_raw = atom_add_u32(&P.ctrl->count[P.depth + 1], (uint32_t)__popc(ballot));
+  }
+}
+
+// Many geoms (BASELINE config "10k spheres/cubes"): the hierarchy of pt_bvh.cuh, read through L1/L2.  A ray's
+// traversal takes anything from a handful to hundreds of steps, and neighbouring paths stop being neighbours in space
+// after the first bounce, so a warp that walked 32 rays in lock step kept 9 of its 32 lanes busy on average
+// (profiles/r01_bvh_v1_*).  Work decomposition here, per warp:
+//   phase 0  a ticket = a POOL of kPoolUnits x 32 consecutive paths; their rays are generated / loaded (coalesced) into
+//            the warp's slice of shared memory;
+//   phase 1  filter traversal of the pool: every lane walks one ray at a time and, when it is done, takes the next ray
+//            of the pool (lanes are refilled once kRefillMin of them are idle, so the refill code runs rarely);
+//            the result (k1, lo2) of a ray goes to shared memory;
+//   phase 2  unit by unit, all 32 lanes together: exact test of each path's candidate k1, shading, compaction --
+//            as in k_bounce.  A path whose candidate is not confirmed (the fallback, ~3 % of the paths) is NOT
+//            re-traversed on the spot -- that would occupy the warp with one or two live lanes for a whole traversal
+//            -- but DEFERRED: its index goes to a per-warp list, and whenever 32 have gathered they are run as a unit
+//            of their own through the exact traversal, shading and compaction.
+#ifndef PT_BVH_POOL_UNITS
+#define PT_BVH_POOL_UNITS 4
+#endif
+#ifndef PT_BVH_REFILL_MIN
+#define PT_BVH_REFILL_MIN 8
+#endif
+constexpr int kPoolUnits = PT_BVH_POOL_UNITS, kPool = kPoolUnits * kUnit, kRefillMin = PT_BVH_REFILL_MIN, kDeferCap = 2 * kUnit;
+#ifndef PT_BVH_THREADS
+#define PT_BVH_THREADS 256
+#endif
+#ifndef PT_BVH_MIN_BLOCKS
+#define PT_BVH_MIN_BLOCKS 3
+#endif
+constexpr int kBvhThreads = PT_BVH_THREADS;
+struct BvhWarpSmem {
+  float4 ro[kPool];           // (origin.xyz, pixel)
+  float4 rd[kPool];           // (direction.xyz, sample)
+  float2 res[kPool];          // (lo2, bits of k1)
+  uint32_t defer[kDeferCap];  // indices (into the wavefront's input) of paths waiting for the exact traversal
+};
+constexpr size_t kBvhSmemBytes = sizeof(BvhWarpSmem) * (kBvhThreads / 32);
+
+template <bool FIRST>
+__device__ __forceinline__ void load_path(const BounceParams& P, uint32_t idx, f3& o, f3& d, uint32_t& pixel, uint32_t& sample) {
+  if (FIRST) {
+    pixel = idx % P.cam.npix;
+    sample = P.first_sample + idx / P.cam.npix;
+    raygen(P.cam, P.seed, pixel, sample, o, d);
+  } else {
+    const float4 a = __ldg(P.in_o + idx), b = __ldg(P.in_d + idx);
+    o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
+    d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
+  }
+}
+
+// `n` (<= 32, warp-uniform) deferred paths, taken from the top of the warp's list: exact traversal, shading, compaction
+template <bool FIRST, bool LAST>
+__device__ __noinline__ void run_deferred(const BounceParams& P, const uint32_t* list, uint32_t n) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const bool valid = lane < n;
+  f3 o = mk(0, 0, 0), d = mk(0, 0, 1), thr = mk(1, 1, 1);
+  uint32_t pixel = 0, sample = 0;
+  Hit h;
+  h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
+  if (valid) {
+    const uint32_t idx = list[lane];
+    load_path<FIRST>(P, idx, o, d, pixel, sample);
+    if (!FIRST) { const float4 c = __ldg(P.in_t + idx); thr = mk(c.x, c.y, c.z); }
+    const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene, true);
+    ScanBest unused;
+    scan_init(unused);
+    bvh_traverse<true>(P.bvh, P.g, ray, unused, h);
+  }
+  if (lane == 0) atomicAdd(&P.ctrl->fallbacks, n);
+  shade_and_compact<LAST, false>(P, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample);
+}
+
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(const __grid_constant__ BounceParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t lane = threadIdx.x & 31u;
+  BvhWarpSmem& S = reinterpret_cast<BvhWarpSmem*>(smem_raw)[threadIdx.x >> 5];
+
+  const uint32_t n_in = FIRST ? P.n_first : P.ctrl->count[P.depth];
+  if (FIRST && blockIdx.x == 0 && threadIdx.x == 0) P.ctrl->count[0] = n_in;
+  uint32_t* const ticket = &P.ctrl->tile_ctr[P.depth];
+  uint32_t n_defer = 0;  // warp-uniform
+
+  uint32_t next_raw = 0;  // lane 0: the ticket taken ahead of time
+  if (lane == 0) next_raw = atom_add_u32(ticket, 1u);
+
+  for (;;) {
+    const uint64_t base64 = (uint64_t)__shfl_sync(0xffffffffu, next_raw, 0) * kPool;
+    if (base64 >= n_in) break;
+    const uint32_t base = (uint32_t)base64;
+    if (lane == 0) next_raw = atom_add_u32(ticket, 1u);
+    const uint32_t n_pool = min((uint32_t)kPool, n_in - base);
+
+    // ---- phase 0: the pool's rays ----
+#pragma unroll 1
+    for (uint32_t j = lane; j < n_pool; j += kUnit) {
+      f3 o, d;
+      uint32_t pixel, sample;
+      load_path<FIRST>(P, base + j, o, d, pixel, sample);
+      S.ro[j] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
+      S.rd[j] = make_float4(d.x, d.y, d.z, __uint_as_float(sample));
     }
-    if (hit) {
-      const int gi = h.id;
-      // few geoms: the per-geom table (L1-resident); many geoms: from the winner's rows, which the exact test just loaded
-      const f3 n = BVH ? hit_normal(__ldg(P.g.fwd0 + gi), __ldg(P.g.fwd1 + gi), __ldg(P.g.fwd2 + gi), h)
-                       : hit_normal_table(P.normals, h);
-      MatRows m;
-      m.a = __ldg(P.mats + 4 * mat); m.b = __ldg(P.mats + 4 * mat + 1); m.c = __ldg(P.mats + 4 * mat + 2); m.d = md;
-      f3 L;
-      const int kind = shade(m, P.g, gi, h.p, n, P.seed, pixel, sample, P.depth, o, d, thr, L);
-      if (kind == 3) {
-        float* px = reinterpret_cast<float*>(P.accum + pixel);
-        atomicAdd(px + 0, L.x);
-        atomicAdd(px + 1, L.y);
-        atomicAdd(px + 2, L.z);
+    __syncwarp();
+
+    // ---- phase 1: filter traversal; idle lanes take the next rays of the pool ----
+    {
+      uint32_t next = 0;  // warp-uniform: first ray of the pool nobody has taken yet
+      int ray = -1;       // this lane's ray, -1 = idle
+      ScanRay r;
+      TravRay tr;
+      ScanBest best;
+      Hit unused;
+      int stack[kBvhStack];
+      int sp = 0, cur = 0;
+      r = make_scan_ray(mk(0, 0, 0), mk(0, 0, 1), 0.0f, true);
+      tr = make_trav_ray(P.bvh, r);
+      scan_init(best);
+      for (;;) {
+        const uint32_t idle = __ballot_sync(0xffffffffu, ray < 0);
+        if (idle) {
+          if (next < n_pool && (__popc(idle) >= kRefillMin || idle == 0xffffffffu)) {
+            const uint32_t j = next + __popc(idle & ((1u << lane) - 1u));
+            if (ray < 0 && j < n_pool) {
+              ray = (int)j;
+              const float4 a = S.ro[j], b = S.rd[j];
+              r = make_scan_ray(mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), P.filt.r_scene, true);
+              tr = make_trav_ray(P.bvh, r);
+              scan_init(best);
+              sp = 0;
+              cur = bvh_root(P.bvh);
+            }
+            next += __popc(idle);
+          } else if (idle == 0xffffffffu) {
+            break;
+          }
+        }
+        if (ray >= 0 && !trav_step<false>(P.bvh, P.g, r, tr, best, unused, cur, sp, stack)) {
+          S.res[ray] = make_float2(best.lo2, __int_as_float(best.k1));
+          ray = -1;
+        }
       }
     }
-    if (!LAST) {
-      const uint32_t slot = __shfl_sync(0xffffffffu, base_raw, 0) + __popc(ballot & ((1u << lane) - 1u));
-      if (alive) {
-        __stcs(P.out_o + slot, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
-        __stcs(P.out_d + slot, make_float4(d.x, d.y, d.z, __uint_as_float(sample)));
-        __stcs(P.out_t + slot, make_float4(thr.x, thr.y, thr.z, 0.0f));
+    __syncwarp();
+
+    // ---- phase 2: exact test of the candidates, shading, compaction; unit by unit ----
+#pragma unroll 1
+    for (uint32_t j0 = 0; j0 < n_pool; j0 += kUnit) {
+      const uint32_t j = j0 + lane;
+      const bool valid = j < n_pool;
+      f3 o = mk(0, 0, 0), d = mk(0, 0, 1), thr = mk(1, 1, 1);
+      uint32_t pixel = 0, sample = 0;
+      Hit h;
+      h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
+      bool defer = false;
+      if (valid) {
+        const float4 a = S.ro[j], b = S.rd[j];
+        const float2 res = S.res[j];
+        o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
+        d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
+        if (!FIRST) { const float4 c = __ldcs(P.in_t + base + j); thr = mk(c.x, c.y, c.z); }
+        const int k1 = __float_as_int(res.y);
+        if (k1 >= 0) defer = !confirm_candidate(k1, res.x, P.bvh, P.g, o, d, h);  // k1 < 0: every geom is a proven miss
+      }
+      const uint32_t dmask = __ballot_sync(0xffffffffu, defer);
+      if (defer) S.defer[n_defer + __popc(dmask & ((1u << lane) - 1u))] = base + j;
+      n_defer += __popc(dmask);
+      shade_and_compact<LAST, false>(P, lane, valid && !defer && h.id >= 0, h, o, d, thr, pixel, sample);
+      if (n_defer >= kUnit) {
+        __syncwarp();
+        n_defer -= kUnit;
+        run_deferred<FIRST, LAST>(P, S.defer + n_defer, kUnit);
+        __syncwarp();
       }
     }
-    }
+  }
+  if (n_defer) {
+    __syncwarp();
+    run_deferred<FIRST, LAST>(P, S.defer, n_defer);
   }
 }
 
@@ -293,7 +468,7 @@ __global__ void __launch_bounds__(kTile) k_intersect_list(GeomSoA g, int n_geoms
       const ScanRay ray = make_scan_ray(oo, dd, filt.r_scene, true);
       ScanBest best;
       scan_init(best);
-      bvh_traverse<false>(bvh, g, ray, oo, dd, best, h);
+      bvh_traverse<false>(bvh, g, ray, best, h);
       if (resolve_bvh(best, bvh, g, filt.r_scene, oo, dd, h)) atomicAdd(fallbacks, 1ull);
     }
   } else {

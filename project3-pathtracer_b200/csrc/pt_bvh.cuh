@@ -27,7 +27,7 @@ namespace ptd {
 //   n0 = (min0.x, min1.x | min0.y, min1.y)  n1 = (min0.z, min1.z | max0.x, max1.x)  n2 = (max0.y, max1.y | max0.z, max1.z)
 //   n3 = (P1_0, P1_1 | P2_0, P2_1)  n4 = int bits (child0, child1, -, -); child >= 0: node, < 0: leaf ~child
 // (a 64-byte node -- one P1, P2 per node, the children in n3 -- read 18 % fewer sectors and still ran 12 % slower:
-// profiles/r01_bvh_v2_notes.txt)
+// profiles/r01_bvh_notes.txt)
 // leaf = 5 float4 (scalar filter record) + int2 (class, geom index):
 //   class 0: l0 = (c.xyz, Wc)  l1 = (Ww, Wr, Ew_c, Ew_w)
 //   class 2: l0 = (c.xyz, Ew_c)  l1 = (Hc.xyz, Ew_w)  l2 = (Hw.xyz, -)

@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_bounce(const 
 // Many geoms (BASELINE config "10k spheres/cubes"): the hierarchy of pt_bvh.cuh, read through L1/L2.  A ray's
 // traversal takes anything from a handful to hundreds of steps, and neighbouring paths stop being neighbours in space
 // after the first bounce, so a warp that walked 32 rays in lock step kept 9 of its 32 lanes busy on average
-// (profiles/r01_bvh_v1_*).  Work decomposition here, per warp:
+// (profiles/r01_bvh_v1_metrics.txt).  Work decomposition here, per warp:
 //   phase 0  a ticket = a POOL of kPoolUnits x 32 consecutive paths; their rays are generated / loaded (coalesced) into
 //            the warp's slice of shared memory;
 //   phase 1  filter traversal of the pool: every lane walks one ray at a time and, when it is done, takes the next ray

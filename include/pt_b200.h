@@ -169,6 +169,22 @@ int pt_filter_stats(pt_context* ctx, uint64_t* fallbacks);
  * operators; bad[0..2] = number of differing results of each (must be 0) */
 int pt_selftest_math(int device, uint64_t bad[3]);
 
+/* ---- surface-point / direction sampling and absorption (host buffers; one launch each) ---- */
+/* getRandomPointOnCube (src/intersections.h:133-175, implemented there: results are bit-identical to the reference's
+ * host build, including its right-to-left argument evaluation order) and getRandomPointOnSphere (stub at :179-182;
+ * uniform on the object-space sphere of radius .5), chosen by geom->type.  One world-space point per float seed:
+ * generator = thrust minstd seeded with hash((unsigned)seed) like the reference; seeds must lie in [0, 2^32). */
+int pt_random_points_on_geom(int device, const pt_static_geom* geom, int n, const float* seeds, float* points);
+/* the same samplers driven by caller-supplied uniforms in [0,1): u = n x 3 (face roulette, two in-face coordinates
+ * for a cube; z and azimuth for a sphere, third ignored) */
+int pt_points_on_geom_u(int device, const pt_static_geom* geom, int n, const float* u, float* points);
+/* getRandomDirectionInSphere (stub at src/interactions.h:93-95): uniform unit vectors from (xi1, xi2) */
+int pt_random_directions_in_sphere(int device, int n, const float* xi1, const float* xi2, float* dirs);
+/* calculateTransmission (stub at src/interactions.h:31-33): Beer-Lambert exp(-absorption * distance) per channel;
+ * absorption = n x 3, distance = n.  pt_render applies it to every segment that runs inside a refractive geom whose
+ * material has ABSCOEFF > 0. */
+int pt_calculate_transmission(int device, int n, const float* absorption, const float* distance, float* out);
+
 /* ---- scene file and image file (host side; same formats as the reference) ---- */
 typedef struct pt_scene pt_scene;
 /* scene::scene(string), src/scene.cpp:11-35.  rotat_degrees = 0 reproduces the reference exactly (ROTAT is

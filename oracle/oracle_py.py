@@ -134,6 +134,32 @@ class Oracle:
         self.lib.or_getRadiuses(_p(g), _p(out))
         return out
 
+    def random_points(self, geom, seeds):
+        """getRandomPointOnCube / getRandomPointOnSphere (by geom type) for every float seed"""
+        g, sd = np.ascontiguousarray(geom), _f32(seeds).ravel()
+        out = np.zeros((sd.size, 3), np.float32)
+        self.lib.or_random_points_batch(_p(g), C.c_int(sd.size), _p(sd), _p(out))
+        return out
+
+    def points_u(self, geom, u):
+        """the same samplers driven by given uniforms, u = (n, 3)"""
+        g, u = np.ascontiguousarray(geom), _f32(u).reshape(-1, 3)
+        out = np.zeros_like(u)
+        self.lib.or_points_u_batch(_p(g), C.c_int(u.shape[0]), _p(u), _p(out))
+        return out
+
+    def sphere_dirs(self, xi1, xi2):
+        xi1, xi2 = _f32(xi1).ravel(), _f32(xi2).ravel()
+        out = np.zeros((xi1.size, 3), np.float32)
+        self.lib.or_sphere_dirs_batch(C.c_int(xi1.size), _p(xi1), _p(xi2), _p(out))
+        return out
+
+    def transmission(self, absorption, distance):
+        a, d = _f32(absorption).reshape(-1, 3), _f32(distance).ravel()
+        out = np.zeros_like(a)
+        self.lib.or_transmission_batch(C.c_int(d.size), _p(a), _p(d), _p(out))
+        return out
+
     def intersect_one(self, geom, which, o, d):
         """rays (n,3) against one geom with the sphere (0) or box (1) test."""
         g = np.ascontiguousarray(geom)
@@ -285,6 +311,17 @@ class Ref:
         xi1, xi2 = _f32(xi1).ravel(), _f32(xi2).ravel()
         out = np.zeros_like(normal)
         self.lib.ref_hemisphere_batch(C.c_int(normal.shape[0]), _p(normal), _p(xi1), _p(xi2), _p(out))
+        return out
+
+    def random_points_on_cube(self, geom, seeds):
+        g, sd = np.ascontiguousarray(geom), _f32(seeds).ravel()
+        out = np.zeros((sd.size, 3), np.float32)
+        self.lib.ref_getRandomPointOnCube_batch(_p(g), C.c_int(sd.size), _p(sd), _p(out))
+        return out
+
+    def sampling_stubs(self):
+        out = np.zeros(9, np.float32)
+        self.lib.ref_sampling_stubs(_p(out))
         return out
 
     def bsdf_stub(self):

@@ -299,6 +299,134 @@ void or_raygen(const or_camera_data* cam, const or_lens* lens, uint64_t seed, ui
   st3(d, dir);
 }
 
+/* ---- surface-point / direction sampling and absorption (a12, a13, a15, a20) ---- */
+
+/* (R) thrust::default_random_engine = minstd_rand = LCG(48271, 0, 2^31-1) as the reference seeds and draws it
+ * (src/intersections.h:135-137, src/raytraceKernel.cu:32-33; thrust/random/detail/linear_congruential_engine.inl:
+ * seed s -> s mod m, 0 -> 1) and thrust::uniform_real_distribution<float>(a,b)
+ * (detail/uniform_real_distribution.inl): (float)(x - min) / (1.0f + (float)(max - min)) * (b - a) + a. */
+typedef struct { uint32_t x; } minstd;
+static inline void minstd_seed(minstd* r, uint32_t s) {
+  uint32_t v = s % 2147483647u;
+  r->x = v == 0 ? 1u : v;
+}
+static inline float minstd_uniform(minstd* r, float a, float b) {
+  r->x = (uint32_t)(((uint64_t)r->x * 48271u) % 2147483647u);
+  float res = (float)(r->x - 1u);
+  res /= (1.0f + (float)2147483645u);
+  return (res * (b - a)) + a;
+}
+
+/* body of src/intersections.h:140-172 given the three draws: face by area-weighted roulette, then the two
+ * in-face coordinates (a = first vec3 argument that is random, b = second) */
+static inline v3 cube_point_body(const or_static_geom* g, float roulette, float a, float b) {
+  float radii[3];
+  or_getRadiuses(g, radii);
+  float side1 = radii[0] * radii[1] * 4.0f;
+  float side2 = radii[2] * radii[1] * 4.0f;
+  float side3 = radii[0] * radii[2] * 4.0f;
+  float totalarea = 2.0f * (side1 + side2 + side3);
+  v3 point;
+  if (roulette < (side1 / totalarea)) point = V(a, b, .5f);
+  else if (roulette < ((side1 * 2) / totalarea)) point = V(a, b, -.5f);
+  else if (roulette < (((side1 * 2) + (side2)) / totalarea)) point = V(.5f, a, b);
+  else if (roulette < (((side1 * 2) + (side2 * 2)) / totalarea)) point = V(-.5f, a, b);
+  else if (roulette < (((side1 * 2) + (side2 * 2) + (side3)) / totalarea)) point = V(a, .5f, b);
+  else point = V(a, -.5f, b);
+  return mulMV(g->transform, point.x, point.y, point.z, 1.0f);
+}
+
+/* (R) getRandomPointOnCube, src/intersections.h:133-175, as the reference's HOST build behaves: the two u02(rng)
+ * arguments of each glm::vec3(...) are evaluated right to left by g++, so the SECOND random
+ * coordinate is drawn first.  randomSeed is converted float -> unsigned (defined for 0 <= seed < 2^32). */
+void or_getRandomPointOnCube(const or_static_geom* g, float randomSeed, float out[3]) {
+  minstd rng;
+  minstd_seed(&rng, or_hash((unsigned int)randomSeed));
+  float roulette = minstd_uniform(&rng, 0.0f, 1.0f);
+  float b = minstd_uniform(&rng, -0.5f, 0.5f);
+  float a = minstd_uniform(&rng, -0.5f, 0.5f);
+  st3(out, cube_point_body(g, roulette, a, b));
+}
+
+/* (S) the same sampler driven by three given uniforms in [0,1) (the path loop feeds it Philox numbers) */
+void or_cube_point_u(const or_static_geom* g, float u0, float u1, float u2, float out[3]) {
+  st3(out, cube_point_body(g, u0, u1 - 0.5f, u2 - 0.5f));
+}
+
+/* (S) uniform direction on the unit sphere from two uniforms: z = 1 - 2*xi1, azimuth 2*pi*xi2
+ * (getRandomDirectionInSphere, stub at src/interactions.h:93-95) */
+static inline v3 sphere_dir(float xi1, float xi2) {
+  float z = 1.0f - 2.0f * xi1;
+  float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+  float sn, cs;
+  or_sincos_2pi(xi2, &sn, &cs);
+  return V(r * cs, r * sn, z);
+}
+void or_getRandomDirectionInSphere(float xi1, float xi2, float out[3]) { st3(out, sphere_dir(xi1, xi2)); }
+
+/* (S) uniform point on the unit sphere of radius .5 in object space, mapped to world space like the cube sampler */
+void or_sphere_point_u(const or_static_geom* g, float u0, float u1, float out[3]) {
+  v3 d = sphere_dir(u0, u1);
+  st3(out, mulMV(g->transform, 0.5f * d.x, 0.5f * d.y, 0.5f * d.z, 1.0f));
+}
+/* (S) getRandomPointOnSphere (stub at src/intersections.h:179-182): same generator construction as the cube sampler,
+ * two draws in statement order */
+void or_getRandomPointOnSphere(const or_static_geom* g, float randomSeed, float out[3]) {
+  minstd rng;
+  minstd_seed(&rng, or_hash((unsigned int)randomSeed));
+  float u0 = minstd_uniform(&rng, 0.0f, 1.0f);
+  float u1 = minstd_uniform(&rng, 0.0f, 1.0f);
+  or_sphere_point_u(g, u0, u1, out);
+}
+
+/* (S) exp(x) in binary32 with +,-,* only (Cody-Waite reduction by ln2 = 0.693359375 - 2.12194440e-4, degree-5
+ * polynomial of the classic single-precision expf, scale by 2^k through the exponent field): the same operation
+ * sequence in the CUDA kernels, so absorption is bit-reproducible (libm and CUDA expf are not).  x <= -87 (and NaN)
+ * gives 0, x is clamped to 88 from above. */
+float or_exp(float x) {
+  if (!(x > -87.0f)) return 0.0f;
+  if (x > 88.0f) x = 88.0f;
+  float kf = (float)(int)(x * 1.44269504f + (x < 0 ? -0.5f : 0.5f));
+  float r = (x - kf * 0.693359375f) - kf * -2.12194440e-4f;
+  float p = 1.9875691500e-4f;
+  p = p * r + 1.3981999507e-3f;
+  p = p * r + 8.3334519073e-3f;
+  p = p * r + 4.1665795894e-2f;
+  p = p * r + 1.6666665459e-1f;
+  p = p * r + 5.0000001201e-1f;
+  float y = (p * (r * r) + r) + 1.0f;
+  union { uint32_t u; float f; } sc;
+  sc.u = (uint32_t)((int)kf + 127) << 23;
+  return y * sc.f;
+}
+
+/* (S) calculateTransmission (stub at src/interactions.h:31-33): Beer-Lambert, exp(-sigma_a * distance) per channel */
+void or_calculateTransmission(const float absorption[3], float distance, float out[3]) {
+  out[0] = or_exp(-(absorption[0] * distance));
+  out[1] = or_exp(-(absorption[1] * distance));
+  out[2] = or_exp(-(absorption[2] * distance));
+}
+
+/* batch forms for the tests: n seeds (or n uniform triples) against ONE geom; type 0 = sphere, else cube */
+void or_random_points_batch(const or_static_geom* g, int n, const float* seed, float* out) {
+  for (int i = 0; i < n; i++) {
+    if (g->type == 0) or_getRandomPointOnSphere(g, seed[i], out + 3 * i);
+    else or_getRandomPointOnCube(g, seed[i], out + 3 * i);
+  }
+}
+void or_points_u_batch(const or_static_geom* g, int n, const float* u, float* out) {
+  for (int i = 0; i < n; i++) {
+    if (g->type == 0) or_sphere_point_u(g, u[3 * i], u[3 * i + 1], out + 3 * i);
+    else or_cube_point_u(g, u[3 * i], u[3 * i + 1], u[3 * i + 2], out + 3 * i);
+  }
+}
+void or_sphere_dirs_batch(int n, const float* xi1, const float* xi2, float* out) {
+  for (int i = 0; i < n; i++) or_getRandomDirectionInSphere(xi1[i], xi2[i], out + 3 * i);
+}
+void or_transmission_batch(int n, const float* absorption, const float* distance, float* out) {
+  for (int i = 0; i < n; i++) or_calculateTransmission(absorption + 3 * i, distance[i], out + 3 * i);
+}
+
 /* (S) closest hit: scan in index order, keep the strictly smaller positive world distance. MESH has no
  * geometry (scene.cpp:57-66) and is never hit. */
 int or_closest_hit(const or_static_geom* geoms, int n_geoms, const float o[3], const float d[3], float* t,
@@ -320,7 +448,7 @@ int or_closest_hit(const or_static_geom* geoms, int n_geoms, const float o[3], c
 }
 
 /* (S) src/interactions.h:99-104 stub (calculateBSDF) + README.md:63-82 feature list.  See SURVEY.md appendix E. */
-int or_shade(const or_scene* sc, int geom_id, const float p[3], const float n[3], uint64_t seed, uint32_t pixel,
+int or_shade(const or_scene* sc, int geom_id, float t, const float p[3], const float n[3], uint64_t seed, uint32_t pixel,
              uint32_t sample, uint32_t depth, float o[3], float d[3], float thr[3], float L[3]) {
   const or_static_geom* g = &sc->geoms[geom_id];
   const or_material* m = &sc->materials[g->materialid];
@@ -338,6 +466,14 @@ int or_shade(const or_scene* sc, int geom_id, const float p[3], const float n[3]
   v3 nd, no;
   if (m->hasRefractive > 0) {
     float ior = m->indexOfRefraction;
+    /* the segment that ends here ran INSIDE the geom if it arrives from within: Beer-Lambert absorption over its
+     * world length t with the material's ABSCOEFF (scene.cpp:250-252; calculateTransmission) */
+    const float* ab = m->absorptionCoefficient;
+    if (!entering && (ab[0] > 0 || ab[1] > 0 || ab[2] > 0)) {
+      float tr3[3];
+      or_calculateTransmission(ab, t, tr3);
+      T = vmul(T, ld3(tr3));
+    }
     float ei = entering ? 1.0f : ior, et = entering ? ior : 1.0f;
     v3 refl = reflect3(ns, D);
     v3 tr;
@@ -427,7 +563,7 @@ double or_render(const or_scene* sc, uint32_t first_sample, uint32_t n_samples, 
           int id = or_closest_hit(sc->geoms, sc->n_geoms, o, d, &t, p, n);
           if (id < 0) break;
           float L[3];
-          int kind = or_shade(sc, id, p, n, seed, (uint32_t)pix, s, (uint32_t)depth, o, d, thr, L);
+          int kind = or_shade(sc, id, t, p, n, seed, (uint32_t)pix, s, (uint32_t)depth, o, d, thr, L);
           if (kind == 3) {
             sum_rgb[3 * pix + 0] += L[0];
             sum_rgb[3 * pix + 1] += L[1];

@@ -78,6 +78,8 @@ void or_multiplyMV(const float m[16], const float v[4], float out[3]);
 void or_getPointOnRay(const float o[3], const float d[3], float t, float out[3]);
 float or_sphereIntersectionTest(const or_static_geom* g, const float o[3], const float d[3], float p[3], float n[3]);
 void or_getRadiuses(const or_static_geom* g, float out[3]);
+/* src/intersections.h:133-175 with the host build's argument evaluation order; thrust minstd inside */
+void or_getRandomPointOnCube(const or_static_geom* g, float randomSeed, float out[3]);
 /* reference formula with libm sinf/cosf, for pinning only */
 void or_hemisphere_ref(const float n[3], float xi1, float xi2, float out[3]);
 
@@ -92,6 +94,13 @@ void or_reflect(const float n[3], const float i[3], float out[3]);
 int or_refract(const float n[3], const float i[3], float ior_i, float ior_t, float out[3]); /* returns 1 on TIR */
 void or_fresnel(const float n[3], const float i[3], float ior_i, float ior_t, const float refl[3],
                 const float trans[3], int tir, float* R, float* T);
+/* a12/a13/a15: surface points and directions; a20: Beer-Lambert transmission with a reproducible exp */
+void or_cube_point_u(const or_static_geom* g, float u0, float u1, float u2, float out[3]);
+void or_sphere_point_u(const or_static_geom* g, float u0, float u1, float out[3]);
+void or_getRandomPointOnSphere(const or_static_geom* g, float randomSeed, float out[3]);
+void or_getRandomDirectionInSphere(float xi1, float xi2, float out[3]);
+float or_exp(float x);
+void or_calculateTransmission(const float absorption[3], float distance, float out[3]);
 void or_raygen(const or_camera_data* cam, const or_lens* lens, uint64_t seed, uint32_t pixel, uint32_t sample,
                float o[3], float d[3]);
 /* closest hit in index order with strict '<'; returns geom index or -1 */
@@ -99,12 +108,16 @@ int or_closest_hit(const or_static_geom* geoms, int n_geoms, const float o[3], c
                    float p[3], float n[3]);
 /* One shading event. Returns 0 diffuse, 1 reflected, 2 transmitted (src/interactions.h:97-101),
  * 3 = emissive hit (path ends, radiance written to L). Updates o, d, thr in place. */
-int or_shade(const or_scene* sc, int geom_id, const float p[3], const float n[3], uint64_t seed, uint32_t pixel,
+int or_shade(const or_scene* sc, int geom_id, float t, const float p[3], const float n[3], uint64_t seed, uint32_t pixel,
              uint32_t sample, uint32_t depth, float o[3], float d[3], float thr[3], float L[3]);
 
 /* ---- batch / whole-frame entry points used by tests and the CPU baseline ---- */
 void or_intersect_rays(const or_static_geom* geoms, int n_geoms, int n_rays, const float* o, const float* d,
                        int* id, float* t, float* p, float* n);
+void or_random_points_batch(const or_static_geom* g, int n, const float* seed, float* out);
+void or_points_u_batch(const or_static_geom* g, int n, const float* u, float* out);
+void or_sphere_dirs_batch(int n, const float* xi1, const float* xi2, float* out);
+void or_transmission_batch(int n, const float* absorption, const float* distance, float* out);
 void or_raygen_batch(const or_camera_data* cam, const or_lens* lens, uint64_t seed, int n, const uint32_t* pixel,
                      const uint32_t* sample, float* o, float* d);
 /* Render samples [first_sample, first_sample+n_samples) of pixels [pix_begin, pix_end) and ADD radiance to

@@ -17,6 +17,9 @@
 //   getRadiuses                           src/intersections.h:120-129
 //   calculateRandomDirectionInHemisphere  src/interactions.h:62-87
 //   calculateBSDF (stub, 1)               src/interactions.h:99-104
+//   getRandomPointOnCube                  src/intersections.h:133-175 (host evaluation order of the reference build)
+//   getRandomPointOnSphere (stub, 0)      src/intersections.h:179-182
+//   calculateTransmission / getRandomDirectionInSphere (stubs, 0)   src/interactions.h:31-33,93-95
 //
 // intersections.h must come before any header that says `using namespace std`
 // (::hash vs std::hash).
@@ -85,6 +88,25 @@ int ref_calculateBSDF_stub(void) {
   glm::vec3 c(0), u(0);
   material m; std::memset(&m, 0, sizeof(m));
   return calculateBSDF(r, glm::vec3(0), glm::vec3(0, 1, 0), glm::vec3(0), a, c, u, m);
+}
+
+// n seeds against ONE cube: the reference's own sampler (thrust minstd seeded with hash((uint)seed))
+void ref_getRandomPointOnCube_batch(const void* geom172, int n, const float* seed, float* out) {
+  staticGeom g;
+  std::memcpy(&g, geom172, sizeof(g));
+  for (int i = 0; i < n; i++) {
+    glm::vec3 p = getRandomPointOnCube(g, seed[i]);
+    out[3 * i] = p.x; out[3 * i + 1] = p.y; out[3 * i + 2] = p.z;
+  }
+}
+
+// the stubs this repo specifies itself: what the reference returns today (all zeros)
+void ref_sampling_stubs(float* out9) {
+  staticGeom g; std::memset(&g, 0, sizeof(g));
+  glm::vec3 a = getRandomPointOnSphere(g, 1.0f), b = getRandomDirectionInSphere(0.3f, 0.7f),
+            c = calculateTransmission(glm::vec3(1, 2, 3), 1.0f);
+  out9[0] = a.x; out9[1] = a.y; out9[2] = a.z; out9[3] = b.x; out9[4] = b.y; out9[5] = b.z;
+  out9[6] = c.x; out9[7] = c.y; out9[8] = c.z;
 }
 
 // sizeof / offsetof table

@@ -212,6 +212,40 @@ def selftest_math(device=0):
     return tuple(int(x) for x in bad)
 
 
+def random_points_on_geom(geom, seeds, device=0):
+    """getRandomPointOnCube / getRandomPointOnSphere (src/intersections.h:133-182), one world point per float seed"""
+    g, sd = np.ascontiguousarray(geom), _arr(seeds, np.float32).ravel()
+    out = np.zeros((sd.size, 3), np.float32)
+    _check(lib().pt_random_points_on_geom(C.c_int(device), _p(g), C.c_int(sd.size), _p(sd), _p(out)))
+    return out
+
+
+def points_on_geom_u(geom, u, device=0):
+    """the same samplers driven by given uniforms, u = (n, 3)"""
+    g, u = np.ascontiguousarray(geom), _arr(u, np.float32).reshape(-1, 3)
+    out = np.zeros_like(u)
+    _check(lib().pt_points_on_geom_u(C.c_int(device), _p(g), C.c_int(u.shape[0]), _p(u), _p(out)))
+    return out
+
+
+def random_directions_in_sphere(xi1, xi2, device=0):
+    """getRandomDirectionInSphere (src/interactions.h:93-95)"""
+    a, b = _arr(xi1, np.float32).ravel(), _arr(xi2, np.float32).ravel()
+    assert a.shape == b.shape
+    out = np.zeros((a.size, 3), np.float32)
+    _check(lib().pt_random_directions_in_sphere(C.c_int(device), C.c_int(a.size), _p(a), _p(b), _p(out)))
+    return out
+
+
+def calculate_transmission(absorption, distance, device=0):
+    """calculateTransmission (src/interactions.h:31-33): exp(-absorption * distance) per channel"""
+    a, d = _arr(absorption, np.float32).reshape(-1, 3), _arr(distance, np.float32).ravel()
+    assert a.shape[0] == d.size
+    out = np.zeros_like(a)
+    _check(lib().pt_calculate_transmission(C.c_int(device), C.c_int(d.size), _p(a), _p(d), _p(out)))
+    return out
+
+
 def compact_u32(values, flags, device=0):
     """Stream compaction primitive on its own (pt_compact_u32): values[flags != 0], order preserved."""
     v, f = _arr(values, np.uint32).ravel(), _arr(flags, np.uint8).ravel()

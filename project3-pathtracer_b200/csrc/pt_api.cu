@@ -1083,6 +1083,63 @@ extern "C" int pt_selftest_math(int device, uint64_t bad[3]) {
   return PT_OK;
 }
 
+// ---------------------------------------------------------------- sampling / transmission parity entry points
+static int select_device_(int device) {
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { pt_set_error_("device %d out of range (%d devices)", device, ndev); return PT_ERR_INVALID; }
+  CU(cudaSetDevice(device));
+  return PT_OK;
+}
+static int points_impl(int device, const pt_static_geom* g, int mode, int n, const float* in, float* points) {
+  if (!g || n < 0 || (n > 0 && (!in || !points))) { pt_set_error_("bad arguments"); return PT_ERR_INVALID; }
+  if (g->type != 0 && g->type != 1) { pt_set_error_("geom type %d has no surface sampler (sphere = 0, cube = 1)", g->type); return PT_ERR_INVALID; }
+  if (n == 0) return PT_OK;
+  if (int rc = select_device_(device)) return rc;
+  const size_t per = mode == 0 ? 1 : 3;
+  DevBuf<float> din, dout;
+  CU(din.alloc(per * n)); CU(dout.alloc(3 * (size_t)n));
+  CU(cudaMemcpy(din.p, in, per * n * sizeof(float), cudaMemcpyHostToDevice));
+  const float* T = g->transform;
+  k_points_on_geom<<<(n + 255) / 256, 256>>>(g->type, make_float4(T[0], T[1], T[2], T[3]), make_float4(T[4], T[5], T[6], T[7]),
+                                             make_float4(T[8], T[9], T[10], T[11]), mode, n, din.p, dout.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(points, dout.p, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  return PT_OK;
+}
+extern "C" int pt_random_points_on_geom(int device, const pt_static_geom* geom, int n, const float* seeds, float* points) {
+  return points_impl(device, geom, 0, n, seeds, points);
+}
+extern "C" int pt_points_on_geom_u(int device, const pt_static_geom* geom, int n, const float* u, float* points) {
+  return points_impl(device, geom, 1, n, u, points);
+}
+extern "C" int pt_random_directions_in_sphere(int device, int n, const float* xi1, const float* xi2, float* dirs) {
+  if (n < 0 || (n > 0 && (!xi1 || !xi2 || !dirs))) { pt_set_error_("bad arguments"); return PT_ERR_INVALID; }
+  if (n == 0) return PT_OK;
+  if (int rc = select_device_(device)) return rc;
+  DevBuf<float> d1, d2, dout;
+  CU(d1.alloc(n)); CU(d2.alloc(n)); CU(dout.alloc(3 * (size_t)n));
+  CU(cudaMemcpy(d1.p, xi1, n * sizeof(float), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d2.p, xi2, n * sizeof(float), cudaMemcpyHostToDevice));
+  k_sphere_dirs<<<(n + 255) / 256, 256>>>(n, d1.p, d2.p, dout.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(dirs, dout.p, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  return PT_OK;
+}
+extern "C" int pt_calculate_transmission(int device, int n, const float* absorption, const float* distance, float* out) {
+  if (n < 0 || (n > 0 && (!absorption || !distance || !out))) { pt_set_error_("bad arguments"); return PT_ERR_INVALID; }
+  if (n == 0) return PT_OK;
+  if (int rc = select_device_(device)) return rc;
+  DevBuf<float> da, dd, dout;
+  CU(da.alloc(3 * (size_t)n)); CU(dd.alloc(n)); CU(dout.alloc(3 * (size_t)n));
+  CU(cudaMemcpy(da.p, absorption, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dd.p, distance, n * sizeof(float), cudaMemcpyHostToDevice));
+  k_transmission<<<(n + 255) / 256, 256>>>(n, da.p, dd.p, dout.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, dout.p, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  return PT_OK;
+}
+
 // ---------------------------------------------------------------- multi-GPU combine (single process, one context per GPU)
 // One ncclReduce(sum) of the float4 accumulation images to ctxs[0] over NVLink / NVSwitch.  NCCL is resolved at run
 // time (dlopen) so that a process that already carries its own libnccl (PyTorch) keeps a single copy; processes

@@ -17,6 +17,7 @@
 #include "pt_device.cuh"
 #include "pt_filter.cuh"
 #include "pt_bvh.cuh"
+#include "pt_sampling.cuh"
 
 namespace ptd {
 

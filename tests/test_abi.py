@@ -61,6 +61,12 @@ def test_compute_entry_points_fail_loudly_without_a_gpu(pt, sample_scene):
     assert "cuda" in str(e.value).lower()
     with pytest.raises(pt.PtError):
         pt.compact_u32(np.arange(4, dtype=np.uint32), np.ones(4, np.uint8))
+    with pytest.raises(pt.PtError):
+        pt.random_points_on_geom(sample_scene["geoms"][0:1], [1.0])
+    with pytest.raises(pt.PtError):
+        pt.random_directions_in_sphere([0.5], [0.5])
+    with pytest.raises(pt.PtError):
+        pt.calculate_transmission([[1, 1, 1]], [1.0])
 
 
 def test_argument_validation(pt):

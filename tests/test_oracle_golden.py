@@ -2,10 +2,15 @@
 
 ref_vectors.json holds outputs of the REFERENCE'S OWN functions (generated in the build container from
 oracle/_ref, see oracle/gen_golden.py): the restatement must reproduce them bit for bit.
-spec_vectors.json freezes our specification of the stubbed pieces; its Philox entries are Random123's KATs."""
-import numpy as np
+spec_vectors.json freezes our specification of the stubbed pieces; its Philox entries are Random123's KATs.
+sampling_vectors.json: the reference's getRandomPointOnCube (pinned) and the frozen sampling / absorption stubs."""
+import json
+import os
 
-from conftest import f32, same_bits
+import numpy as np
+import pytest
+
+from conftest import GOLD, f32, same_bits
 
 
 def _geoms(ref_gold, pt):
@@ -147,3 +152,64 @@ def test_render_fixture_frozen(oracle, spec_gold, ref_gold, pt):
     a, la, _ = oracle.render(oracle.make_scene(g, m, cam), 0, 2, 8, 11, pix_begin=0, pix_end=700)
     b, lb, _ = oracle.render(oracle.make_scene(g, m, cam), 0, 2, 8, 11, pix_begin=700, pix_end=1600, sum_rgb=a)
     assert same_bits(b, img) and (la + lb).tolist() == live.tolist()
+
+
+# ---- surface-point / direction sampling and absorption (a12, a13, a15, a20) ----
+@pytest.fixture(scope="module")
+def samp_gold():
+    with open(os.path.join(GOLD, "sampling_vectors.json")) as f:
+        return json.load(f)
+
+
+def _as_cube(g):
+    c = np.array(g).reshape(1).copy()
+    c["type"] = 1
+    return c
+
+
+def test_getRandomPointOnCube_bit_exact(oracle, ref_gold, samp_gold, pt):
+    """the restatement (thrust minstd + hash + the host build's right-to-left draws) against the reference's own
+    getRandomPointOnCube, src/intersections.h:133-175: 9 transforms x 256 seeds"""
+    g = _geoms(ref_gold, pt)
+    seeds = f32(samp_gold["seeds"])
+    assert len(samp_gold["ref_cube_points"]) == len(g)
+    for k in samp_gold["ref_cube_points"]:
+        got = oracle.random_points(_as_cube(g[k["geom"]]), seeds)
+        assert same_bits(got.ravel(), f32(k["p"]))
+    assert (f32(samp_gold["ref_stubs"]) == 0).all()  # what the reference's three stubs return today
+
+
+def test_sampling_spec_frozen(oracle, ref_gold, samp_gold, pt):
+    g = _geoms(ref_gold, pt)
+    seeds, u = f32(samp_gold["seeds"]), f32(samp_gold["u"]).reshape(-1, 3)
+    for k in samp_gold["sphere_points"]:
+        assert same_bits(oracle.random_points(g[k["geom"]], seeds).ravel(), f32(k["p"]))
+    for k in samp_gold["points_u"]:
+        assert same_bits(oracle.points_u(g[k["geom"]], u).ravel(), f32(k["p"]))
+    assert same_bits(oracle.sphere_dirs(u[:, 0], u[:, 1]).ravel(), f32(samp_gold["sphere_dirs"]))
+    t = samp_gold["transmission"]
+    ab, dist = f32(t["absorption"]).reshape(-1, 3), f32(t["distance"])
+    assert same_bits(oracle.transmission(ab, dist).ravel(), f32(t["T"]))
+
+
+def test_sampling_properties(oracle, ref_gold, pt):
+    g = _geoms(ref_gold, pt)
+    rng = np.random.default_rng(9)
+    u = rng.random((4000, 3), dtype=np.float32)
+    d = oracle.sphere_dirs(u[:, 0], u[:, 1]).astype(np.float64)
+    assert np.abs(np.linalg.norm(d, axis=1) - 1).max() < 1e-6 and np.abs(d.mean(axis=0)).max() < 0.05
+    for gi in range(len(g)):
+        inv = np.array(g[gi]["inverseTransform"], np.float64).reshape(4, 4)
+        p = oracle.points_u(g[gi], u).astype(np.float64)
+        po = p @ inv[:3, :3].T + inv[:3, 3]  # object space
+        if int(g[gi]["type"]) == 0:
+            assert np.abs(np.linalg.norm(po, axis=1) - 0.5).max() < 1e-3  # on the sphere of radius .5
+        else:
+            assert np.abs(np.abs(po).max(axis=1) - 0.5).max() < 1e-3  # on a face (walls are scaled by .01: 100x rounding)
+    # Beer-Lambert against exp() in binary64; zero absorption transmits everything, huge absorption nothing
+    ab = (rng.random((2000, 3)) * 5).astype(np.float32)
+    dist = (rng.random(2000) * 8).astype(np.float32)
+    T = oracle.transmission(ab, dist)
+    want = np.exp(-(ab * dist[:, None]).astype(np.float64))
+    assert np.abs(T - want).max() <= 2e-7 * 1 + 0 and (np.abs(T - want) / want).max() < 2e-7
+    assert (oracle.transmission([[0, 0, 0]], [3.0]) == 1).all() and (oracle.transmission([[200, 300, 1e30]], [1.0]) == 0).all()

@@ -169,6 +169,17 @@ int pt_filter_stats(pt_context* ctx, uint64_t* fallbacks);
  * operators; bad[0..2] = number of differing results of each (must be 0) */
 int pt_selftest_math(int device, uint64_t bad[3]);
 
+/* ---- direct light sampling (README.md "Sphere surface point sampling") ----
+ * Off by default (every result above is then unchanged).  On: at each diffuse bounce that is not the path's last
+ * allowed segment, one emissive sphere / cube is picked uniformly, one point on it is drawn with
+ * getRandomPointOnCube's area-weighted face rule (src/intersections.h:140-172) or the sphere sampler (:179-182),
+ * a shadow ray is traced through the same closest hit, and a visible point adds
+ * thr * Le * cos cos' / (pi t^2) * area * lights; the continuing path does not add emission if it then reaches a light
+ * by itself.  Same expected image, less noise; shadow rays are counted apart from the path segments. */
+int pt_set_direct_lighting(pt_context* ctx, int on);
+/* shadow rays traced by pt_render calls since the last pt_clear; n_lights (may be NULL) = emissive geoms of the scene */
+int pt_shadow_rays(pt_context* ctx, uint64_t* shadow_rays, int* n_lights);
+
 /* ---- surface-point / direction sampling and absorption (host buffers; one launch each) ---- */
 /* getRandomPointOnCube (src/intersections.h:133-175, implemented there: results are bit-identical to the reference's
  * host build, including its right-to-left argument evaluation order) and getRandomPointOnSphere (stub at :179-182;

@@ -72,6 +72,7 @@ class OrScene(C.Structure):
         ("n_materials", C.c_int),
         ("cam", OrCamera),
         ("lens", OrLens),
+        ("direct_lighting", C.c_int),
     ]
 
 
@@ -112,6 +113,8 @@ class Oracle:
             C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32,
             C.c_void_p, C.c_void_p, C.c_int,
         ]
+        L.or_render_ex.restype = C.c_double
+        L.or_render_ex.argtypes = L.or_render.argtypes + [C.c_void_p]
         L.or_max_threads.restype = C.c_int
         L.or_refract.restype = C.c_int
 
@@ -238,7 +241,7 @@ class Oracle:
         self.lib.or_intersect_rays(_p(g), C.c_int(g.shape[0]), C.c_int(n), _p(o), _p(d), _p(gid), _p(t), _p(p), _p(nr))
         return gid, t, p, nr
 
-    def make_scene(self, geoms, materials, cam, lens=(0.0, 0.0)):
+    def make_scene(self, geoms, materials, cam, lens=(0.0, 0.0), direct_lighting=False):
         g = np.ascontiguousarray(geoms)
         m = np.ascontiguousarray(materials)
         sc = OrScene()
@@ -246,6 +249,7 @@ class Oracle:
         sc.materials, sc.n_materials = m.ctypes.data, m.shape[0]
         sc.cam = self._cam(cam)
         sc.lens = OrLens(float(lens[0]), float(lens[1]))
+        sc.direct_lighting = 1 if direct_lighting else 0
         sc._keep = (g, m)
         return sc
 
@@ -257,8 +261,10 @@ class Oracle:
         if sum_rgb is None:
             sum_rgb = np.zeros((W * H, 3), np.float32)
         live = np.zeros(64, np.uint64)
-        secs = self.lib.or_render(C.byref(scene), first_sample, n_samples, max_depth, seed, pix_begin, pix_end,
-                                  _p(sum_rgb), _p(live), threads)
+        shadow = C.c_uint64(0)
+        secs = self.lib.or_render_ex(C.byref(scene), first_sample, n_samples, max_depth, seed, pix_begin, pix_end,
+                                     _p(sum_rgb), _p(live), threads, C.byref(shadow))
+        self.last_shadow_rays = int(shadow.value)
         return sum_rgb, live[:max_depth].copy(), float(secs)
 
     def max_threads(self):

@@ -319,21 +319,35 @@ static inline float minstd_uniform(minstd* r, float a, float b) {
 
 /* body of src/intersections.h:140-172 given the three draws: face by area-weighted roulette, then the two
  * in-face coordinates (a = first vec3 argument that is random, b = second) */
-static inline v3 cube_point_body(const or_static_geom* g, float roulette, float a, float b) {
+/* the five face thresholds of :149-169 and the total area; they depend on the geom only */
+static inline float cube_thresholds(const or_static_geom* g, float th[5]) {
   float radii[3];
   or_getRadiuses(g, radii);
   float side1 = radii[0] * radii[1] * 4.0f;
   float side2 = radii[2] * radii[1] * 4.0f;
   float side3 = radii[0] * radii[2] * 4.0f;
   float totalarea = 2.0f * (side1 + side2 + side3);
+  th[0] = (side1 / totalarea);
+  th[1] = ((side1 * 2) / totalarea);
+  th[2] = (((side1 * 2) + (side2)) / totalarea);
+  th[3] = (((side1 * 2) + (side2 * 2)) / totalarea);
+  th[4] = (((side1 * 2) + (side2 * 2) + (side3)) / totalarea);
+  return totalarea;
+}
+static inline v3 cube_point_th(const or_static_geom* g, const float th[5], float roulette, float a, float b) {
   v3 point;
-  if (roulette < (side1 / totalarea)) point = V(a, b, .5f);
-  else if (roulette < ((side1 * 2) / totalarea)) point = V(a, b, -.5f);
-  else if (roulette < (((side1 * 2) + (side2)) / totalarea)) point = V(.5f, a, b);
-  else if (roulette < (((side1 * 2) + (side2 * 2)) / totalarea)) point = V(-.5f, a, b);
-  else if (roulette < (((side1 * 2) + (side2 * 2) + (side3)) / totalarea)) point = V(a, .5f, b);
+  if (roulette < th[0]) point = V(a, b, .5f);
+  else if (roulette < th[1]) point = V(a, b, -.5f);
+  else if (roulette < th[2]) point = V(.5f, a, b);
+  else if (roulette < th[3]) point = V(-.5f, a, b);
+  else if (roulette < th[4]) point = V(a, .5f, b);
   else point = V(a, -.5f, b);
   return mulMV(g->transform, point.x, point.y, point.z, 1.0f);
+}
+static inline v3 cube_point_body(const or_static_geom* g, float roulette, float a, float b) {
+  float th[5];
+  cube_thresholds(g, th);
+  return cube_point_th(g, th, roulette, a, b);
 }
 
 /* (R) getRandomPointOnCube, src/intersections.h:133-175, as the reference's HOST build behaves: the two u02(rng)
@@ -535,11 +549,49 @@ static double now_s(void) {
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
+/* ---- (S) direct light sampling (README.md "Sphere surface point sampling") ----
+ * Lights = sphere / cube geoms whose material has EMITTANCE > 0, in index order.  At every diffuse shading event that
+ * is not the path's last allowed segment, ONE light is picked uniformly and ONE point y on it is drawn with the
+ * reference's own area-weighted cube sampler / the sphere sampler above (uniforms: Philox block 65 + depth); the
+ * shadow ray from the new path origin towards y is traced with the ordinary closest hit, and if it arrives on that
+ * light at y (distance within 1e-3 relative + 1e-3 of |y - o|) the estimate  thr * (1/pi) * Le * cos_s * cos_l / t^2 * area * n_lights  is added.  The continuing path then
+ * carries a flag that suppresses emission if it reaches a light by itself at its next hit (no double counting);
+ * specular and refractive events clear the flag.  area: the cube sampler's totalarea; spheres 4*pi/3 * (rx*ry + ry*rz
+ * + rx*rz) (exact for uniform scale). */
+typedef struct { int geom; float E[3]; float th[5]; } or_light;
+static int build_lights(const or_scene* sc, or_light* out, int cap) {
+  int n = 0;
+  float area[1024];
+  if (cap > 1024) cap = 1024;
+  for (int i = 0; i < sc->n_geoms && n < cap; i++) {
+    const or_static_geom* g = &sc->geoms[i];
+    if (g->type != 0 && g->type != 1) continue;
+    if (!(sc->materials[g->materialid].emittance > 0)) continue;
+    out[n].geom = i;
+    if (g->type == 1) {
+      area[n] = cube_thresholds(g, out[n].th);
+    } else {
+      float r[3];
+      or_getRadiuses(g, r);
+      area[n] = 4.1887903f * ((r[0] * r[1] + r[1] * r[2]) + r[0] * r[2]);
+      memset(out[n].th, 0, sizeof(out[n].th));
+    }
+    n++;
+  }
+  for (int k = 0; k < n; k++) {
+    const or_material* m = &sc->materials[sc->geoms[out[k].geom].materialid];
+    float kk = (area[k] * (float)n) * 0.31830987f;
+    st3(out[k].E, vscale(vscale(ld3(m->color), m->emittance), kk));
+  }
+  return n;
+}
+
 /* (S) the per-pixel path loop the reference sketches in raytraceRay (src/raytraceKernel.cu:93-104) and the
  * running accumulation of cudaRaytraceCore (:108-165): one path per (pixel, sample); a path ends on a miss
  * (black background), on an emissive hit (adds throughput*color*emittance) or after max_depth segments. */
-double or_render(const or_scene* sc, uint32_t first_sample, uint32_t n_samples, int max_depth, uint64_t seed,
-                 uint32_t pix_begin, uint32_t pix_end, float* sum_rgb, uint64_t* live, int threads) {
+double or_render_ex(const or_scene* sc, uint32_t first_sample, uint32_t n_samples, int max_depth, uint64_t seed,
+                    uint32_t pix_begin, uint32_t pix_end, float* sum_rgb, uint64_t* live, int threads,
+                    uint64_t* shadow_rays) {
   if (max_depth > 64) max_depth = 64;
 #ifdef _OPENMP
   int nt = threads > 0 ? threads : omp_get_max_threads();
@@ -547,15 +599,20 @@ double or_render(const or_scene* sc, uint32_t first_sample, uint32_t n_samples, 
   int nt = 1;
   (void)threads;
 #endif
+  static or_light lights_buf[1024];
+  or_light* lights = lights_buf;
+  int n_lights = 0;
+  if (sc->direct_lighting) n_lights = build_lights(sc, lights, 1024);
   double t0 = now_s();
 #pragma omp parallel num_threads(nt)
   {
-    uint64_t mylive[64];
+    uint64_t mylive[64], myshadow = 0;
     memset(mylive, 0, sizeof(mylive));
 #pragma omp for schedule(dynamic, 256)
     for (int64_t pix = (int64_t)pix_begin; pix < (int64_t)pix_end; pix++) {
       for (uint32_t s = first_sample; s < first_sample + n_samples; s++) {
         float o[3], d[3], thr[3] = {1.0f, 1.0f, 1.0f};
+        int skip_emission = 0;
         or_raygen(&sc->cam, &sc->lens, seed, (uint32_t)pix, s, o, d);
         for (int depth = 0; depth < max_depth; depth++) {
           mylive[depth]++;
@@ -563,18 +620,71 @@ double or_render(const or_scene* sc, uint32_t first_sample, uint32_t n_samples, 
           int id = or_closest_hit(sc->geoms, sc->n_geoms, o, d, &t, p, n);
           if (id < 0) break;
           float L[3];
+          v3 din = ld3(d);
           int kind = or_shade(sc, id, t, p, n, seed, (uint32_t)pix, s, (uint32_t)depth, o, d, thr, L);
           if (kind == 3) {
-            sum_rgb[3 * pix + 0] += L[0];
-            sum_rgb[3 * pix + 1] += L[1];
-            sum_rgb[3 * pix + 2] += L[2];
+            if (!skip_emission) {
+              sum_rgb[3 * pix + 0] += L[0];
+              sum_rgb[3 * pix + 1] += L[1];
+              sum_rgb[3 * pix + 2] += L[2];
+            }
             break;
+          }
+          skip_emission = 0;
+          if (kind == 0 && n_lights > 0 && depth + 1 < max_depth) {
+            skip_emission = 1;
+            v3 N = ld3(n);
+            v3 ns = vdot(din, N) < 0 ? N : vneg(N);
+            float v[4];
+            rng4(seed, (uint32_t)pix, s, 65u + (uint32_t)depth, v);
+            int li = (int)(v[0] * (float)n_lights);
+            if (li > n_lights - 1) li = n_lights - 1;
+            const or_light* Lt = &lights[li];
+            const or_static_geom* gl = &sc->geoms[Lt->geom];
+            v3 y;
+            if (gl->type == 0) {
+              float yy[3];
+              or_sphere_point_u(gl, v[1], v[2], yy);
+              y = ld3(yy);
+            } else {
+              y = cube_point_th(gl, Lt->th, v[1], v[2] - 0.5f, v[3] - 0.5f);
+            }
+            v3 wv = vsub(y, ld3(o));
+            v3 wd = vnormalize(wv);
+            float dy = vlength(wv);
+            float cs = vdot(ns, wd);
+            if (cs > 0) {
+              myshadow++;
+              float wdv[3], t2, p2[3], n2[3];
+              st3(wdv, wd);
+              int id2 = or_closest_hit(sc->geoms, sc->n_geoms, o, wdv, &t2, p2, n2);
+              /* y is visible iff the ray arrives ON the light AT y (a point on the light's far side is hidden by the
+               * light itself: same geom, shorter distance) */
+              if (id2 == Lt->geom && (dy - t2) < 1e-3f * dy + 1e-3f) {
+                float cl = -vdot(ld3(n2), wd);
+                if (cl > 0) {
+                  float G = (cs * cl) / (t2 * t2);
+                  v3 Ld = vscale(vmul(ld3(thr), ld3(Lt->E)), G);
+                  sum_rgb[3 * pix + 0] += Ld.x;
+                  sum_rgb[3 * pix + 1] += Ld.y;
+                  sum_rgb[3 * pix + 2] += Ld.z;
+                }
+              }
+            }
           }
         }
       }
     }
 #pragma omp critical
-    for (int i = 0; i < max_depth; i++) live[i] += mylive[i];
+    {
+      for (int i = 0; i < max_depth; i++) live[i] += mylive[i];
+      if (shadow_rays) *shadow_rays += myshadow;
+    }
   }
   return now_s() - t0;
+}
+
+double or_render(const or_scene* sc, uint32_t first_sample, uint32_t n_samples, int max_depth, uint64_t seed,
+                 uint32_t pix_begin, uint32_t pix_end, float* sum_rgb, uint64_t* live, int threads) {
+  return or_render_ex(sc, first_sample, n_samples, max_depth, seed, pix_begin, pix_end, sum_rgb, live, threads, NULL);
 }

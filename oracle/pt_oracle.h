@@ -70,6 +70,7 @@ typedef struct {
   int n_materials;
   or_camera_data cam;
   or_lens lens;
+  int direct_lighting; /* 0: emission only where a path arrives (the default); 1: direct light sampling at diffuse hits */
 } or_scene;
 
 /* ---- (R) reference-pinned pieces ---- */
@@ -126,6 +127,11 @@ void or_raygen_batch(const or_camera_data* cam, const or_lens* lens, uint64_t se
  * time spent in the render loop. */
 double or_render(const or_scene* sc, uint32_t first_sample, uint32_t n_samples, int max_depth, uint64_t seed,
                  uint32_t pix_begin, uint32_t pix_end, float* sum_rgb, uint64_t* live, int threads);
+/* the same with direct light sampling counted: *shadow_rays (may be NULL) is incremented by the number of shadow
+ * rays for which closest-hit was evaluated */
+double or_render_ex(const or_scene* sc, uint32_t first_sample, uint32_t n_samples, int max_depth, uint64_t seed,
+                    uint32_t pix_begin, uint32_t pix_end, float* sum_rgb, uint64_t* live, int threads,
+                    uint64_t* shadow_rays);
 int or_max_threads(void);
 
 #ifdef __cplusplus

@@ -164,6 +164,16 @@ class Context:
         _check(lib().pt_counters(self._h, C.byref(paths), C.byref(segs), _p(live)))
         return paths.value, segs.value, live
 
+    def set_direct_lighting(self, on=True):
+        """direct light sampling at diffuse bounces (pt_set_direct_lighting); off by default"""
+        _check(lib().pt_set_direct_lighting(self._h, C.c_int(1 if on else 0)))
+
+    def shadow_rays(self):
+        """(shadow rays traced since the last clear, emissive geoms in the scene)"""
+        n, nl = C.c_uint64(), C.c_int()
+        _check(lib().pt_shadow_rays(self._h, C.byref(n), C.byref(nl)))
+        return n.value, nl.value
+
     def launch_count(self):
         n = C.c_uint64()
         _check(lib().pt_launch_count(self._h, C.byref(n)))

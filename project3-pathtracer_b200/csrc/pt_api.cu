@@ -61,6 +61,9 @@ struct pt_context {
   int2* d_meta = nullptr;
   float4* d_normals = nullptr;  // kNormalRows float4 per geom: face normals + sphere centre (k_normal_table)
   float4* d_mats = nullptr;
+  float4* d_lights = nullptr;  // direct light sampling: 3 float4 per emissive sphere / cube (build_lights)
+  int n_lights = 0;
+  bool nee = false;            // pt_set_direct_lighting
   float4* d_filt = nullptr;   // kFiltRows arrays of n_pairs float4: filter geometry (pt_filter.cuh)
   int2* d_filt_ids = nullptr;
   FiltSoA filt{};
@@ -84,7 +87,7 @@ struct pt_context {
   int n_slots = kSlots;      // slots in use (1 for frames whose accumulation image alone fills the L2)
   cudaStream_t wf_stream[kSlots] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {nullptr, nullptr};
-  unsigned long long* d_live = nullptr;  // kMaxDepth totals
+  unsigned long long* d_live = nullptr;  // kMaxDepth totals, then fallbacks, then shadow rays
   uint64_t paths_total = 0;
   uint64_t launches = 0;     // kernels of this library launched on behalf of this context
   // image
@@ -92,6 +95,7 @@ struct pt_context {
   float* d_rgb = nullptr;      // staging for packed RGB
   uchar4* d_rgba8 = nullptr;   // staging for the 8-bit resolve
   int grid_blocks[4] = {0, 0, 0, 0};  // persistent grid per (FIRST,LAST) variant
+  int grid_blocks_nee[4] = {0, 0, 0, 0};  // ... of the direct-light-sampling variants
   int mode = -1;                      // 0: linear scan over pairs staged in shared memory, 1: hierarchy (pt_bvh.cuh)
   size_t smem_bytes = 0;   // k_bounce: filter geometry
   size_t geom_smem = 0;    // filter geometry only (k_intersect_list)
@@ -521,19 +525,90 @@ static RaygenConsts make_raygen(const pt_camera_data& c, const pt_lens* lens) {
   return R;
 }
 
+// the direct-light-sampling variant of (FIRST, LAST); the last segment never samples a light, and a first-and-last
+// segment cannot carry the no-emission flag either, so <true, true> needs no variant of its own
+template <bool F, bool L>
+struct NeeOf { static constexpr bool value = !(F && L); };
+
 template <bool F, bool L>
 static int setup_variant(pt_context* c, int slot) {
-  int per_sm = 0;
+  int per_sm = 0, per_sm_nee = 0;
+  constexpr bool N = NeeOf<F, L>::value;
   if (c->mode) {
     CU(cudaFuncSetAttribute(k_bounce_bvh<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce_bvh<F, L>, kBvhThreads, c->smem_bytes));
+    CU(cudaFuncSetAttribute(k_bounce_bvh<F, L, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_nee, k_bounce_bvh<F, L, N>, kBvhThreads, c->smem_bytes));
   } else {
     CU(cudaFuncSetAttribute(k_bounce<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce<F, L>, kBounceThreads, c->smem_bytes));
+    CU(cudaFuncSetAttribute(k_bounce<F, L, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_nee, k_bounce<F, L, N>, kBounceThreads, c->smem_bytes));
   }
-  if (per_sm < 1) { pt_set_error_("k_bounce does not fit on an SM"); return PT_ERR_CUDA; }
+  if (per_sm < 1 || per_sm_nee < 1) { pt_set_error_("k_bounce does not fit on an SM"); return PT_ERR_CUDA; }
   c->grid_blocks[slot] = per_sm * c->sm_count;
+  c->grid_blocks_nee[slot] = per_sm_nee * c->sm_count;
   return PT_OK;
+}
+
+// ---- direct light sampling: the light table (DESIGN.md "direct light sampling"; same binary32 expressions, in the same
+// order, as getRadiuses / getRandomPointOnCube, src/intersections.h:120-129,140-147) ----
+static float h_length3(float x, float y, float z) { return sqrtf((x * x + y * y) + z * z); }
+static void h_mulMV(const float* m, float vx, float vy, float vz, float vw, float out[3]) {
+  for (int r = 0; r < 3; r++) out[r] = (m[4 * r] * vx) + (m[4 * r + 1] * vy) + (m[4 * r + 2] * vz) + (m[4 * r + 3] * vw);
+}
+static void h_radiuses(const pt_static_geom& g, float r[3]) {
+  float o[3], x[3], y[3], z[3];
+  h_mulMV(g.transform, 0, 0, 0, 1, o);
+  h_mulMV(g.transform, .5f, 0, 0, 1, x);
+  h_mulMV(g.transform, 0, .5f, 0, 1, y);
+  h_mulMV(g.transform, 0, 0, .5f, 1, z);
+  r[0] = h_length3(x[0] - o[0], x[1] - o[1], x[2] - o[2]);
+  r[1] = h_length3(y[0] - o[0], y[1] - o[1], y[2] - o[2]);
+  r[2] = h_length3(z[0] - o[0], z[1] - o[1], z[2] - o[2]);
+}
+static std::vector<float4> build_lights(const pt_static_geom* geoms, int n_geoms, const pt_material* mats) {
+  std::vector<float4> T;
+  std::vector<float> area;
+  std::vector<int> ids;
+  for (int i = 0; i < n_geoms; i++) {
+    const pt_static_geom& g = geoms[i];
+    if (g.type != 0 && g.type != 1) continue;
+    if (!(mats[g.materialid].emittance > 0)) continue;
+    float r[3], th[5] = {0, 0, 0, 0, 0}, a;
+    h_radiuses(g, r);
+    if (g.type == 1) {
+      const float side1 = r[0] * r[1] * 4.0f;
+      const float side2 = r[2] * r[1] * 4.0f;
+      const float side3 = r[0] * r[2] * 4.0f;
+      const float totalarea = 2.0f * (side1 + side2 + side3);
+      th[0] = (side1 / totalarea);
+      th[1] = ((side1 * 2) / totalarea);
+      th[2] = (((side1 * 2) + (side2)) / totalarea);
+      th[3] = (((side1 * 2) + (side2 * 2)) / totalarea);
+      th[4] = (((side1 * 2) + (side2 * 2) + (side3)) / totalarea);
+      a = totalarea;
+    } else {
+      a = 4.1887903f * ((r[0] * r[1] + r[1] * r[2]) + r[0] * r[2]);  // 4 pi / 3 * (...): 4 pi r^2 for a uniform scale
+    }
+    int gi = i, ty = g.type;
+    float gf, tf;
+    memcpy(&gf, &gi, 4); memcpy(&tf, &ty, 4);
+    T.push_back(make_float4(0, 0, 0, gf));
+    T.push_back(make_float4(th[0], th[1], th[2], th[3]));
+    T.push_back(make_float4(th[4], tf, 0, 0));
+    area.push_back(a);
+    ids.push_back(i);
+  }
+  const int n = (int)ids.size();
+  for (int k = 0; k < n; k++) {
+    const pt_material& m = mats[geoms[ids[k]].materialid];
+    const float kk = (area[k] * (float)n) * 0.31830987f;  // area * lights / pi
+    T[3 * k].x = (m.color[0] * m.emittance) * kk;
+    T[3 * k].y = (m.color[1] * m.emittance) * kk;
+    T[3 * k].z = (m.color[2] * m.emittance) * kk;
+  }
+  return T;
 }
 
 static int upload_filter(pt_context* c) {
@@ -624,6 +699,14 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
   CU(cudaMemcpyAsync(c->d_rows, rows.data(), rows.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_meta, meta.data(), meta.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_mats, mats, (size_t)n_mats * sizeof(pt_material), cudaMemcpyHostToDevice, c->stream));
+  const std::vector<float4> lights = build_lights(geoms, n_geoms, mats);
+  if (c->d_lights) CU(cudaFree(c->d_lights));
+  c->d_lights = nullptr;
+  c->n_lights = (int)(lights.size() / 3);
+  if (c->n_lights > 0) {
+    CU(cudaMalloc(&c->d_lights, lights.size() * sizeof(float4)));
+    CU(cudaMemcpyAsync(c->d_lights, lights.data(), lights.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  }
   CU(cudaStreamSynchronize(c->stream));  // the host vectors die at return
   c->n_geoms = n_geoms;
   c->n_mats = n_mats;
@@ -681,7 +764,7 @@ extern "C" int pt_context_destroy(pt_context* c) {
   if (!c) return PT_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_rows); cudaFree(c->d_meta); cudaFree(c->d_normals); cudaFree(c->d_mats); cudaFree(c->d_state);
+  cudaFree(c->d_rows); cudaFree(c->d_meta); cudaFree(c->d_normals); cudaFree(c->d_mats); cudaFree(c->d_lights); cudaFree(c->d_state);
   cudaFree(c->d_filt); cudaFree(c->d_filt_ids); cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_leaves); cudaFree(c->d_bvh_meta);
   cudaFree(c->d_ctrl); cudaFree(c->d_live); cudaFree(c->d_accum); cudaFree(c->d_rgb); cudaFree(c->d_rgba8);
   for (int i = 0; i < pt_context::kSlots; i++) {
@@ -723,7 +806,7 @@ extern "C" int pt_context_create(const pt_static_geom* geoms, int n_geoms, const
       cudaMalloc(&c->d_rgb, (size_t)c->npix * 3 * sizeof(float)) != cudaSuccess ||
       cudaMalloc(&c->d_rgba8, (size_t)c->npix * sizeof(uchar4)) != cudaSuccess ||
       cudaMalloc(&c->d_ctrl, pt_context::kSlots * sizeof(WfCtrl)) != cudaSuccess ||
-      cudaMalloc(&c->d_live, (kMaxDepth + 1) * sizeof(unsigned long long)) != cudaSuccess) {
+      cudaMalloc(&c->d_live, (kMaxDepth + 2) * sizeof(unsigned long long)) != cudaSuccess) {
     pt_set_error_("cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     return fail(PT_ERR_CUDA);
   }
@@ -762,22 +845,26 @@ extern "C" int pt_set_stream(pt_context* c, void* cuda_stream) {
 extern "C" int pt_clear(pt_context* c) {
   CTX(c);
   CU(cudaMemsetAsync(c->d_accum, 0, (size_t)c->npix * sizeof(float4), c->stream));
-  CU(cudaMemsetAsync(c->d_live, 0, (kMaxDepth + 1) * sizeof(unsigned long long), c->stream));
+  CU(cudaMemsetAsync(c->d_live, 0, (kMaxDepth + 2) * sizeof(unsigned long long), c->stream));
   c->paths_total = 0;
   return PT_OK;
 }
 
 template <bool F, bool L>
 static cudaError_t launch_bounce(pt_context* c, int slot, const BounceParams& P, uint32_t n_upper, cudaStream_t st) {
-  uint32_t grid = (uint32_t)c->grid_blocks[slot];
+  const bool nee = c->nee && c->n_lights > 0 && NeeOf<F, L>::value;
+  constexpr bool N = NeeOf<F, L>::value;
+  uint32_t grid = (uint32_t)(nee ? c->grid_blocks_nee[slot] : c->grid_blocks[slot]);
   if (c->mode) {
     const uint32_t ctas = (n_upper + kPool * (kBvhThreads / 32) - 1) / (kPool * (kBvhThreads / 32));  // one pool per warp at least
     if (ctas < grid) grid = ctas ? ctas : 1;
-    k_bounce_bvh<F, L><<<grid, kBvhThreads, c->smem_bytes, st>>>(P);
+    if (nee) k_bounce_bvh<F, L, N><<<grid, kBvhThreads, c->smem_bytes, st>>>(P);
+    else k_bounce_bvh<F, L><<<grid, kBvhThreads, c->smem_bytes, st>>>(P);
   } else {
     const uint32_t ctas = (n_upper + kBounceThreads - 1) / kBounceThreads;  // one unit per warp at least
     if (ctas < grid) grid = ctas ? ctas : 1;
-    k_bounce<F, L><<<grid, kBounceThreads, c->smem_bytes, st>>>(P);
+    if (nee) k_bounce<F, L, N><<<grid, kBounceThreads, c->smem_bytes, st>>>(P);
+    else k_bounce<F, L><<<grid, kBounceThreads, c->smem_bytes, st>>>(P);
   }
   c->launches++;
   return cudaGetLastError();
@@ -818,6 +905,7 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
       P.filt = c->filt; P.filt_cap = c->filt_cap;
       P.bvh = c->bvh;
       P.mats = c->d_mats;
+      P.lights = c->d_lights; P.n_lights = c->n_lights;
       P.cam = c->cam;
       P.ctrl = ctrl;
       P.depth = (uint32_t)depth;
@@ -1004,6 +1092,23 @@ extern "C" int pt_filter_stats(pt_context* c, uint64_t* fallbacks) {
   CU(cudaMemcpyAsync(&h, c->d_live + kMaxDepth, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   *fallbacks = h;
+  return PT_OK;
+}
+
+extern "C" int pt_set_direct_lighting(pt_context* c, int on) {
+  CTX(c);
+  CU(cudaStreamSynchronize(c->stream));
+  c->nee = on != 0;
+  return PT_OK;
+}
+extern "C" int pt_shadow_rays(pt_context* c, uint64_t* shadow_rays, int* n_lights) {
+  CTX(c);
+  if (!shadow_rays) { pt_set_error_("shadow_rays is NULL"); return PT_ERR_INVALID; }
+  unsigned long long h = 0;
+  CU(cudaMemcpyAsync(&h, c->d_live + kMaxDepth + 1, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *shadow_rays = h;
+  if (n_lights) *n_lights = c->n_lights;
   return PT_OK;
 }
 

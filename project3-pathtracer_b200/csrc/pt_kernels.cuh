@@ -36,6 +36,7 @@ struct WfCtrl {
   uint32_t count[kMaxDepth + 1];     // count[d] = live paths entering depth d
   uint32_t tile_ctr[kMaxDepth + 1];  // ticket counter of the depth-d launch
   uint32_t fallbacks;                // rays whose filtered closest hit fell back to the exact scan (statistics)
+  unsigned long long shadow;         // shadow rays traced by direct light sampling
 };
 
 // ---- decoupled look-back (Merrill & Garland 2016) on 64-bit status words ----
@@ -99,6 +100,8 @@ struct BounceParams {
   int filt_cap;                      // pairs that fit in shared memory
   BvhSoA bvh;                        // hierarchy over the same filter tests for scenes with many geoms (pt_bvh.cuh)
   const float4* mats;                // 4 float4 per material
+  const float4* lights;              // direct light sampling: 3 float4 per light (E.xyz | geom) (th0..th3) (th4, type, -, -)
+  int n_lights;
   RaygenConsts cam;
   WfCtrl* ctrl;
   uint32_t depth;
@@ -134,12 +137,80 @@ __device__ __forceinline__ uint32_t atom_add_u32(uint32_t* p, uint32_t v) {  // 
 #endif
 constexpr uint32_t kTicketUnits = PT_TICKET_UNITS;
 
+// closest hit of one ray on its own (direct light sampling's shadow rays).  LINEAR: pair scan over `fs`, else hierarchy.
+template <bool LINEAR>
+__device__ __forceinline__ void closest_hit_one(const BounceParams& P, const float4* fs, f3 o, f3 d, Hit& h) {
+  ScanBest best;
+  scan_init(best);
+  bool fell_back;
+  if (LINEAR) {
+    const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene, P.filt.end[2] > P.filt.end[1]);
+    filter_scan(fs, 0, P.filt.end[3], P.filt.end, ray, best);
+    fell_back = resolve_scan(best, P.filt, P.g, P.n_geoms, o, d, h);
+  } else {
+    const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene, true);
+    bvh_traverse<false>(P.bvh, P.g, ray, best, h);
+    fell_back = resolve_bvh(best, P.bvh, P.g, P.filt.r_scene, o, d, h);
+  }
+  if (fell_back) atomicAdd(&P.ctrl->fallbacks, 1u);
+}
+
+// Direct light sampling (DESIGN.md "direct light sampling"; oracle: or_render_ex), by a whole warp; `active` lanes
+// have just sampled a diffuse bounce: o = new path origin, ns = shading normal, thr = throughput after the bounce.
+// One light, one point on it (getRandomPointOnCube's area-weighted faces / the sphere sampler, Philox block 65 + depth),
+// one shadow ray through the ordinary closest hit.
+template <bool TABLE>
+__device__ __noinline__ void direct_light(const BounceParams& P, const float4* fs, uint32_t lane, bool active, f3 ns, f3 o, f3 thr,
+                                          uint32_t pixel, uint32_t sample) {
+  bool traced = false;
+  f3 wd = mk(0, 0, 1), E = mk(0, 0, 0);
+  float cs = 0.0f, dy = 0.0f;
+  int gl = -1;
+  if (active) {
+    float v[4];
+    rng4(P.seed, pixel, sample, 65u + P.depth, v);
+    int li = (int)(v[0] * (float)P.n_lights);
+    if (li > P.n_lights - 1) li = P.n_lights - 1;
+    const float4 L0 = __ldg(P.lights + 3 * li), L1 = __ldg(P.lights + 3 * li + 1), L2 = __ldg(P.lights + 3 * li + 2);
+    gl = __float_as_int(L0.w);
+    E = mk(L0.x, L0.y, L0.z);
+    const float4 f0 = __ldg(P.g.fwd0 + gl), f1 = __ldg(P.g.fwd1 + gl), f2 = __ldg(P.g.fwd2 + gl);
+    const f3 y = __float_as_int(L2.y) == 0 ? sphere_point(f0, f1, f2, v[1], v[2])
+                                           : cube_point_th(f0, f1, f2, L1, L2.x, v[1], v[2] - 0.5f, v[3] - 0.5f);
+    const f3 wv = y - o;
+    wd = normalize(wv);
+    dy = length(wv);
+    cs = dot(ns, wd);
+    traced = cs > 0;
+  }
+  const uint32_t tmask = __ballot_sync(0xffffffffu, traced);
+  if (lane == 0 && tmask) atomicAdd(&P.ctrl->shadow, (unsigned long long)__popc(tmask));
+  if (!traced) return;
+  Hit h;
+  h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
+  closest_hit_one<TABLE>(P, fs, o, wd, h);
+  // y is visible iff the ray arrives ON the light AT y (its far side is hidden by the light itself)
+  if (h.id != gl || !((dy - h.t) < 1e-3f * dy + 1e-3f)) return;
+  const f3 n2 = TABLE ? hit_normal_table(P.normals, h)
+                      : hit_normal(__ldg(P.g.fwd0 + gl), __ldg(P.g.fwd1 + gl), __ldg(P.g.fwd2 + gl), h);
+  const float cl = -dot(n2, wd);
+  if (!(cl > 0)) return;
+  const float G = (cs * cl) / (h.t * h.t);
+  const f3 Ld = (thr * E) * G;
+  float* px = reinterpret_cast<float*>(P.accum + pixel);
+  atomicAdd(px + 0, Ld.x);
+  atomicAdd(px + 1, Ld.y);
+  atomicAdd(px + 2, Ld.z);
+}
+
 // The second half of a segment, by a whole warp: material lookup, reservation of the unit's output slots, BSDF
 // sampling, radiance of finished paths, survivors written to base + rank.  `hit` lanes carry a closest hit in h.
-// TABLE: normals from the per-geom table (few geoms, L1-resident) or from the winner's own rows (many geoms).
-template <bool LAST, bool TABLE>
-__device__ __forceinline__ void shade_and_compact(const BounceParams& P, uint32_t lane, bool hit, const Hit& h, f3 o, f3 d, f3 thr,
-                                                  uint32_t pixel, uint32_t sample) {
+// TABLE: normals from the per-geom table (few geoms, L1-resident; `fs` = the filter pairs in shared memory) or from the
+// winner's own rows (many geoms, hierarchy).  NEE: direct light sampling at diffuse bounces; `no_emit` = the path's
+// previous event was one (the flag travels in throughput.w), so a light it reaches by itself adds nothing.
+template <bool LAST, bool TABLE, bool NEE>
+__device__ __forceinline__ void shade_and_compact(const BounceParams& P, const float4* fs, uint32_t lane, bool hit, const Hit& h, f3 o, f3 d, f3 thr,
+                                                  uint32_t pixel, uint32_t sample, bool no_emit) {
   // a path survives this segment unless it left the scene or reached a light; the slot of the unit's survivors
   // is reserved before shading so that the atomic's latency hides behind it
   int mat = 0;
@@ -154,6 +225,8 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, uint32_
     ballot = __ballot_sync(0xffffffffu, alive);
     if (lane == 0 && ballot) base_raw = atom_add_u32(&P.ctrl->count[P.depth + 1], (uint32_t)__popc(ballot));
   }
+  bool sampled = false;  // NEE: this lane's bounce was diffuse and gets a light sample
+  f3 ns = mk(0, 0, 1);
   if (hit) {
     const int gi = h.id;
     const f3 n = TABLE ? hit_normal_table(P.normals, h)
@@ -161,26 +234,29 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, uint32_
     MatRows m;
     m.a = __ldg(P.mats + 4 * mat); m.b = __ldg(P.mats + 4 * mat + 1); m.c = __ldg(P.mats + 4 * mat + 2); m.d = md;
     f3 L;
+    if (NEE && !LAST) ns = dot(d, n) < 0 ? n : neg(n);  // the shading normal shade() uses
     const int kind = shade(m, P.g, gi, h.p, n, P.seed, pixel, sample, P.depth, o, d, thr, L);
-    if (kind == 3) {
+    if (kind == 3 && !(NEE && no_emit)) {
       float* px = reinterpret_cast<float*>(P.accum + pixel);
       atomicAdd(px + 0, L.x);
       atomicAdd(px + 1, L.y);
       atomicAdd(px + 2, L.z);
     }
+    sampled = NEE && !LAST && kind == 0 && P.n_lights > 0;
   }
   if (!LAST) {
     const uint32_t slot = __shfl_sync(0xffffffffu, base_raw, 0) + __popc(ballot & ((1u << lane) - 1u));
     if (alive) {
       __stcs(P.out_o + slot, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
       __stcs(P.out_d + slot, make_float4(d.x, d.y, d.z, __uint_as_float(sample)));
-      __stcs(P.out_t + slot, make_float4(thr.x, thr.y, thr.z, 0.0f));
+      __stcs(P.out_t + slot, make_float4(thr.x, thr.y, thr.z, sampled ? 1.0f : 0.0f));
     }
+    if (NEE && __any_sync(0xffffffffu, sampled)) direct_light<TABLE>(P, fs, lane, sampled, ns, o, thr, pixel, sample);
   }
 }
 
 // Few geoms (every BASELINE config but the 10k one): linear scan over the filter pairs staged in shared memory.
-template <bool FIRST, bool LAST>
+template <bool FIRST, bool LAST, bool NEE = false>
 __global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_bounce(const __grid_constant__ BounceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31u;
@@ -208,6 +284,7 @@ __global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_bounce(const 
 
     f3 o = mk(0, 0, 0), d = mk(0, 0, 1), thr = mk(1, 1, 1);
     uint32_t pixel = 0, sample = 0;
+    bool no_emit = false;
     if (valid) {
       if (FIRST) {
         pixel = idx % P.cam.npix;
@@ -218,6 +295,7 @@ __global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_bounce(const 
         o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
         d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
         thr = mk(c.x, c.y, c.z);
+        if (NEE) no_emit = c.w != 0.0f;
       }
     }
 
@@ -231,7 +309,7 @@ __global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_bounce(const 
       if (resolve_scan(best, P.filt, P.g, P.n_geoms, o, d, h)) atomicAdd(&P.ctrl->fallbacks, 1u);
     }
 
-    shade_and_compact<LAST, true>(P, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample);
+    shade_and_compact<LAST, true, NEE>(P, fs, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
     }
   }
 }
@@ -286,28 +364,29 @@ __device__ __forceinline__ void load_path(const BounceParams& P, uint32_t idx, f
 }
 
 // `n` (<= 32, warp-uniform) deferred paths, taken from the top of the warp's list: exact traversal, shading, compaction
-template <bool FIRST, bool LAST>
+template <bool FIRST, bool LAST, bool NEE>
 __device__ __noinline__ void run_deferred(const BounceParams& P, const uint32_t* list, uint32_t n) {
   const uint32_t lane = threadIdx.x & 31u;
   const bool valid = lane < n;
   f3 o = mk(0, 0, 0), d = mk(0, 0, 1), thr = mk(1, 1, 1);
   uint32_t pixel = 0, sample = 0;
+  bool no_emit = false;
   Hit h;
   h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
   if (valid) {
     const uint32_t idx = list[lane];
     load_path<FIRST>(P, idx, o, d, pixel, sample);
-    if (!FIRST) { const float4 c = __ldg(P.in_t + idx); thr = mk(c.x, c.y, c.z); }
+    if (!FIRST) { const float4 c = __ldg(P.in_t + idx); thr = mk(c.x, c.y, c.z); no_emit = NEE && c.w != 0.0f; }
     const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene, true);
     ScanBest unused;
     scan_init(unused);
     bvh_traverse<true>(P.bvh, P.g, ray, unused, h);
   }
   if (lane == 0) atomicAdd(&P.ctrl->fallbacks, n);
-  shade_and_compact<LAST, false>(P, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample);
+  shade_and_compact<LAST, false, NEE>(P, nullptr, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
 }
 
-template <bool FIRST, bool LAST>
+template <bool FIRST, bool LAST, bool NEE = false>
 __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(const __grid_constant__ BounceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31u;
@@ -386,6 +465,7 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
       const bool valid = j < n_pool;
       f3 o = mk(0, 0, 0), d = mk(0, 0, 1), thr = mk(1, 1, 1);
       uint32_t pixel = 0, sample = 0;
+      bool no_emit = false;
       Hit h;
       h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
       bool defer = false;
@@ -394,25 +474,25 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
         const float2 res = S.res[j];
         o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
         d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
-        if (!FIRST) { const float4 c = __ldcs(P.in_t + base + j); thr = mk(c.x, c.y, c.z); }
+        if (!FIRST) { const float4 c = __ldcs(P.in_t + base + j); thr = mk(c.x, c.y, c.z); no_emit = NEE && c.w != 0.0f; }
         const int k1 = __float_as_int(res.y);
         if (k1 >= 0) defer = !confirm_candidate(k1, res.x, P.bvh, P.g, o, d, h);  // k1 < 0: every geom is a proven miss
       }
       const uint32_t dmask = __ballot_sync(0xffffffffu, defer);
       if (defer) S.defer[n_defer + __popc(dmask & ((1u << lane) - 1u))] = base + j;
       n_defer += __popc(dmask);
-      shade_and_compact<LAST, false>(P, lane, valid && !defer && h.id >= 0, h, o, d, thr, pixel, sample);
+      shade_and_compact<LAST, false, NEE>(P, nullptr, lane, valid && !defer && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
       if (n_defer >= kUnit) {
         __syncwarp();
         n_defer -= kUnit;
-        run_deferred<FIRST, LAST>(P, S.defer + n_defer, kUnit);
+        run_deferred<FIRST, LAST, NEE>(P, S.defer + n_defer, kUnit);
         __syncwarp();
       }
     }
   }
   if (n_defer) {
     __syncwarp();
-    run_deferred<FIRST, LAST>(P, S.defer, n_defer);
+    run_deferred<FIRST, LAST, NEE>(P, S.defer, n_defer);
   }
 }
 
@@ -422,6 +502,7 @@ __global__ void k_accum_counts(const WfCtrl* ctrl, unsigned long long* live_tota
   // atomics: the two wavefront slots run on different streams and may fold their counts at the same time
   if (d < max_depth) atomicAdd(live_total + d, (unsigned long long)ctrl->count[d]);
   if (d == 0) atomicAdd(live_total + kMaxDepth, (unsigned long long)ctrl->fallbacks);
+  if (d == 1) atomicAdd(live_total + kMaxDepth + 1, ctrl->shadow);
 }
 
 // the ray-independent part of hit_normal, once per scene: identical instructions, so identical bits

@@ -65,6 +65,19 @@ __device__ __forceinline__ f3 cube_point(float4 f0, float4 f1, float4 f2, float 
   return mulMV(f0, f1, f2, p.x, p.y, p.z, 1.0f);
 }
 
+// the same with the five face thresholds precomputed per geom (pt_api.cu: build_lights evaluates the expressions above
+// in the same binary32 order on the host); th = (th0..th3), th4
+__device__ __forceinline__ f3 cube_point_th(float4 f0, float4 f1, float4 f2, float4 th, float th4, float roulette, float a, float b) {
+  f3 p;
+  if (roulette < th.x) p = mk(a, b, 0.5f);
+  else if (roulette < th.y) p = mk(a, b, -0.5f);
+  else if (roulette < th.z) p = mk(0.5f, a, b);
+  else if (roulette < th.w) p = mk(-0.5f, a, b);
+  else if (roulette < th4) p = mk(a, 0.5f, b);
+  else p = mk(a, -0.5f, b);
+  return mulMV(f0, f1, f2, p.x, p.y, p.z, 1.0f);
+}
+
 // uniform direction on the unit sphere: z = 1 - 2*xi1, azimuth 2*pi*xi2
 __device__ __forceinline__ f3 sphere_dir(float xi1, float xi2) {
   const float z = 1.0f - 2.0f * xi1;

@@ -213,3 +213,30 @@ def test_sampling_properties(oracle, ref_gold, pt):
     want = np.exp(-(ab * dist[:, None]).astype(np.float64))
     assert np.abs(T - want).max() <= 2e-7 * 1 + 0 and (np.abs(T - want) / want).max() < 2e-7
     assert (oracle.transmission([[0, 0, 0]], [3.0]) == 1).all() and (oracle.transmission([[200, 300, 1e30]], [1.0]) == 0).all()
+
+
+def test_direct_light_sampling_is_unbiased(oracle, pt):
+    """oracle only: a grey floor under a sphere light seen through one tiny pixel.  Radiance leaving the floor point
+    below a sphere light of radius r at height D is albedo * Le * (r/D)^2; plain path tracing and direct light
+    sampling must both converge to it."""
+    from scenes_for_tests import build_geom
+    m = np.zeros(2, pt.MATERIAL_DTYPE)
+    m[0]["color"] = [0.5, 0.5, 0.5]
+    m[1]["color"] = [1, 1, 1]
+    m[1]["emittance"] = 2.0
+    g = np.zeros(2, pt.GEOM_DTYPE)
+    g[0] = build_geom(pt, 1, 0, (0, -0.5, 0), (0, 0, 0), (100, 1, 100))
+    g[1] = build_geom(pt, 0, 1, (0, 5, 0), (0, 0, 0), (2, 2, 2))
+    cam = np.zeros(1, pt.CAMERA_DTYPE)
+    v = np.array([0, -1, -3.0]) / np.sqrt(10.0)
+    cam["resolution"][0], cam["position"][0], cam["view"][0] = [2, 2], [0, 1, 3], v
+    cam["up"][0], cam["fov"][0] = [0, 1, 0], [0.01, 0.01]
+    spp, want = 40000, 0.5 * 2.0 * (1 / 5) ** 2
+    for nee, tol in ((False, 0.03), (True, 0.01)):
+        img, live, _ = oracle.render(oracle.make_scene(g, m, cam, direct_lighting=nee), 0, spp, 2, 3)
+        assert abs(float(img.mean()) / spp - want) < tol * want
+        assert (oracle.last_shadow_rays > 0) == nee
+    g[1] = build_geom(pt, 1, 1, (0, 5, 0), (10, 20, 30), (2, 1, 3))  # a rotated box light: both estimators agree
+    a = oracle.render(oracle.make_scene(g, m, cam, direct_lighting=False), 0, spp, 2, 3)[0].mean() / spp
+    b = oracle.render(oracle.make_scene(g, m, cam, direct_lighting=True), 0, spp, 2, 3)[0].mean() / spp
+    assert abs(a - b) < 0.03 * a

@@ -218,6 +218,10 @@ __device__ __forceinline__ void filter_scan(const float4* v, int first, int last
 __device__ __forceinline__ bool exact_hit(int type, float4 i0, float4 i1, float4 i2, float4 f0, float4 f1, float4 f2,
                                           f3 o, f3 d, float& dist, f3& P, int& ncode) {
   // intersections.h:85-86: object-space origin and re-normalised direction
+  // (Scalar on purpose.  Doing both products side by side with the packed f32x2 instructions would halve these 42
+  // operations, but ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad false -- also when
+  // they are spelled fma(a, b, -0) and fma(a, 1, b) -- and the fused sums differ in the last bit: parity with the
+  // reference's arithmetic was lost (tests/test_gpu_parity.py::test_closest_hit_primary_rays) for no gain.  DESIGN.md 3b.)
   const f3 ro = mulMV(i0, i1, i2, o.x, o.y, o.z, 1.0f);
   const f3 rd = normalize(mulMV(i0, i1, i2, d.x, d.y, d.z, 0.0f));
   float t;

@@ -131,3 +131,23 @@ def test_headless_driver_renders_every_frame_of_an_animation(pt, oracle, tmp_pat
         assert (got8 == want8).all()  # two samples per pixel: the sum is order-independent, so bits match
         imgs.append(got8)
     assert (imgs[0] != imgs[1]).any() and (imgs[1] != imgs[2]).any()
+
+
+def test_headless_driver_direct_lighting_switch(pt, oracle, tmp_path):
+    """pt_render ... direct=1: same segments as the oracle with direct light sampling, pixels within one LSB"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "scenes"))
+    import gen_scenes
+    p = tmp_path / "small.txt"
+    p.write_text(gen_scenes.sample_scene((96, 64), 2))
+    out = subprocess.check_output([os.path.join(ROOT, "project3-pathtracer_b200", "pt_render"), "scene=%s" % p,
+                                   "depth=4", "seed=8", "direct=1", "out=%s" % (tmp_path / "d.png"), "json=1"], text=True)
+    info = json.loads(out.strip().splitlines()[-1])
+    g, m, cam, lens = pt.Scene(p).frame(0)
+    want_sum, live, _ = oracle.render(oracle.make_scene(g, m, cam, lens, direct_lighting=True), 0, 2, 4, 8)
+    assert oracle.last_shadow_rays > 0 and info["segments"] == int(live.sum())
+    want8 = pt.image_to_rgb8(want_sum / np.float32(2), 96, 64)
+    got8 = np.asarray(Image.open(info["file"]).convert("RGB"))
+    assert np.abs(got8.astype(int) - want8.astype(int)).max() <= 1 and (got8 != want8).mean() < 1e-2
+    plain, _, _ = oracle.render(oracle.make_scene(g, m, cam, lens), 0, 2, 4, 8)
+    assert (pt.image_to_rgb8(plain / np.float32(2), 96, 64) != want8).mean() > 0.2  # and it is a different estimator

@@ -339,7 +339,7 @@ constexpr int kPoolUnits = PT_BVH_POOL_UNITS, kPool = kPoolUnits * kUnit, kRefil
 #define PT_BVH_THREADS 256
 #endif
 #ifndef PT_BVH_MIN_BLOCKS
-#define PT_BVH_MIN_BLOCKS 3
+#define PT_BVH_MIN_BLOCKS 4  // 64 registers, 32 resident warps per SM: +3 % over 3 x 80 registers (the kernel waits on node fetches)
 #endif
 constexpr int kBvhThreads = PT_BVH_THREADS;
 struct BvhWarpSmem {

@@ -909,7 +909,7 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
       P.cam = c->cam;
       P.ctrl = ctrl;
       P.depth = (uint32_t)depth;
-      P.seed = seed;
+      P.keys = philox_keys(seed);
       P.first_sample = first_sample + s0;
       P.n_first = n_first;
       const bool first = depth == 0, last = depth == max_depth - 1;

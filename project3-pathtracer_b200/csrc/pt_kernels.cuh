@@ -105,7 +105,7 @@ struct BounceParams {
   RaygenConsts cam;
   WfCtrl* ctrl;
   uint32_t depth;
-  uint64_t seed;
+  PhiloxKeys keys;                   // round keys of the render's seed
   uint32_t first_sample, n_first;    // FIRST only: paths to generate = npix * samples in this wavefront
 };
 
@@ -168,7 +168,7 @@ __device__ __noinline__ void direct_light(const BounceParams& P, const float4* f
   int gl = -1;
   if (active) {
     float v[4];
-    rng4(P.seed, pixel, sample, 65u + P.depth, v);
+    rng4(P.keys, pixel, sample, 65u + P.depth, v);
     int li = (int)(v[0] * (float)P.n_lights);
     if (li > P.n_lights - 1) li = P.n_lights - 1;
     const float4 L0 = __ldg(P.lights + 3 * li), L1 = __ldg(P.lights + 3 * li + 1), L2 = __ldg(P.lights + 3 * li + 2);
@@ -235,7 +235,7 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const f
     m.a = __ldg(P.mats + 4 * mat); m.b = __ldg(P.mats + 4 * mat + 1); m.c = __ldg(P.mats + 4 * mat + 2); m.d = md;
     f3 L;
     if (NEE && !LAST) ns = dot(d, n) < 0 ? n : neg(n);  // the shading normal shade() uses
-    const int kind = shade(m, P.g, gi, h.p, n, P.seed, pixel, sample, P.depth, o, d, thr, L);
+    const int kind = shade(m, P.g, gi, h.p, n, P.keys, pixel, sample, P.depth, o, d, thr, L);
     if (kind == 3 && !(NEE && no_emit)) {
       float* px = reinterpret_cast<float*>(P.accum + pixel);
       atomicAdd(px + 0, L.x);
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_bounce(const 
       if (FIRST) {
         pixel = idx % P.cam.npix;
         sample = P.first_sample + idx / P.cam.npix;
-        raygen(P.cam, P.seed, pixel, sample, o, d);
+        raygen(P.cam, P.keys, pixel, sample, o, d);
       } else {
         const float4 a = __ldcs(P.in_o + idx), b = __ldcs(P.in_d + idx), c = __ldcs(P.in_t + idx);
         o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
@@ -355,7 +355,7 @@ __device__ __forceinline__ void load_path(const BounceParams& P, uint32_t idx, f
   if (FIRST) {
     pixel = idx % P.cam.npix;
     sample = P.first_sample + idx / P.cam.npix;
-    raygen(P.cam, P.seed, pixel, sample, o, d);
+    raygen(P.cam, P.keys, pixel, sample, o, d);
   } else {
     const float4 a = __ldg(P.in_o + idx), b = __ldg(P.in_d + idx);
     o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);

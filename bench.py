@@ -121,7 +121,7 @@ def run_reference(args, rank):
     tot_t = sum(t for _, t in rates)
     val = tot_s / tot_t / 1e6
     sample = "sample scene 800x800, %d spp, 8 bounces per step (BASELINE configs[0] x %d); %d segments per step" % (CPU_SPP, CPU_SPP, rates[0][0])
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -145,6 +145,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line, the JSON: libraries that write to file descriptor 1 on their own (NCCL prints
+    # "NCCL version ..." there when NCCL_DEBUG is set) are sent to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    def _emit(line):
+        os.write(json_fd, (line + "\n").encode())
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -288,7 +296,7 @@ def main():
             s1, t1, _ = cpu_oracle_rate(threads=1, spp=2)  # the same oracle on ONE core
             out["cpu_baseline_1core"] = {"value": s1 / t1 / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
                                          "sample": "sample scene 800x800, 2 spp, 8 bounces (%d segments, %.2f s)" % (s1, t1)}
-        print(json.dumps(out))
+        _emit(json.dumps(out))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

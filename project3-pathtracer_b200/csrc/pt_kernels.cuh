@@ -1,17 +1,19 @@
 // pt_kernels.cuh -- the wavefront kernels (sm_100a).
 //
-//   k_bounce<FIRST,LAST>  (k_bounce_bvh for scenes with many geoms) one path segment for every live path of the wavefront, fused:
+//   k_bounce<FIRST,LAST,NEE>  (k_bounce_bvh for scenes with many geoms) one path segment for every live path of the wavefront, fused:
 //                           [FIRST: raygen + depth of field]  (raycastFromCameraKernel, src/raytraceKernel.cu:40-45)
 //                           closest hit over SoA geometry staged in shared memory (src/intersections.h:74-117)
-//                           BSDF sampling with Philox (calculateBSDF, src/interactions.h:99-104)
+//                           BSDF sampling with Philox (calculateBSDF, src/interactions.h:99-104), absorption inside glass
+//                           (calculateTransmission, :31-33), [NEE: direct light sampling, src/intersections.h:133-182]
 //                           radiance accumulation in HBM (the running image of src/raytraceKernel.cu:118-120,154)
-//                           stream compaction of the survivors (README.md:63-70): warp ballot -> block scan ->
-//                           decoupled look-back across tiles, survivors written once, in order, to the other
-//                           ping-pong buffer.
-//                         Persistent CTAs take tiles from a ticket counter, so a tile's predecessors are always
-//                         resident and the look-back cannot deadlock; the live count never visits the host.
+//                           stream compaction of the survivors (README.md:63-70): warp ballot -> ranks inside a 32-path
+//                           unit, one slot-reserving atomic per unit, survivors written once to the other ping-pong
+//                           buffer.
+//                         Persistent CTAs; warps take units from a ticket counter and never wait for each other; the
+//                         live count never visits the host.
 //   k_raygen_list / k_intersect_list   the same device functions on caller-supplied lists (parity entry points)
-//   k_compact_u32                      the compaction primitive on its own
+//   k_compact_u32                      the stable compaction primitive on its own: ballot -> block scan -> decoupled look-back
+//   k_points_on_geom / k_sphere_dirs / k_transmission (pt_sampling.cuh)   sampling and absorption parity entry points
 //   k_resolve_*                        accumulation buffer -> float RGB / uchar4 (sendImageToPBO, :58-89)
 #pragma once
 #include "pt_device.cuh"

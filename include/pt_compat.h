@@ -88,6 +88,7 @@ int pt_compat_set_seed(unsigned long long seed);
 int pt_compat_set_device(int device);
 int pt_compat_set_lens(float aperture, float focal_distance);
 int pt_compat_set_exit_on_error(int on);
+int pt_compat_set_direct_lighting(int on); /* pt_set_direct_lighting for the calls that follow (default off) */
 int pt_compat_last_status(void);
 // drop the cached context (the reference's cudaDeviceReset() between frames, src/main.cpp:155)
 void pt_compat_reset(void);

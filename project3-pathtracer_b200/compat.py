@@ -95,6 +95,10 @@ def set_exit_on_error(on):
     lib().pt_compat_set_exit_on_error(C.c_int(1 if on else 0))
 
 
+def set_direct_lighting(on):
+    lib().pt_compat_set_direct_lighting(C.c_int(1 if on else 0))
+
+
 def last_status():
     return int(lib().pt_compat_last_status())
 

@@ -38,6 +38,7 @@ unsigned long long g_seed = 0;
 int g_device = 0;
 pt_lens g_lens{0.0f, 0.0f};
 int g_exit_on_error = 1;
+int g_direct = 0;  // pt_compat_set_direct_lighting
 int g_status = PT_OK;
 
 void fail(int rc) {
@@ -63,6 +64,7 @@ extern "C" int pt_compat_set_lens(float aperture, float focal_distance) {
   return PT_OK;
 }
 extern "C" int pt_compat_set_exit_on_error(int on) { g_exit_on_error = on; return PT_OK; }
+extern "C" int pt_compat_set_direct_lighting(int on) { g_direct = on != 0; return PT_OK; }
 extern "C" int pt_compat_last_status(void) { return g_status; }
 // The caller reads renderCam->image after every call (src/main.cpp:118-131), so its D2H copy cannot go away; but a
 // pageable destination makes it a staged ~10 GB/s copy.  Page-locking the caller's buffer in place (it lives as long as
@@ -151,6 +153,7 @@ void cudaRaytraceCore(uchar4* PBOpos, camera* renderCam, int frame, int iteratio
     if ((rc = pt_upload_sum(g.ctx, g.scaled.data()))) return fail(rc);
   }
   if (in_sequence || iterations == 1) pin(renderCam->image, npix * 3 * sizeof(float));  // a render loop, not a one-off call
+  if ((rc = pt_set_direct_lighting(g.ctx, g_direct))) return fail(rc);
   if ((rc = pt_render(g.ctx, (uint32_t)(iterations - 1), 1, g_depth, g_seed))) return fail(rc);
   if (PBOpos && (rc = pt_resolve_rgba8(g.ctx, (uint32_t)iterations, nullptr, PBOpos))) return fail(rc);
   if ((rc = pt_download_mean(g.ctx, reinterpret_cast<float*>(renderCam->image), (uint32_t)iterations))) return fail(rc);

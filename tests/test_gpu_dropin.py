@@ -151,3 +151,21 @@ def test_headless_driver_direct_lighting_switch(pt, oracle, tmp_path):
     assert np.abs(got8.astype(int) - want8.astype(int)).max() <= 1 and (got8 != want8).mean() < 1e-2
     plain, _, _ = oracle.render(oracle.make_scene(g, m, cam, lens), 0, 2, 4, 8)
     assert (pt.image_to_rgb8(plain / np.float32(2), 96, 64) != want8).mean() > 0.2  # and it is a different estimator
+
+
+def test_cudaRaytraceCore_with_direct_lighting(pt, compat, oracle, sample_scene):
+    """pt_compat_set_direct_lighting(1): the reference entry point renders with direct light sampling"""
+    cam = with_resolution(sample_scene["camera"], 64, 64)
+    rs = compat.RefScene([(sample_scene["geoms"], cam)], sample_scene["materials"], iterations=2)
+    compat.reset(); compat.set_trace_depth(3); compat.set_seed(5); compat.set_exit_on_error(False)
+    compat.set_direct_lighting(True)
+    try:
+        compat.cudaRaytraceCore(None, rs.camera, 0, 1, rs.materials, len(rs.materials), rs.geoms, len(rs.geoms))
+        assert compat.last_status() == 0
+        scn = oracle.make_scene(sample_scene["geoms"], sample_scene["materials"], cam, direct_lighting=True)
+        want, _, _ = oracle.render(scn, 0, 1, 3, 5)
+        assert oracle.last_shadow_rays > 0
+        assert np.allclose(rs.image, want, rtol=1e-5, atol=1e-6)
+    finally:
+        compat.set_direct_lighting(False)
+        compat.reset()

@@ -196,6 +196,15 @@ int pt_random_directions_in_sphere(int device, int n, const float* xi1, const fl
  * material has ABSCOEFF > 0. */
 int pt_calculate_transmission(int device, int n, const float* absorption, const float* distance, float* out);
 
+/* What the reference's own cudaRaytraceCore leaves in renderCam->image TODAY: its raytraceRay is a stub that overwrites
+ * every pixel with generateRandomNumberFromThread(resolution, (float)iterations, x, y) (src/raytraceKernel.cu:29-36,
+ * 93-104).  Reproduced bit for bit so that a maintainer can check the drop-in against the unmodified reference: order
+ * PT_STUB_ORDER_DEVICE = the draw order of the reference's kernel on the GPU, PT_STUB_ORDER_HOST = of its host build
+ * (the three draws are arguments of one constructor call, so their order is the compiler's). */
+#define PT_STUB_ORDER_DEVICE 0
+#define PT_STUB_ORDER_HOST 1
+int pt_reference_stub_image(int device, int width, int height, int iterations, int order, float* rgb);
+
 /* ---- scene file and image file (host side; same formats as the reference) ---- */
 typedef struct pt_scene pt_scene;
 /* scene::scene(string), src/scene.cpp:11-35.  rotat_degrees = 0 reproduces the reference exactly (ROTAT is

@@ -12,6 +12,33 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libpt_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libptref.so")
+REF_GPU_SO = os.path.join(HERE, "_ref", "libptref_gpu.so")  # the reference's own (stub) kernels for sm_100a
+
+
+class RefGpu:
+    """The reference's own cudaRaytraceCore and kernels (oracle/ref_kernel_shim.cu); needs a GPU except noise_host."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_GPU_SO)
+
+    def __init__(self):
+        self.lib = C.CDLL(REF_GPU_SO)
+
+    def noise_host(self, W, H, time):
+        out = np.zeros((W * H, 3), np.float32)
+        self.lib.ref_noise_host(C.c_int(W), C.c_int(H), C.c_float(time), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def cudaRaytraceCore(self, W, H, iterations, image=None):
+        """one call of the reference's entry point: returns (renderCam->image afterwards, the PBO bytes)"""
+        img = np.zeros((W * H, 3), np.float32) if image is None else np.ascontiguousarray(image, np.float32).copy()
+        pbo = np.zeros((W * H, 4), np.uint8)
+        rc = self.lib.ref_cudaRaytraceCore(C.c_int(W), C.c_int(H), C.c_int(iterations), img.ctypes.data_as(C.c_void_p),
+                                           pbo.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RuntimeError("ref_cudaRaytraceCore: CUDA error %d" % rc)
+        return img, pbo
 
 GEOM_DTYPE = np.dtype(
     [
@@ -83,7 +110,7 @@ def build_oracle(force=False):
     ):
         subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     if os.path.isdir("/root/reference/src"):
-        srcs = [os.path.join(HERE, "ref_shim.cu"), os.path.join(HERE, "ref_scene_shim.cpp")]
+        srcs = [os.path.join(HERE, "ref_shim.cu"), os.path.join(HERE, "ref_scene_shim.cpp"), os.path.join(HERE, "ref_kernel_shim.cu")]
         if force or not os.path.exists(REF_SO) or os.path.getmtime(REF_SO) < max(os.path.getmtime(s) for s in srcs):
             subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
 
@@ -135,6 +162,12 @@ class Oracle:
         g = np.ascontiguousarray(geom)
         out = np.zeros(3, np.float32)
         self.lib.or_getRadiuses(_p(g), _p(out))
+        return out
+
+    def noise_image(self, W, H, time, reversed_order):
+        """generateRandomNumberFromThread over a W x H frame (the reference's stub renderer)"""
+        out = np.zeros((W * H, 3), np.float32)
+        self.lib.or_noise_image(C.c_int(W), C.c_int(H), C.c_float(time), C.c_int(1 if reversed_order else 0), _p(out))
         return out
 
     def random_points(self, geom, seeds):

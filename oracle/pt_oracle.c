@@ -317,6 +317,24 @@ static inline float minstd_uniform(minstd* r, float a, float b) {
   return (res * (b - a)) + a;
 }
 
+/* (R) generateRandomNumberFromThread, src/raytraceKernel.cu:29-36: what the reference's raytraceRay stub writes into
+ * each pixel (:93-104).  index = x + y * resolution.x (binary32), seed = hash((unsigned)(index * time)), three draws.
+ * reversed = 1: the draw order of the reference's HOST build (g++ evaluates the constructor's arguments right to
+ * left), pinned against it; reversed = 0: left to right (its device build, checked on the GPU box). */
+void or_generateRandomNumberFromThread(int W, int H, float time, int x, int y, int reversed, float out[3]) {
+  (void)H;
+  int index = (int)((float)x + ((float)y * (float)W));
+  minstd rng;
+  minstd_seed(&rng, or_hash((unsigned int)((float)index * time)));
+  float a = minstd_uniform(&rng, 0.0f, 1.0f), b = minstd_uniform(&rng, 0.0f, 1.0f), c = minstd_uniform(&rng, 0.0f, 1.0f);
+  if (reversed) { out[0] = c; out[1] = b; out[2] = a; }
+  else { out[0] = a; out[1] = b; out[2] = c; }
+}
+void or_noise_image(int W, int H, float time, int reversed, float* out) {
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) or_generateRandomNumberFromThread(W, H, time, x, y, reversed, out + 3 * ((size_t)y * W + x));
+}
+
 /* body of src/intersections.h:140-172 given the three draws: face by area-weighted roulette, then the two
  * in-face coordinates (a = first vec3 argument that is random, b = second) */
 /* the five face thresholds of :149-169 and the total area; they depend on the geom only */

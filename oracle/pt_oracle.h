@@ -81,6 +81,9 @@ float or_sphereIntersectionTest(const or_static_geom* g, const float o[3], const
 void or_getRadiuses(const or_static_geom* g, float out[3]);
 /* src/intersections.h:133-175 with the host build's argument evaluation order; thrust minstd inside */
 void or_getRandomPointOnCube(const or_static_geom* g, float randomSeed, float out[3]);
+/* src/raytraceKernel.cu:29-36 (the stub renderer's per-pixel noise); reversed = the host build's draw order */
+void or_generateRandomNumberFromThread(int W, int H, float time, int x, int y, int reversed, float out[3]);
+void or_noise_image(int W, int H, float time, int reversed, float* out);
 /* reference formula with libm sinf/cosf, for pinning only */
 void or_hemisphere_ref(const float n[3], float xi1, float xi2, float out[3]);
 

@@ -256,6 +256,17 @@ def calculate_transmission(absorption, distance, device=0):
     return out
 
 
+STUB_ORDER_DEVICE, STUB_ORDER_HOST = 0, 1
+
+
+def reference_stub_image(width, height, iterations, order=STUB_ORDER_DEVICE, device=0):
+    """the noise image the reference's raytraceRay stub writes for this iteration (src/raytraceKernel.cu:93-104)"""
+    out = np.zeros((width * height, 3), np.float32)
+    _check(lib().pt_reference_stub_image(C.c_int(device), C.c_int(width), C.c_int(height), C.c_int(iterations),
+                                         C.c_int(order), _p(out)))
+    return out
+
+
 def compact_u32(values, flags, device=0):
     """Stream compaction primitive on its own (pt_compact_u32): values[flags != 0], order preserved."""
     v, f = _arr(values, np.uint32).ravel(), _arr(flags, np.uint8).ravel()

@@ -1245,6 +1245,22 @@ extern "C" int pt_calculate_transmission(int device, int n, const float* absorpt
   return PT_OK;
 }
 
+extern "C" int pt_reference_stub_image(int device, int width, int height, int iterations, int order, float* rgb) {
+  if (width <= 0 || height <= 0 || !rgb || (order != 0 && order != 1) || (uint64_t)width * height > (1ull << 28)) {
+    pt_set_error_("bad arguments");
+    return PT_ERR_INVALID;
+  }
+  if (int rc = select_device_(device)) return rc;
+  DevBuf<float> d;
+  const size_t n = (size_t)width * height * 3;
+  CU(d.alloc(n));
+  const dim3 block(8, 8), grid((width + 7) / 8, (height + 7) / 8);  // the reference's launch shape, src/raytraceKernel.cu:113-115
+  k_reference_stub<<<grid, block>>>(width, height, (float)iterations, order, d.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(rgb, d.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return PT_OK;
+}
+
 // ---------------------------------------------------------------- multi-GPU combine (single process, one context per GPU)
 // One ncclReduce(sum) of the float4 accumulation images to ctxs[0] over NVLink / NVSwitch.  NCCL is resolved at run
 // time (dlopen) so that a process that already carries its own libnccl (PyTorch) keeps a single copy; processes

@@ -8,6 +8,7 @@
 //   getRandomDirectionInSphere (stub)     src/interactions.h:93-95
 //   calculateTransmission (stub)          src/interactions.h:31-33
 //   thrust::minstd_rand / uniform_real_distribution<float>   (the generator the reference seeds at :135-137)
+//   generateRandomNumberFromThread        src/raytraceKernel.cu:29-36   (the noise its raytraceRay stub writes, :93-104)
 //
 // getRandomPointOnCube is evaluation-order dependent in the reference (`glm::vec3(u02(rng), u02(rng), .5)`): its host
 // build draws the SECOND random coordinate first (g++ evaluates arguments right to left).  The oracle is pinned to
@@ -104,6 +105,25 @@ __device__ __forceinline__ f3 random_point_on_geom(int type, float4 f0, float4 f
   const float b = minstd_uniform(rng, -0.5f, 0.5f);  // the host build's order: second coordinate first
   const float a = minstd_uniform(rng, -0.5f, 0.5f);
   return cube_point(f0, f1, f2, roulette, a, b);
+}
+
+// generateRandomNumberFromThread (src/raytraceKernel.cu:29-36), what the reference's raytraceRay stub writes into every
+// pixel (:93-104): index = x + y * resolution.x in binary32, seed = hash((unsigned)(index * time)), three draws of
+// uniform(0,1).  The three draws are arguments of one glm::vec3(...) call, so their order is the compiler's: reversed =
+// false draws x, y, z (what the reference's kernel does on the device), true draws z, y, x (its host build under g++).
+__device__ __forceinline__ f3 reference_noise(float res_x, float time, int x, int y, bool reversed) {
+  const int index = (int)((float)x + ((float)y * res_x));
+  Minstd rng;
+  minstd_seed(rng, ref_hash((uint32_t)((float)index * time)));
+  const float a = minstd_uniform(rng, 0.0f, 1.0f), b = minstd_uniform(rng, 0.0f, 1.0f), c = minstd_uniform(rng, 0.0f, 1.0f);
+  return reversed ? mk(c, b, a) : mk(a, b, c);
+}
+__global__ void k_reference_stub(int W, int H, float time, int reversed, float* rgb) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const f3 c = reference_noise((float)W, time, x, y, reversed != 0);
+  float* o = rgb + 3 * ((size_t)y * W + x);
+  o[0] = c.x; o[1] = c.y; o[2] = c.z;
 }
 
 // ---- parity entry points (lists) ----

@@ -67,6 +67,8 @@ def test_compute_entry_points_fail_loudly_without_a_gpu(pt, sample_scene):
         pt.random_directions_in_sphere([0.5], [0.5])
     with pytest.raises(pt.PtError):
         pt.calculate_transmission([[1, 1, 1]], [1.0])
+    with pytest.raises(pt.PtError):
+        pt.reference_stub_image(8, 8, 1)
 
 
 def test_argument_validation(pt):

@@ -240,3 +240,12 @@ def test_direct_light_sampling_is_unbiased(oracle, pt):
     a = oracle.render(oracle.make_scene(g, m, cam, direct_lighting=False), 0, spp, 2, 3)[0].mean() / spp
     b = oracle.render(oracle.make_scene(g, m, cam, direct_lighting=True), 0, spp, 2, 3)[0].mean() / spp
     assert abs(a - b) < 0.03 * a
+
+
+def test_generateRandomNumberFromThread_bit_exact(oracle, samp_gold):
+    """the noise the reference's stub renderer writes (src/raytraceKernel.cu:29-36, 93-104), host build's draw order"""
+    for k in samp_gold["ref_noise_host"]:
+        got = oracle.noise_image(k["W"], k["H"], k["time"], True)
+        assert same_bits(got.ravel(), f32(k["rgb"]))
+        fwd = oracle.noise_image(k["W"], k["H"], k["time"], False)
+        assert same_bits(fwd[:, ::-1], got)  # the other order is the same three numbers reversed

@@ -146,7 +146,11 @@ int pt_intersect(pt_context* ctx, int n, const float* origin, const float* direc
  * preserved; out must have room for n entries */
 int pt_compact_u32(int device, const uint32_t* values, const uint8_t* flags, uint64_t n, uint32_t* out,
                    uint64_t* n_out);
-/* the same, and the kernel alone timed on the device (CUDA events, mean of `iters` launches after one warm-up) */
+/* how pt_compact_u32 runs: 0 (default) = three launches -- per-tile counts (warp ballot / popc, block reduce), exclusive
+ * scan of the tile aggregates (block scan + decoupled look-back across CTAs), scatter -- so that no streaming CTA ever
+ * waits for another; 1 = the single-pass kernel with the look-back inside (half the throughput on B200) */
+int pt_set_compact_mode(int mode);
+/* the same, and the kernel(s) alone timed on the device (CUDA events, mean of `iters` launches after one warm-up) */
 int pt_compact_u32_timed(int device, const uint32_t* values, const uint8_t* flags, uint64_t n, uint32_t* out,
                          uint64_t* n_out, int iters, float* kernel_ms);
 

@@ -267,6 +267,11 @@ def reference_stub_image(width, height, iterations, order=STUB_ORDER_DEVICE, dev
     return out
 
 
+def set_compact_mode(mode):
+    """0 = count / scan / scatter (default), 1 = single pass with the look-back inside"""
+    _check(lib().pt_set_compact_mode(C.c_int(mode)))
+
+
 def compact_u32(values, flags, device=0):
     """Stream compaction primitive on its own (pt_compact_u32): values[flags != 0], order preserved."""
     v, f = _arr(values, np.uint32).ravel(), _arr(flags, np.uint8).ravel()

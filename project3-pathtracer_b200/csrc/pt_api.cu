@@ -1112,6 +1112,12 @@ extern "C" int pt_shadow_rays(pt_context* c, uint64_t* shadow_rays, int* n_light
   return PT_OK;
 }
 
+static int g_compact_mode = 0;  // 0: count / scan / scatter (three launches), 1: k_compact_u32 (single pass)
+extern "C" int pt_set_compact_mode(int mode) {
+  if (mode != 0 && mode != 1) { pt_set_error_("compact mode %d (0 = three kernels, 1 = single pass)", mode); return PT_ERR_INVALID; }
+  g_compact_mode = mode;
+  return PT_OK;
+}
 static int compact_impl(int device, const uint32_t* values, const uint8_t* flags, uint64_t n, uint32_t* out,
                         uint64_t* n_out, int timed_iters, float* kernel_ms) {
   if (!n_out || (n > 0 && (!values || !flags || !out))) { pt_set_error_("bad arguments"); return PT_ERR_INVALID; }
@@ -1125,11 +1131,14 @@ static int compact_impl(int device, const uint32_t* values, const uint8_t* flags
   CU(cudaSetDevice(device));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
-  DevBuf<uint32_t> dv, dout, dctl;
+  DevBuf<uint32_t> dv, dout, dctl, dcount, dprefix;
   DevBuf<uint8_t> df;
-  DevBuf<uint64_t> dst;
+  DevBuf<uint64_t> dst, dst2;
   const uint64_t tiles = (n + kCompactTile - 1) / kCompactTile;
+  const uint64_t chunks = (tiles + kScanChunk - 1) / kScanChunk;  // CTAs of k_compact_scan: <= 1024, all resident
   CU(dv.alloc(n)); CU(dout.alloc(n)); CU(dctl.alloc(2)); CU(df.alloc(n)); CU(dst.alloc(tiles));
+  CU(dcount.alloc(tiles)); CU(dprefix.alloc(tiles)); CU(dst2.alloc(chunks));
+  CU(cudaMemset(dst2.p, 0, chunks * sizeof(uint64_t)));
   CU(cudaMemcpy(dv.p, values, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(df.p, flags, n, cudaMemcpyHostToDevice));
   CU(cudaMemset(dst.p, 0, tiles * sizeof(uint64_t)));
@@ -1137,6 +1146,12 @@ static int compact_impl(int device, const uint32_t* values, const uint8_t* flags
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_compact_u32, kCompactThreads, 0));
   uint64_t grid = (uint64_t)per_sm * prop.multiProcessorCount;
   if (tiles < grid) grid = tiles;
+  int per_sm_c = 0, per_sm_s = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, k_compact_count, kCompactThreads, 0));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_compact_scatter, kCompactThreads, 0));
+  uint64_t grid_c = (uint64_t)per_sm_c * prop.multiProcessorCount, grid_s = (uint64_t)per_sm_s * prop.multiProcessorCount;
+  if (tiles < grid_c) grid_c = tiles;
+  if (tiles < grid_s) grid_s = tiles;
   // the status words carry the launch epoch, so repeated launches need no clearing in between
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timed_iters > 0) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); }
@@ -1144,7 +1159,13 @@ static int compact_impl(int device, const uint32_t* values, const uint8_t* flags
   for (int it = 0; it < launches; it++) {
     CU(cudaMemsetAsync(dctl.p, 0, 2 * sizeof(uint32_t), 0));
     if (timed_iters > 0 && it == 1) CU(cudaEventRecord(e0, 0));
-    k_compact_u32<<<(unsigned)grid, kCompactThreads>>>(dv.p, df.p, (uint32_t)n, dout.p, dctl.p + 1, dctl.p, dst.p, (uint32_t)(it + 1));
+    if (g_compact_mode == 1) {
+      k_compact_u32<<<(unsigned)grid, kCompactThreads>>>(dv.p, df.p, (uint32_t)n, dout.p, dctl.p + 1, dctl.p, dst.p, (uint32_t)(it + 1));
+    } else {
+      k_compact_count<<<(unsigned)grid_c, kCompactThreads>>>(df.p, (uint32_t)n, (uint32_t)tiles, dcount.p);
+      k_compact_scan<<<(unsigned)chunks, kScanThreads>>>(dcount.p, (uint32_t)tiles, dprefix.p, dctl.p + 1, dst2.p, (uint32_t)(it + 1));
+      k_compact_scatter<<<(unsigned)grid_s, kCompactThreads>>>(dv.p, df.p, (uint32_t)n, (uint32_t)tiles, dprefix.p, dout.p);
+    }
     CU(cudaGetLastError());
   }
   if (timed_iters > 0) {

@@ -673,6 +673,142 @@ __global__ void __launch_bounds__(kCompactThreads, PT_COMPACT_BLOCKS) k_compact_
   }
 }
 
+// ---- the same compaction with the ordered prefix taken out of the streaming kernels (three launches) ----
+// k_compact_u32 keeps every resident CTA waiting in its look-back until the prefix wave reaches it, with no loads in
+// flight meanwhile: it streams at 31-41 % of the HBM copy peak (profiles/r01_compact_u32.txt).  Here the dependency
+// between tiles is confined to a tiny kernel over the tiles' aggregates:
+//   k_compact_count    flags only (1 B per element): kept elements per 4096-element tile
+//   k_compact_scan     exclusive prefix over the tile aggregates: 1024 aggregates per CTA, block scan, decoupled look-back
+//                      across the CTAs (at most 1024 CTAs for 2^32 elements: all resident)
+//   k_compact_scatter  values + flags again, ranks inside the tile exactly as k_compact_u32 computes them, base from the
+//                      prefix array: no CTA ever waits for another
+// Traffic 6 B read per element + 4 B written per kept one (the flags are read twice) against 5 + 4 algorithmic.
+__device__ __forceinline__ uint32_t flag_bytes_to_bits(uint32_t fb) {  // byte != 0 -> 1, per byte
+  return ((((fb & 0x7f7f7f7fu) + 0x7f7f7f7fu) | fb) & 0x80808080u) >> 7;
+}
+__global__ void __launch_bounds__(kCompactThreads) k_compact_count(const uint8_t* __restrict__ flags, uint32_t n, uint32_t n_tiles,
+                                                                   uint32_t* __restrict__ tile_count) {
+  __shared__ uint32_t s_warp[kCompactThreads / 32];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const bool aligned = (reinterpret_cast<uintptr_t>(flags) & 3u) == 0;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t chunk = tile * kCompactTile + warp * (32 * kCompactItems);
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t e = chunk + (j * 32 + lane) * 4;
+      uint32_t fb = 0;
+      if (e + 4 <= n && aligned) fb = __ldg(reinterpret_cast<const uint32_t*>(flags + e));  // read again by the scatter: keep it cached
+      else
+        for (int k = 0; k < 4; k++)
+          if (e + k < n) fb |= (uint32_t)flags[e + k] << (8 * k);
+      cnt += (flag_bytes_to_bits(fb) * 0x01010101u) >> 24;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_warp[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t t = 0;
+      for (int w = 0; w < kCompactThreads / 32; w++) t += s_warp[w];
+      tile_count[tile] = t;
+    }
+    __syncthreads();
+  }
+}
+constexpr int kScanThreads = 256, kScanItems = 4, kScanChunk = kScanThreads * kScanItems;
+__global__ void __launch_bounds__(kScanThreads) k_compact_scan(const uint32_t* __restrict__ tile_count, uint32_t n_tiles,
+                                                               uint32_t* __restrict__ tile_prefix, uint32_t* n_out,
+                                                               uint64_t* status, uint32_t epoch) {
+  __shared__ uint32_t s_warp[kScanThreads / 32];
+  __shared__ uint32_t s_base;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t first = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+  uint32_t c[kScanItems], mine = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) { c[k] = first + k < n_tiles ? tile_count[first + k] : 0u; mine += c[k]; }
+  uint32_t incl = mine;  // inclusive scan over the threads of the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((int)lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = lane < kScanThreads / 32 ? s_warp[lane] : 0u;
+    uint32_t wi = w;
+#pragma unroll
+    for (int o = 1; o < kScanThreads / 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if ((int)lane >= o) wi += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, wi, kScanThreads / 32 - 1);
+    const uint32_t excl = lookback_exclusive(status, blockIdx.x, epoch, total);
+    if (lane < kScanThreads / 32) s_warp[lane] = wi - w;
+    if (lane == 0) {
+      s_base = excl;
+      if (blockIdx.x == gridDim.x - 1) *n_out = excl + total;
+    }
+  }
+  __syncthreads();
+  uint32_t run = s_base + s_warp[warp] + (incl - mine);
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    if (first + k < n_tiles) tile_prefix[first + k] = run;
+    run += c[k];
+  }
+}
+__global__ void __launch_bounds__(kCompactThreads, PT_COMPACT_BLOCKS) k_compact_scatter(const uint32_t* __restrict__ values,
+                                                                                        const uint8_t* __restrict__ flags, uint32_t n,
+                                                                                        uint32_t n_tiles,
+                                                                                        const uint32_t* __restrict__ tile_prefix,
+                                                                                        uint32_t* __restrict__ out) {
+  __shared__ uint32_t s_warp[kCompactThreads / 32];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const bool aligned = (reinterpret_cast<uintptr_t>(values) & 15u) == 0 && (reinterpret_cast<uintptr_t>(flags) & 3u) == 0;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t chunk = tile * kCompactTile + warp * (32 * kCompactItems);
+    uint4 v[4];
+    uint32_t f[4], before[4], run = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t e = chunk + (j * 32 + lane) * 4;
+      uint32_t fb = 0;
+      if (e + 4 <= n && aligned) {
+        v[j] = __ldcs(reinterpret_cast<const uint4*>(values + e));
+        fb = __ldcs(reinterpret_cast<const uint32_t*>(flags + e));
+      } else {
+        uint32_t t[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (e + k < n) { t[k] = values[e + k]; fb |= (uint32_t)flags[e + k] << (8 * k); }
+        v[j] = make_uint4(t[0], t[1], t[2], t[3]);
+      }
+      f[j] = flag_bytes_to_bits(fb);
+      const uint32_t cnt = (f[j] * 0x01010101u) >> 24;
+      const uint32_t b0 = __ballot_sync(0xffffffffu, cnt & 1u), b1 = __ballot_sync(0xffffffffu, cnt & 2u),
+                     b2 = __ballot_sync(0xffffffffu, cnt & 4u);
+      before[j] = run + __popc(b0 & lt) + 2u * __popc(b1 & lt) + 4u * __popc(b2 & lt);
+      run += __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+    }
+    __syncthreads();  // s_warp of the previous tile is no longer read
+    if (lane == 0) s_warp[warp] = run;
+    __syncthreads();
+    uint32_t base = __ldg(tile_prefix + tile);
+    for (uint32_t w = 0; w < warp; w++) base += s_warp[w];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint32_t pos = base + before[j];
+      if (f[j] & 0x00000001u) out[pos++] = v[j].x;
+      if (f[j] & 0x00000100u) out[pos++] = v[j].y;
+      if (f[j] & 0x00010000u) out[pos++] = v[j].z;
+      if (f[j] & 0x01000000u) out[pos++] = v[j].w;
+    }
+  }
+}
+
 // ---- exhaustive self-test of sqrt_ieee / rcp_ieee / inv_sqrt_ieee (pt_device.cuh) against the generic operators ----
 // every one of the 2^32 bit patterns; NaN results compare equal to NaN results
 __global__ void k_selftest_math(unsigned long long* bad) {

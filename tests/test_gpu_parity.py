@@ -199,7 +199,9 @@ def test_upload_sum_roundtrip(pt, sample_scene):
 
 @pytest.mark.parametrize("n", [0, 1, 3, 4, 5, 31, 32, 33, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 4095, 4096, 4097,
                                8191, 8193, 100003, 10_000_000])
-def test_compaction_is_a_stable_partition(pt, n):
+@pytest.mark.parametrize("mode", [0, 1])  # 0: count / scan / scatter, 1: single pass with the look-back inside
+def test_compaction_is_a_stable_partition(pt, n, mode):
+    pt.set_compact_mode(mode)
     rng = np.random.default_rng(n)
     v = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
     for density in (0.0, 0.5, 1.0, 0.03):
@@ -211,6 +213,7 @@ def test_compaction_is_a_stable_partition(pt, n):
     if n > 8:  # unaligned views of the host arrays end up aligned on the device; ragged tails are covered by the sizes
         out = pt.compact_u32(v[1:], (v[1:] & 1).astype(np.uint8))
         assert (out == v[1:][(v[1:] & 1) != 0]).all()
+    pt.set_compact_mode(0)
 
 
 def test_single_guard_ieee_math_exhaustive(pt):

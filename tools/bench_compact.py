@@ -24,11 +24,15 @@ def main():
         v = rng.integers(0, 2**32, n, dtype=np.uint32)
         for keep in (0.1, 0.5, 0.7, 1.0):
             f = (rng.random(n) < keep).astype(np.uint8)
-            out, ms = pt.compact_u32_timed(v, f, iters=10)
-            assert (out == v[f != 0]).all()
-            bytes_alg = 5.0 * n + 4.0 * len(out)
-            print(json.dumps({"n": n, "keep": keep, "kept": int(len(out)), "kernel_ms": ms, "Gelem_per_s": n / ms / 1e6,
-                              "GB_per_s": bytes_alg / ms / 1e6, "frac_of_hbm_peak": bytes_alg / ms / 1e6 / peak}), flush=True)
+            for mode, name in ((0, "count/scan/scatter"), (1, "single pass")):
+                pt.set_compact_mode(mode)
+                out, ms = pt.compact_u32_timed(v, f, iters=10)
+                assert (out == v[f != 0]).all()
+                bytes_alg = 5.0 * n + 4.0 * len(out)
+                print(json.dumps({"mode": name, "n": n, "keep": keep, "kept": int(len(out)), "kernel_ms": ms,
+                                  "Gelem_per_s": n / ms / 1e6, "GB_per_s": bytes_alg / ms / 1e6,
+                                  "frac_of_hbm_peak": bytes_alg / ms / 1e6 / peak}), flush=True)
+    pt.set_compact_mode(0)
 
 
 if __name__ == "__main__":

@@ -148,6 +148,15 @@ class Oracle:
     def hash(self, a):
         return int(self.lib.or_hash(C.c_uint(a & 0xFFFFFFFF)))
 
+    def epsilonCheck(self, a, b):
+        return bool(self.lib.or_epsilonCheck(C.c_float(a), C.c_float(b)))
+
+    def ray_helpers(self, d):
+        """(getInverseDirectionOfRay, getSignOfRay) of a direction"""
+        d, inv, sign = _f32(d), np.zeros(3, np.float32), np.zeros(3, np.float32)
+        self.lib.or_ray_helpers(_p(d), _p(inv), _p(sign))
+        return inv, sign
+
     def multiplyMV(self, m16, v4):
         m, v, out = _f32(m16), _f32(v4), np.zeros(3, np.float32)
         self.lib.or_multiplyMV(_p(m), _p(v), _p(out))
@@ -351,6 +360,14 @@ class Ref:
         out = np.zeros_like(normal)
         self.lib.ref_hemisphere_batch(C.c_int(normal.shape[0]), _p(normal), _p(xi1), _p(xi2), _p(out))
         return out
+
+    def epsilonCheck(self, a, b):
+        return bool(self.lib.ref_epsilonCheck(C.c_float(a), C.c_float(b)))
+
+    def ray_helpers(self, d):
+        d, inv, sign = _f32(d), np.zeros(3, np.float32), np.zeros(3, np.float32)
+        self.lib.ref_ray_helpers(_p(d), _p(inv), _p(sign))
+        return inv, sign
 
     def random_points_on_cube(self, geom, seeds):
         g, sd = np.ascontiguousarray(geom), _f32(seeds).ravel()

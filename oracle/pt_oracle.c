@@ -54,6 +54,18 @@ unsigned int or_hash(unsigned int a) {
   return a;
 }
 
+/* (R) src/intersections.h:37-43: binary64 comparison against EPSILON = 1e-9 (src/utilities.h:24); unused by the
+ * reference's implemented code */
+int or_epsilonCheck(float a, float b) { return fabs(fabs((double)a) - fabs((double)b)) < 0.000000001 ? 1 : 0; }
+/* (R) src/intersections.h:62-70: 1.0 / d in binary64, rounded to binary32 on the way into the vec3; signs as 0 / 1.
+ * Slab-test helpers the reference provides and never calls; the box test of this repo uses the binary32 reciprocal. */
+void or_ray_helpers(const float d[3], float inv[3], float sign[3]) {
+  for (int k = 0; k < 3; k++) {
+    inv[k] = (float)(1.0 / (double)d[k]);
+    sign[k] = (float)(int)(inv[k] < 0);
+  }
+}
+
 /* (R) src/intersections.h:53-59: rows x,y,z of the row-stored cudaMat4 times v, left to right. */
 static inline v3 mulMV(const float* m, float vx, float vy, float vz, float vw) {
   v3 r;

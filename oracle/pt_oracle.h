@@ -75,6 +75,8 @@ typedef struct {
 
 /* ---- (R) reference-pinned pieces ---- */
 unsigned int or_hash(unsigned int a);
+int or_epsilonCheck(float a, float b);
+void or_ray_helpers(const float d[3], float inv[3], float sign[3]);
 void or_multiplyMV(const float m[16], const float v[4], float out[3]);
 void or_getPointOnRay(const float o[3], const float d[3], float t, float out[3]);
 float or_sphereIntersectionTest(const or_static_geom* g, const float o[3], const float d[3], float p[3], float n[3]);

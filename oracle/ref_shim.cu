@@ -100,6 +100,14 @@ void ref_getRandomPointOnCube_batch(const void* geom172, int n, const float* see
   }
 }
 
+// the small helpers: epsilonCheck :37-43, getInverseDirectionOfRay :62-64, getSignOfRay :67-70
+int ref_epsilonCheck(float a, float b) { return epsilonCheck(a, b) ? 1 : 0; }
+void ref_ray_helpers(const float* d3, float* inv3, float* sign3) {
+  ray r; r.origin = glm::vec3(0); r.direction = glm::vec3(d3[0], d3[1], d3[2]);
+  glm::vec3 a = getInverseDirectionOfRay(r), b = getSignOfRay(r);
+  inv3[0] = a.x; inv3[1] = a.y; inv3[2] = a.z; sign3[0] = b.x; sign3[1] = b.y; sign3[2] = b.z;
+}
+
 // the stubs this repo specifies itself: what the reference returns today (all zeros)
 void ref_sampling_stubs(float* out9) {
   staticGeom g; std::memset(&g, 0, sizeof(g));

@@ -249,3 +249,13 @@ def test_generateRandomNumberFromThread_bit_exact(oracle, samp_gold):
         assert same_bits(got.ravel(), f32(k["rgb"]))
         fwd = oracle.noise_image(k["W"], k["H"], k["time"], False)
         assert same_bits(fwd[:, ::-1], got)  # the other order is the same three numbers reversed
+
+
+def test_small_helpers_bit_exact(oracle, samp_gold):
+    """epsilonCheck, getInverseDirectionOfRay, getSignOfRay (src/intersections.h:37-43, 62-70) against the reference"""
+    for k in samp_gold["epsilonCheck"]:
+        assert int(oracle.epsilonCheck(float(f32([k["a"]])[0]), float(f32([k["b"]])[0]))) == k["r"]
+    with np.errstate(divide="ignore"):
+        for k in samp_gold["ray_helpers"]:
+            inv, sign = oracle.ray_helpers(f32(k["d"]))
+            assert same_bits(inv, f32(k["inv"])) and same_bits(sign, f32(k["sign"]))

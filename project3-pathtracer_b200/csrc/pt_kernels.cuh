@@ -161,8 +161,11 @@ __device__ __forceinline__ void closest_hit_one(const BounceParams& P, const flo
 // have just sampled a diffuse bounce: o = new path origin, ns = shading normal, thr = throughput after the bounce.
 // One light, one point on it (getRandomPointOnCube's area-weighted faces / the sphere sampler, Philox block 65 + depth),
 // one shadow ray through the ordinary closest hit.
+#ifndef PT_NEE_INLINE
+#define PT_NEE_INLINE __forceinline__  // measured: 19.75 G rays/s inlined, 19.25 out of line (sample scene, direct light on)
+#endif
 template <bool TABLE>
-__device__ __noinline__ void direct_light(const BounceParams& P, const float4* fs, uint32_t lane, bool active, f3 ns, f3 o, f3 thr,
+__device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const float4* fs, uint32_t lane, bool active, f3 ns, f3 o, f3 thr,
                                           uint32_t pixel, uint32_t sample) {
   bool traced = false;
   f3 wd = mk(0, 0, 1), E = mk(0, 0, 0);

@@ -296,6 +296,23 @@ def main():
             s1, t1, _ = cpu_oracle_rate(threads=1, spp=2)  # the same oracle on ONE core
             out["cpu_baseline_1core"] = {"value": s1 / t1 / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
                                          "sample": "sample scene 800x800, 2 spp, 8 bounces (%d segments, %.2f s)" % (s1, t1)}
+            # the other kernel the north star asks a roofline for: the stable stream-compaction primitive (an HBM-bound
+            # kernel by nature), device-timed on its own, outside the timed region above
+            try:
+                n_c, keep = 1 << 27, 0.7
+                rng = np.random.default_rng(1)
+                vals = rng.integers(0, 2 ** 32, n_c, dtype=np.uint32)
+                flg = (rng.random(n_c, dtype=np.float32) < keep).astype(np.uint8)
+                kept, cms = pt.compact_u32_timed(vals, flg, iters=10)
+                cbytes = 5.0 * n_c + 4.0 * len(kept)
+                out["compaction_primitive"] = {
+                    "kernels": "k_compact_count + k_compact_scan + k_compact_scatter (pt_compact_u32)", "elements": n_c,
+                    "keep": keep, "ms": cms, "Gelem_per_s": n_c / cms / 1e6, "bound": "hbm", "achieved": cbytes / cms / 1e6,
+                    "peak": peak, "unit": "GB/s", "frac": cbytes / cms / 1e6 / peak,
+                    "algorithmic_bytes": "5 B read per element + 4 B written per kept element"}
+                del vals, flg, kept
+            except Exception as e:  # never let the side measurement take the headline line down
+                out["compaction_primitive"] = {"error": str(e)}
         _emit(json.dumps(out))
     ctx.close()
     if world > 1:

@@ -164,6 +164,10 @@ class Context:
         _check(lib().pt_counters(self._h, C.byref(paths), C.byref(segs), _p(live)))
         return paths.value, segs.value, live
 
+    def set_band_pixels(self, pixels):
+        """pixels per wavefront band (0 = automatic); results do not depend on it"""
+        _check(lib().pt_set_band_pixels(self._h, C.c_uint32(pixels)))
+
     def set_direct_lighting(self, on=True):
         """direct light sampling at diffuse bounces (pt_set_direct_lighting); off by default"""
         _check(lib().pt_set_direct_lighting(self._h, C.c_int(1 if on else 0)))

@@ -79,6 +79,7 @@ struct pt_context {
   uint32_t W = 0, H = 0, npix = 0;
   // wavefront
   uint64_t wf_capacity = 0;  // paths
+  uint32_t band_pixels = 0;  // pixels per wavefront band; 0 = automatic (pt_set_band_pixels)
   // Two wavefronts are in flight at a time, each on its own internal stream with its own path-state buffers and control
   // block: the tail of one wavefront's launch (its last units) overlaps the head of the other's instead of idling SMs.
   static const int kSlots = 2;
@@ -745,7 +746,7 @@ static int alloc_wavefront(pt_context* c, uint64_t max_paths) {
   c->d_state = nullptr; c->wf_capacity = 0;
   // ... as long as the accumulation image leaves room in the 126 MB L2 for two wavefronts' streams: at 3840x2160 (133 MB
   // of float4 sums) a second concurrent sweep over the image costs more in missed RED atomics than the overlap gains
-  c->n_slots = (size_t)c->npix * sizeof(float4) <= ((size_t)48 << 20) ? pt_context::kSlots : 1;
+  c->n_slots = pt_context::kSlots;  // (frames larger than that are rendered band by band, pt_render, so the rule below holds again)
   if (const char* env = getenv("PT_B200_SLOTS")) c->n_slots = atoi(env) >= 2 ? pt_context::kSlots : 1;  // developer knob
   // the internal streams exist only when they are used
   if (c->n_slots > 1 && !c->wf_stream[0]) {
@@ -835,6 +836,13 @@ extern "C" int pt_set_wavefront_paths(pt_context* c, uint64_t max_paths) {
   return alloc_wavefront(c, max_paths);
 }
 
+extern "C" int pt_set_band_pixels(pt_context* c, uint32_t pixels) {
+  CTX(c);
+  CU(cudaStreamSynchronize(c->stream));
+  c->band_pixels = pixels;
+  return PT_OK;
+}
+
 extern "C" int pt_set_stream(pt_context* c, void* cuda_stream) {
   CTX(c);
   CU(cudaStreamSynchronize(c->stream));
@@ -875,24 +883,36 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
   if (max_depth < 1 || max_depth > kMaxDepth) { pt_set_error_("max_depth %d outside [1,%d]", max_depth, kMaxDepth); return PT_ERR_INVALID; }
   if ((uint64_t)first_sample + n_samples > 0xFFFFFFFFull) { pt_set_error_("sample index overflow"); return PT_ERR_INVALID; }
   CU(cudaEventRecord(c->ev0, c->stream));
-  const uint32_t spp_wf = (uint32_t)(c->wf_capacity / c->npix);
   const uint64_t cap = c->wf_capacity;
+  // Bands: a frame whose float4 accumulation image does not leave room in the 126 MB L2 (> 48 MB, e.g. 3840x2160) is
+  // rendered in bands of 1 Mi pixels (16 MB of sums) with proportionally more samples per wavefront, so that the radiance
+  // atomics of the wavefronts in flight keep hitting L2 instead of DRAM.  Results do not depend on it (RNG streams are
+  // keyed by pixel and sample).  3840x2160, Gseg/s by band size: 0.5 Mi 27.3, 1 Mi 27.2, 2 Mi 26.9, 4 Mi 22.1, unbanded 24.9.
+  uint32_t band_cap = c->band_pixels ? c->band_pixels
+                                     : ((size_t)c->npix * sizeof(float4) <= ((size_t)48 << 20) ? c->npix : (1u << 20));
+  if (band_cap > c->npix) band_cap = c->npix;
+  if ((uint64_t)band_cap > cap) band_cap = (uint32_t)cap;
+  const uint32_t spp_band = (uint32_t)(cap / band_cap);  // samples per wavefront of a full band (>= 1)
   // fork: wavefront i runs on internal stream i % kSlots, after everything queued on the caller's stream so far
-  const int n_wf = (int)((n_samples + spp_wf - 1) / spp_wf);
-  const int slots_used = n_wf < c->n_slots ? n_wf : c->n_slots;
+  const uint64_t n_bands = ((uint64_t)c->npix + band_cap - 1) / band_cap;
+  const uint64_t n_wf = n_bands * (((uint64_t)n_samples + spp_band - 1) / spp_band);
+  const int slots_used = n_wf < (uint64_t)c->n_slots ? (int)n_wf : c->n_slots;
   const bool forked = slots_used > 1;  // a single wavefront in flight simply runs on the caller's stream
   if (forked) {
     CU(cudaEventRecord(c->ev_fork, c->stream));
     for (int i = 0; i < slots_used; i++) CU(cudaStreamWaitEvent(c->wf_stream[i], c->ev_fork, 0));
   }
-  int wf = 0;
+  uint64_t wf = 0;
+  for (uint32_t pix0 = 0; pix0 < c->npix; pix0 += band_cap) {
+  const uint32_t band = c->npix - pix0 < band_cap ? c->npix - pix0 : band_cap;
+  const uint32_t spp_wf = (uint32_t)(cap / band);
   for (uint32_t s0 = 0; s0 < n_samples; s0 += spp_wf, wf++) {
-    const int sl = wf % slots_used;
+    const int sl = (int)(wf % (uint64_t)slots_used);
     cudaStream_t st = forked ? c->wf_stream[sl] : c->stream;
     float4* S = c->d_state + (size_t)sl * 6 * cap;
     WfCtrl* ctrl = c->d_ctrl + sl;
     const uint32_t ns = (n_samples - s0 < spp_wf) ? (n_samples - s0) : spp_wf;
-    const uint32_t n_first = ns * c->npix;
+    const uint32_t n_first = ns * band;
     CU(cudaMemsetAsync(ctrl, 0, sizeof(WfCtrl), st));
     for (int depth = 0; depth < max_depth; depth++) {
       BounceParams P;
@@ -912,6 +932,7 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
       P.keys = philox_keys(seed);
       P.first_sample = first_sample + s0;
       P.n_first = n_first;
+      P.pix0 = pix0; P.band = band;
       const bool first = depth == 0, last = depth == max_depth - 1;
       cudaError_t e;
       if (first && last) e = launch_bounce<true, true>(c, 1, P, n_first, st);
@@ -924,6 +945,7 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
     c->launches++;
     CU(cudaGetLastError());
     c->paths_total += n_first;
+  }
   }
   // join: the caller's stream continues when both internal streams are done
   for (int i = 0; forked && i < slots_used; i++) {

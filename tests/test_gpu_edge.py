@@ -132,3 +132,23 @@ def test_update_scene_switches_between_pair_scan_and_hierarchy(pt, sample_scene)
             ctx.render(0, 2, 6, 13)
             assert ctx.counters()[2][:6].tolist() == want[1]
             assert (_bits(ctx.download_sum()) == _bits(want[0])).all()
+
+
+def test_banded_wavefronts_change_nothing(pt, oracle, sample_scene):
+    """large frames are rendered band by band (pt_set_band_pixels; automatic above 48 MB of accumulation image): the image
+    and the live counts are those of the unbanded render and of the oracle -- ragged last band, bands smaller than a
+    wavefront, bands larger than a wavefront, two wavefronts in flight"""
+    from conftest import same_bits, with_resolution
+    cam = with_resolution(sample_scene["camera"], 128, 96)
+    g, m = sample_scene["geoms"], sample_scene["materials"]
+    want, want_live, _ = oracle.render(oracle.make_scene(g, m, cam), 3, 2, 8, 9)
+    with pt.Context(g, m, cam) as c:
+        for band, wf in ((0, 0), (5000, 0), (5000, 3000), (1, 4096), (12287, 12288 * 2), (128 * 96, 128 * 96)):
+            c.set_band_pixels(band)
+            if wf:
+                c.set_wavefront_paths(max(wf, 128 * 96))  # (capacity is rounded to whole frames)
+            c.clear()
+            c.render(3, 2, 8, 9)
+            _, _, live = c.counters()
+            assert live[:8].tolist() == want_live.tolist(), (band, wf)
+            assert same_bits(c.download_sum(), want), (band, wf)

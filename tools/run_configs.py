@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_configs.jsonl"))
     ap.add_argument("--png-dir", default=os.path.join(ROOT, "gpurun_out"))
     ap.add_argument("--only", default="")
+    ap.add_argument("--band", type=int, default=0, help="pixels per wavefront band (pt_set_band_pixels; 0 = automatic)")
     ap.add_argument("--direct", action="store_true", help="direct light sampling on (pt_set_direct_lighting)")
     ap.add_argument("--filter-scale", type=float, default=1.0, help="experiment: scale of the filter's rounding-error bounds")
     args = ap.parse_args()
@@ -61,6 +62,7 @@ def main():
             if args.filter_scale != 1.0:
                 ctx.set_filter_scale(args.filter_scale)
             ctx.set_direct_lighting(args.direct)
+            ctx.set_band_pixels(args.band)
             ctx.render(0, min(spp, wf_spp), depth, 565)  # warm-up
             ctx.sync()
             ctx.clear()

@@ -285,7 +285,7 @@ def main():
                          "algorithmic_bytes_per_launch": alg_bytes / n_bounce, "launches_per_step": n_bounce,
                          "avg_launch_us": 1e3 * ms_per_step / n_bounce,
                          "note": "achieved = algorithmic bytes 96*(S-P) + 32*P of a step / CUDA-event time of the step; the step is "
-                                 "%d k_bounce launches (99.9 %% of its GPU time, profiles/r01_launches_v13.csv), two wavefronts in "
+                                 "%d k_bounce launches (99.9 %% of its GPU time, profiles/r01_launches_v14.csv), two wavefronts in "
                                  "flight on two streams, so this is bytes per average launch / (step time / launches)" % n_bounce},
         }
         if world == 1 and not args.no_cpu_baseline:

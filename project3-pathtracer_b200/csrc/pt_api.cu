@@ -1243,6 +1243,9 @@ static int points_impl(int device, const pt_static_geom* g, int mode, int n, con
   if (!g || n < 0 || (n > 0 && (!in || !points))) { pt_set_error_("bad arguments"); return PT_ERR_INVALID; }
   if (g->type != 0 && g->type != 1) { pt_set_error_("geom type %d has no surface sampler (sphere = 0, cube = 1)", g->type); return PT_ERR_INVALID; }
   if (n == 0) return PT_OK;
+  if (mode == 0)  // the reference converts the seed float -> unsigned (src/intersections.h:135): defined for [0, 2^32) only
+    for (int i = 0; i < n; i++)
+      if (!(in[i] >= 0.0f && in[i] < 4294967296.0f)) { pt_set_error_("seeds[%d] = %g outside [0, 2^32)", i, (double)in[i]); return PT_ERR_INVALID; }
   if (int rc = select_device_(device)) return rc;
   const size_t per = mode == 0 ? 1 : 3;
   DevBuf<float> din, dout;

@@ -71,6 +71,9 @@ def test_empty_and_invalid(pt, sample_scene):
     mesh["type"] = 2
     with pytest.raises(pt.PtError):
         pt.random_points_on_geom(mesh, [1.0])
+    for bad in (-1.0, float("nan"), 4294967296.0, float("inf")):  # float -> unsigned is defined on [0, 2^32) only
+        with pytest.raises(pt.PtError):
+            pt.random_points_on_geom(g[0:1], [3.0, bad])
 
 
 def test_absorbing_glass_paths_match_oracle(pt, oracle, sample_scene):

@@ -629,7 +629,7 @@ double or_render_ex(const or_scene* sc, uint32_t first_sample, uint32_t n_sample
   int nt = 1;
   (void)threads;
 #endif
-  static or_light lights_buf[1024];
+  or_light lights_buf[1024];  /* 36 KB on the stack; more lights than that are ignored (build_lights caps) */
   or_light* lights = lights_buf;
   int n_lights = 0;
   if (sc->direct_lighting) n_lights = build_lights(sc, lights, 1024);

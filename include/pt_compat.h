@@ -89,6 +89,10 @@ int pt_compat_set_device(int device);
 int pt_compat_set_lens(float aperture, float focal_distance);
 int pt_compat_set_exit_on_error(int on);
 int pt_compat_set_direct_lighting(int on); /* pt_set_direct_lighting for the calls that follow (default off) */
+/* 1: cudaRaytraceCore behaves exactly like the UNMODIFIED reference does today -- its raytraceRay is a stub that fills
+ * renderCam->image with per-pixel noise and converts that to the PBO (src/raytraceKernel.cu:93-104,149-154) -- so a
+ * build can be checked against the reference before the renderer is switched on (default 0) */
+int pt_compat_set_reference_stub(int on);
 int pt_compat_last_status(void);
 // drop the cached context (the reference's cudaDeviceReset() between frames, src/main.cpp:155)
 void pt_compat_reset(void);

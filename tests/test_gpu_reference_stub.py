@@ -45,3 +45,26 @@ def test_resolve_rgba8_equals_sendImageToPBO(pt, refgpu, sample_scene):
             assert (got[:, :3] == want).all() and (got[:, 3] == 0).all()
             if scale == 1.0:
                 assert (got == pbo_ref).all()
+
+
+def test_cudaRaytraceCore_drop_in_equals_the_reference_entry_point(pt, refgpu, sample_scene):
+    """the same call -- cudaRaytraceCore(pbo, camera, frame, iterations, ...) -- into the reference's own library and into
+    ours (stub mode): renderCam->image and the device PBO come back identical, byte for byte"""
+    import importlib
+    import torch
+    compat = importlib.import_module("project3-pathtracer_b200.compat")
+    W, H = 96, 64
+    cam = with_resolution(sample_scene["camera"], W, H)
+    rs = compat.RefScene([(sample_scene["geoms"], cam)], sample_scene["materials"], iterations=3)
+    compat.reset(); compat.set_exit_on_error(False); compat.set_reference_stub(True)
+    try:
+        for k in (1, 2, 9):
+            pbo = torch.full((W * H * 4,), 0xAB, dtype=torch.uint8, device="cuda")
+            compat.cudaRaytraceCore(pbo.data_ptr(), rs.camera, 0, k, rs.materials, len(rs.materials), rs.geoms, len(rs.geoms))
+            assert compat.last_status() == 0
+            img_ref, pbo_ref = refgpu.cudaRaytraceCore(W, H, k)
+            assert same_bits(rs.image, img_ref)
+            assert (pbo.cpu().numpy().reshape(-1, 4) == pbo_ref).all()
+    finally:
+        compat.set_reference_stub(False)
+        compat.reset()

@@ -521,6 +521,7 @@ static RaygenConsts make_raygen(const pt_camera_data& c, const pt_lens* lens) {
   R.fh = c.resolution[1];
   R.W = (uint32_t)(int)c.resolution[0];
   R.npix = R.W * (uint32_t)(int)c.resolution[1];
+  R.divW = make_fastdiv(R.W);
   R.aperture = lens ? lens->aperture : 0.0f;
   R.focal = lens ? lens->focal_distance : 0.0f;
   return R;
@@ -933,6 +934,7 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
       P.first_sample = first_sample + s0;
       P.n_first = n_first;
       P.pix0 = pix0; P.band = band;
+      P.div_band = make_fastdiv(band);
       const bool first = depth == 0, last = depth == max_depth - 1;
       cudaError_t e;
       if (first && last) e = launch_bounce<true, true>(c, 1, P, n_first, st);

@@ -110,6 +110,7 @@ struct BounceParams {
   PhiloxKeys keys;                   // round keys of the render's seed
   uint32_t first_sample, n_first;    // FIRST only: paths to generate = band * samples in this wavefront
   uint32_t pix0, band;               // FIRST only: the wavefront covers pixels [pix0, pix0 + band) (the whole frame unless banded)
+  FastDiv div_band;                  // FIRST only: path index -> (sample, pixel of the band)
 };
 
 // Work decomposition of k_bounce: the unit of work is ONE WARP x 32 consecutive paths.  Warps take units from a
@@ -293,8 +294,9 @@ __global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_bounce(const 
     bool no_emit = false;
     if (valid) {
       if (FIRST) {
-        pixel = P.pix0 + idx % P.band;
-        sample = P.first_sample + idx / P.band;
+        const uint32_t si = fastdiv(idx, P.div_band);
+        pixel = P.pix0 + (idx - si * P.band);
+        sample = P.first_sample + si;
         raygen(P.cam, P.keys, pixel, sample, o, d);
       } else {
         const float4 a = __ldcs(P.in_o + idx), b = __ldcs(P.in_d + idx), c = __ldcs(P.in_t + idx);
@@ -359,8 +361,9 @@ constexpr size_t kBvhSmemBytes = sizeof(BvhWarpSmem) * (kBvhThreads / 32);
 template <bool FIRST>
 __device__ __forceinline__ void load_path(const BounceParams& P, uint32_t idx, f3& o, f3& d, uint32_t& pixel, uint32_t& sample) {
   if (FIRST) {
-    pixel = P.pix0 + idx % P.band;
-    sample = P.first_sample + idx / P.band;
+    const uint32_t si = fastdiv(idx, P.div_band);
+    pixel = P.pix0 + (idx - si * P.band);
+    sample = P.first_sample + si;
     raygen(P.cam, P.keys, pixel, sample, o, d);
   } else {
     const float4 a = __ldg(P.in_o + idx), b = __ldg(P.in_d + idx);

@@ -107,6 +107,13 @@ def cpu_oracle_rate(threads=0, spp=CPU_SPP):
     return segs, secs, nthreads
 
 
+_JSON_FD = 1  # the process's original stdout (main() moves everything else to stderr)
+
+
+def _emit(line):
+    os.write(_JSON_FD, (line + "\n").encode())
+
+
 def run_reference(args, rank):
     """--impl reference: the CPU path on the host cores (rank 0 only)."""
     if rank != 0:
@@ -147,12 +154,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     # stdout carries exactly ONE line, the JSON: libraries that write to file descriptor 1 on their own (NCCL prints
     # "NCCL version ..." there when NCCL_DEBUG is set) are sent to stderr instead
+    global _JSON_FD
     sys.stdout.flush()
-    json_fd = os.dup(1)
+    _JSON_FD = os.dup(1)
     os.dup2(2, 1)
-    global _emit
-    def _emit(line):
-        os.write(json_fd, (line + "\n").encode())
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -113,6 +113,11 @@ def build_oracle(force=False):
         srcs = [os.path.join(HERE, "ref_shim.cu"), os.path.join(HERE, "ref_scene_shim.cpp"), os.path.join(HERE, "ref_kernel_shim.cu")]
         if force or not os.path.exists(REF_SO) or os.path.getmtime(REF_SO) < max(os.path.getmtime(s) for s in srcs):
             subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+        # the drop-in build test: a host compiled against the reference's own headers, linked with libpt_b200.so
+        dropin, main = os.path.join(HERE, "_ref", "ref_dropin"), os.path.join(HERE, "ref_dropin_main.cpp")
+        lib = os.path.join(os.path.dirname(HERE), "project3-pathtracer_b200", "libpt_b200.so")
+        if os.path.exists(lib) and (force or not os.path.exists(dropin) or os.path.getmtime(dropin) < os.path.getmtime(main)):
+            subprocess.check_call(["make", "-s", "-C", HERE, "dropin"])
 
 
 def _f32(a):

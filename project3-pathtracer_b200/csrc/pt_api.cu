@@ -97,6 +97,9 @@ struct pt_context {
   uchar4* d_rgba8 = nullptr;   // staging for the 8-bit resolve
   int grid_blocks[4] = {0, 0, 0, 0};  // persistent grid per (FIRST,LAST) variant
   int grid_blocks_nee[4] = {0, 0, 0, 0};  // ... of the direct-light-sampling variants
+  int grid_blocks_q[2] = {0, 0}, grid_blocks_q_nee[2] = {0, 0};  // k_bounce_q<LAST> (depths >= 1 of the linear mode)
+  size_t q_smem_total = 0;            // k_bounce_q: filter geometry + the warps' candidate queues
+  bool use_q = true;                  // depths >= 1 run k_bounce_q (PT_B200_FUSED=1: the fused k_bounce everywhere, for A/B runs)
   int mode = -1;                      // 0: linear scan over pairs staged in shared memory, 1: hierarchy (pt_bvh.cuh)
   size_t smem_bytes = 0;   // k_bounce: filter geometry
   size_t geom_smem = 0;    // filter geometry only (k_intersect_list)
@@ -553,6 +556,22 @@ static int setup_variant(pt_context* c, int slot) {
   return PT_OK;
 }
 
+template <bool L>
+static int setup_variant_q(pt_context* c, int slot) {
+  int per_sm = 0, per_sm_nee = 0;
+  constexpr bool N = true;  // (the last segment never samples a light, but it honours the no-emission flag)
+  CU(cudaFuncSetAttribute(k_bounce_q<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem_total));
+  CU(cudaFuncSetAttribute(k_bounce_q<L>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce_q<L>, kQThreads, c->q_smem_total));
+  CU(cudaFuncSetAttribute(k_bounce_q<L, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem_total));
+  CU(cudaFuncSetAttribute(k_bounce_q<L, N>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_nee, k_bounce_q<L, N>, kQThreads, c->q_smem_total));
+  if (per_sm < 1 || per_sm_nee < 1) { pt_set_error_("k_bounce_q does not fit on an SM"); return PT_ERR_CUDA; }
+  c->grid_blocks_q[slot] = per_sm * c->sm_count;
+  c->grid_blocks_q_nee[slot] = per_sm_nee * c->sm_count;
+  return PT_OK;
+}
+
 // ---- direct light sampling: the light table (DESIGN.md "direct light sampling"; same binary32 expressions, in the same
 // order, as getRadiuses / getRandomPointOnCube, src/intersections.h:120-129,140-147) ----
 static float h_length3(float x, float y, float z) { return sqrtf((x * x + y * y) + z * z); }
@@ -732,6 +751,11 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
     if ((rc = setup_variant<true, true>(c, 1))) return rc;
     if ((rc = setup_variant<false, false>(c, 2))) return rc;
     if ((rc = setup_variant<false, true>(c, 3))) return rc;
+    if (mode == 0) {
+      c->q_smem_total = c->geom_smem + q_smem_bytes();
+      if ((rc = setup_variant_q<false>(c, 0))) return rc;
+      if ((rc = setup_variant_q<true>(c, 1))) return rc;
+    }
     CU(cudaFuncSetAttribute(k_intersect_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->geom_smem));
   }
   return PT_OK;
@@ -743,21 +767,37 @@ static int alloc_wavefront(pt_context* c, uint64_t max_paths) {
   const uint64_t cap = spp * c->npix;
   if (cap > 0xFFFFFF00ull) { pt_set_error_("wavefront of %llu paths exceeds 2^32", (unsigned long long)cap); return PT_ERR_INVALID; }
   if (cap == c->wf_capacity) return PT_OK;
-  if (c->d_state) CU(cudaFree(c->d_state));
-  c->d_state = nullptr; c->wf_capacity = 0;
   // ... as long as the accumulation image leaves room in the 126 MB L2 for two wavefronts' streams: at 3840x2160 (133 MB
   // of float4 sums) a second concurrent sweep over the image costs more in missed RED atomics than the overlap gains
-  c->n_slots = pt_context::kSlots;  // (frames larger than that are rendered band by band, pt_render, so the rule below holds again)
-  if (const char* env = getenv("PT_B200_SLOTS")) c->n_slots = atoi(env) >= 2 ? pt_context::kSlots : 1;  // developer knob
+  int n_slots = pt_context::kSlots;  // (frames larger than that are rendered band by band, pt_render, so the rule below holds again)
+  if (const char* env = getenv("PT_B200_SLOTS")) n_slots = atoi(env) >= 2 ? pt_context::kSlots : 1;  // developer knob
   // the internal streams exist only when they are used
-  if (c->n_slots > 1 && !c->wf_stream[0]) {
+  if (n_slots > 1 && !c->wf_stream[0]) {
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     for (int i = 0; i < pt_context::kSlots; i++) {
       CU(cudaStreamCreateWithFlags(&c->wf_stream[i], cudaStreamNonBlocking));
       CU(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     }
   }
-  CU(cudaMalloc(&c->d_state, (size_t)c->n_slots * 6 * cap * sizeof(float4)));
+  // the old buffers go first (the two together may not fit), but a failed allocation must not leave the context
+  // without any: fall back to the previous capacity, and report the error
+  const uint64_t old_cap = c->wf_capacity;
+  const int old_slots = c->n_slots;
+  if (c->d_state) CU(cudaFree(c->d_state));
+  c->d_state = nullptr; c->wf_capacity = 0;
+  if (cudaMalloc(&c->d_state, (size_t)n_slots * 6 * cap * sizeof(float4)) != cudaSuccess) {
+    const cudaError_t e = cudaGetLastError();
+    c->d_state = nullptr;
+    if (old_cap && cudaMalloc(&c->d_state, (size_t)old_slots * 6 * old_cap * sizeof(float4)) == cudaSuccess) {
+      c->wf_capacity = old_cap; c->n_slots = old_slots;
+    } else {
+      cudaGetLastError();
+      c->d_state = nullptr;  // pt_render refuses to run until pt_set_wavefront_paths succeeds
+    }
+    pt_set_error_("cudaMalloc of %llu wavefront paths failed: %s", (unsigned long long)cap, cudaGetErrorString(e));
+    return PT_ERR_CUDA;
+  }
+  c->n_slots = n_slots;
   c->wf_capacity = cap;
   return PT_OK;
 }
@@ -803,6 +843,7 @@ extern "C" int pt_context_create(const pt_static_geom* geoms, int n_geoms, const
     return fail(PT_ERR_CUDA);
   }
   c->stream = c->own_stream;
+  if (const char* env = getenv("PT_B200_FUSED")) c->use_q = atoi(env) == 0;  // developer knob: A/B against the fused kernel
   if ((rc = upload_scene(c, geoms, n_geoms, materials, n_materials, cam, lens, true))) return fail(rc);
   if (cudaMalloc(&c->d_accum, (size_t)c->npix * sizeof(float4)) != cudaSuccess ||
       cudaMalloc(&c->d_rgb, (size_t)c->npix * 3 * sizeof(float)) != cudaSuccess ||
@@ -864,7 +905,13 @@ static cudaError_t launch_bounce(pt_context* c, int slot, const BounceParams& P,
   const bool nee = c->nee && c->n_lights > 0 && NeeOf<F, L>::value;
   constexpr bool N = NeeOf<F, L>::value;
   uint32_t grid = (uint32_t)(nee ? c->grid_blocks_nee[slot] : c->grid_blocks[slot]);
-  if (c->mode) {
+  if (!F && !c->mode && c->use_q) {  // depths >= 1, few geoms: second half re-batched by winner type
+    uint32_t gq = (uint32_t)(nee ? c->grid_blocks_q_nee[L ? 1 : 0] : c->grid_blocks_q[L ? 1 : 0]);
+    const uint32_t ctas = (n_upper + kQThreads - 1) / kQThreads;  // one unit per warp at least
+    if (ctas < gq) gq = ctas ? ctas : 1;
+    if (nee) k_bounce_q<L, N><<<gq, kQThreads, c->q_smem_total, st>>>(P);
+    else k_bounce_q<L><<<gq, kQThreads, c->q_smem_total, st>>>(P);
+  } else if (c->mode) {
     const uint32_t ctas = (n_upper + kPool * (kBvhThreads / 32) - 1) / (kPool * (kBvhThreads / 32));  // one pool per warp at least
     if (ctas < grid) grid = ctas ? ctas : 1;
     if (nee) k_bounce_bvh<F, L, N><<<grid, kBvhThreads, c->smem_bytes, st>>>(P);
@@ -883,6 +930,10 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
   CTX(c);
   if (max_depth < 1 || max_depth > kMaxDepth) { pt_set_error_("max_depth %d outside [1,%d]", max_depth, kMaxDepth); return PT_ERR_INVALID; }
   if ((uint64_t)first_sample + n_samples > 0xFFFFFFFFull) { pt_set_error_("sample index overflow"); return PT_ERR_INVALID; }
+  if (!c->d_state || c->wf_capacity == 0) {
+    pt_set_error_("no wavefront buffers (a previous pt_set_wavefront_paths failed): call it again with a size that fits");
+    return PT_ERR_STATE;
+  }
   CU(cudaEventRecord(c->ev0, c->stream));
   const uint64_t cap = c->wf_capacity;
   // Bands: a frame whose float4 accumulation image does not leave room in the 126 MB L2 (> 48 MB, e.g. 3840x2160) is
@@ -935,6 +986,7 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
       P.n_first = n_first;
       P.pix0 = pix0; P.band = band;
       P.div_band = make_fastdiv(band);
+      P.q_offset = (uint32_t)c->geom_smem;
       const bool first = depth == 0, last = depth == max_depth - 1;
       cudaError_t e;
       if (first && last) e = launch_bounce<true, true>(c, 1, P, n_first, st);
@@ -1160,7 +1212,7 @@ static int compact_impl(int device, const uint32_t* values, const uint8_t* flags
   DevBuf<uint64_t> dst, dst2;
   const uint64_t tiles = (n + kCompactTile - 1) / kCompactTile;
   const uint64_t chunks = (tiles + kScanChunk - 1) / kScanChunk;  // CTAs of k_compact_scan: <= 1024, all resident
-  CU(dv.alloc(n)); CU(dout.alloc(n)); CU(dctl.alloc(2)); CU(df.alloc(n)); CU(dst.alloc(tiles));
+  CU(dv.alloc(n)); CU(dout.alloc(n)); CU(dctl.alloc(3)); /* ticket of k_compact_u32, n_out, ticket of k_compact_scan */ CU(df.alloc(n)); CU(dst.alloc(tiles));
   CU(dcount.alloc(tiles)); CU(dprefix.alloc(tiles)); CU(dst2.alloc(chunks));
   CU(cudaMemset(dst2.p, 0, chunks * sizeof(uint64_t)));
   CU(cudaMemcpy(dv.p, values, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -1181,13 +1233,13 @@ static int compact_impl(int device, const uint32_t* values, const uint8_t* flags
   if (timed_iters > 0) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); }
   const int launches = timed_iters > 0 ? timed_iters + 1 : 1;  // one warm-up launch before the timed ones
   for (int it = 0; it < launches; it++) {
-    CU(cudaMemsetAsync(dctl.p, 0, 2 * sizeof(uint32_t), 0));
+    CU(cudaMemsetAsync(dctl.p, 0, 3 * sizeof(uint32_t), 0));
     if (timed_iters > 0 && it == 1) CU(cudaEventRecord(e0, 0));
     if (g_compact_mode == 1) {
       k_compact_u32<<<(unsigned)grid, kCompactThreads>>>(dv.p, df.p, (uint32_t)n, dout.p, dctl.p + 1, dctl.p, dst.p, (uint32_t)(it + 1));
     } else {
       k_compact_count<<<(unsigned)grid_c, kCompactThreads>>>(df.p, (uint32_t)n, (uint32_t)tiles, dcount.p);
-      k_compact_scan<<<(unsigned)chunks, kScanThreads>>>(dcount.p, (uint32_t)tiles, dprefix.p, dctl.p + 1, dst2.p, (uint32_t)(it + 1));
+      k_compact_scan<<<(unsigned)chunks, kScanThreads>>>(dcount.p, (uint32_t)tiles, dprefix.p, dctl.p + 1, dctl.p + 2, dst2.p, (uint32_t)(it + 1));
       k_compact_scatter<<<(unsigned)grid_s, kCompactThreads>>>(dv.p, df.p, (uint32_t)n, (uint32_t)tiles, dprefix.p, dout.p);
     }
     CU(cudaGetLastError());
@@ -1225,7 +1277,9 @@ extern "C" int pt_selftest_math(int device, uint64_t bad[3]) {
   DevBuf<unsigned long long> d;
   CU(d.alloc(3));
   CU(cudaMemset(d.p, 0, 3 * sizeof(unsigned long long)));
-  k_selftest_math<<<148 * 8, 256>>>(d.p);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  k_selftest_math<<<prop.multiProcessorCount * 8, 256>>>(d.p);
   CU(cudaGetLastError());
   unsigned long long h[3];
   CU(cudaMemcpy(h, d.p, sizeof(h), cudaMemcpyDeviceToHost));
@@ -1385,7 +1439,7 @@ extern "C" int pt_reduce_to_first(pt_context* const* ctxs, int n) {
     NC(g_nccl.Reduce(ctxs[i]->d_accum, ctxs[i]->d_accum, (size_t)ctxs[i]->npix * 4, 7, 0, 0, g_nccl.comms[i], ctxs[i]->stream));
   }
   NC(g_nccl.GroupEnd());
-  // counters: fold the other contexts' path totals into the first (live counts stay per context)
+  // (path / segment counters stay per context: callers add them up, pt_main.cpp)
   for (int i = 0; i < n; i++) {
     CU(cudaSetDevice(ctxs[i]->device));
     CU(cudaStreamSynchronize(ctxs[i]->stream));

@@ -130,6 +130,26 @@ __device__ __forceinline__ void scan_take(ScanBest& b, float lo, int k) {
 // Scan pairs [first, last) (global pair indices); `v` points at the record of pair `first`; end[k] = first pair
 // index after class k.  Every "miss" needs a comparison to come out TRUE, so a NaN anywhere keeps the geom as a
 // candidate.
+#ifndef PT_FILT_BRANCHFREE
+#define PT_FILT_BRANCHFREE 1
+#endif
+#if PT_FILT_BRANCHFREE
+// Branch-free: a proven miss is handed to the sink as the bound +inf, which changes nothing there (scan_take).  Some
+// lane of a warp nearly always needs the body, so the branches bought nothing but BSSY / BRA / BSYNC.
+// (sqrt of a negative discriminant is NaN, and NaN < 0 is false: the decision is the first comparison's, as before.)
+#define PT_SPHERE_HALF(H, K)                                                                          \
+  {                                                                                                   \
+    const float sd = mufu_sqrt(disc.H), ia = mufu_rcp(a.H);                                           \
+    const bool miss = (disc.H < 0.0f) || ((sd - b.H) * ia < 0.0f); /* 2nd: the sphere lies behind */  \
+    sink(miss ? INFINITY : __fmaf_rn((-b.H - sd) * ia, r.dl, -ew.H), K);                              \
+  }
+#define PT_BOX_HALF(H, K)                                                                             \
+  {                                                                                                   \
+    const float tnear = fmaxf(fmaxf(nx.H, ny.H), nz.H), tfar = fminf(fminf(fx.H, fy.H), fz.H);        \
+    const bool miss = (tnear > tfar) || (tfar < 0.0f); /* misses the inflated box, or it lies behind */ \
+    sink(miss ? INFINITY : __fmaf_rn(tnear, r.dl, -ew.H), K);                                         \
+  }
+#else
 #define PT_SPHERE_HALF(H, K)                                                                          \
   if (!(disc.H < 0.0f)) {                                                                             \
     const float sd = mufu_sqrt(disc.H), ia = mufu_rcp(a.H);                                           \
@@ -142,6 +162,7 @@ __device__ __forceinline__ void scan_take(ScanBest& b, float lo, int k) {
     if (!(tnear > tfar || tfar < 0.0f)) /* else: misses the inflated box, or the box lies behind */   \
       sink(__fmaf_rn(tnear, r.dl, -ew.H), K);                                                         \
   }
+#endif
 // `sink(lo, k)` receives every geom the filter cannot rule out: its lower bound and 2*pair + half
 template <typename Sink>
 __device__ __forceinline__ void filter_scan_to(const float4* v, int first, int last, const int end[kFiltClasses],

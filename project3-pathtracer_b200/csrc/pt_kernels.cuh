@@ -111,6 +111,7 @@ struct BounceParams {
   uint32_t first_sample, n_first;    // FIRST only: paths to generate = band * samples in this wavefront
   uint32_t pix0, band;               // FIRST only: the wavefront covers pixels [pix0, pix0 + band) (the whole frame unless banded)
   FastDiv div_band;                  // FIRST only: path index -> (sample, pixel of the band)
+  uint32_t q_offset;                 // k_bounce_q: byte offset of the warps' candidate queues in dynamic shared memory
 };
 
 // Work decomposition of k_bounce: the unit of work is ONE WARP x 32 consecutive paths.  Warps take units from a
@@ -245,7 +246,9 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const f
     m.a = __ldg(P.mats + 4 * mat); m.b = __ldg(P.mats + 4 * mat + 1); m.c = __ldg(P.mats + 4 * mat + 2); m.d = md;
     f3 L;
     if (NEE && !LAST) ns = dot(d, n) < 0 ? n : neg(n);  // the shading normal shade() uses
-    const int kind = shade(m, P.g, gi, h.p, n, P.keys, pixel, sample, P.depth, o, d, thr, L);
+    const float4* frame = nullptr;
+    if (TABLE && h.ncode != 8) frame = P.normals + (size_t)gi * kNormalRows + kFrameRow0 + 4 * ((h.ncode & 3) + ((h.ncode & 4) ? 3 : 0));
+    const int kind = shade(m, P.g, gi, h.p, n, frame, P.keys, pixel, sample, P.depth, o, d, thr, L);
     if (kind == 3 && !(NEE && no_emit)) {
       accum_add(P.accum + pixel, L);
     }
@@ -318,6 +321,178 @@ __global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_bounce(const 
     }
 
     shade_and_compact<LAST, true, NEE>(P, fs, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
+    }
+  }
+}
+
+// ---- k_bounce_q: the same segment with the second half RE-BATCHED BY WINNER TYPE (depths >= 1, few geoms) ----
+// In k_bounce a warp carries its 32 paths through the exact test and the shading together: after the first bounce a
+// third of them have left the scene in the filter scan and the rest are a mix of sphere and cube winners, so the
+// second half of the segment -- two thirds of the kernel's instructions -- ran with 19-22 of 32 lanes
+// (profiles/r01_k_bounce_v14_*).  Here each warp owns two queues in shared memory, one per winner type.  Per unit:
+//   phase A  load 32 rays (origin, direction; the throughput is not touched), filter scan; every path that has a
+//            candidate is pushed (ray + candidate + lo2 + path index, 48 bytes) onto the queue of its candidate's type
+//            -- ranks by ballot, no atomics, the queues are private to the warp; paths without a candidate end here
+//            (black background) and their throughput is never read from HBM;
+//   phase B  whenever a queue holds >= 32 entries, 32 of them are popped (their throughputs are fetched now: the load's
+//            latency hides behind the exact test) and run through exact test, shading and compaction with ALL 32
+//            lanes busy and with ONE shape's code (the type is warp-uniform: the sphere and the
+//            cube branch of exact_hit / hit_normal / the tangent frame are never both executed).
+// When the ticket counter runs dry the queues are flushed as partial batches.  The two queues grow towards each other
+// in one array of kQCap = 96 entries: before a push each holds <= 31, a push adds <= 32 in total.
+// Results do not depend on the order in which paths are processed (RNG streams are keyed by pixel and sample,
+// radiance goes through atomics), so images and live counts are the ones k_bounce produces, bit for bit.
+constexpr int kQCap = 96;
+#ifndef PT_Q_THR_GATHER
+#define PT_Q_THR_GATHER 0  // 1: the queue carries the path index and phase B fetches the throughput itself (a first touch
+                           // of HBM at the head of every batch: measured slower, profiles/r02_q_*)
+#endif
+#ifndef PT_Q_PREFETCH
+#define PT_Q_PREFETCH 1  // the next unit's path state travels HBM -> shared memory (cp.async) while this unit is traced
+#endif
+struct QWarp {
+  float4 o[kQCap];  // (origin.xyz, pixel)
+  float4 d[kQCap];  // (direction.xyz, sample)
+#if !PT_Q_THR_GATHER
+  float4 t[kQCap];  // (throughput.xyz, no-emission flag)
+#endif
+  float4 c[kQCap];  // (lo2 = second-smallest lower bound, bits of the candidate's geom index, path index, -)
+#if PT_Q_PREFETCH
+  float4 st[3][kUnit];  // staging: the next unit's (origin | direction | throughput) rows, one slot per lane
+#endif
+};
+#ifndef PT_Q_THREADS
+#define PT_Q_THREADS 256
+#endif
+#ifndef PT_Q_MIN_BLOCKS
+#define PT_Q_MIN_BLOCKS 3  // 80 registers: the second half of a segment does not fit 64 without spilling its loop state
+#endif
+constexpr int kQThreads = PT_Q_THREADS;
+__host__ __device__ inline size_t q_smem_bytes() { return sizeof(QWarp) * (size_t)(kQThreads / 32); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <bool LAST, bool NEE = false>
+__global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const __grid_constant__ BounceParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt = (1u << lane) - 1u;
+  const float4* const fs = reinterpret_cast<const float4*>(smem_raw);
+  stage_filt(P.filt, 0, P.filt.end[3], reinterpret_cast<float4*>(smem_raw));
+  __syncthreads();  // the only CTA-wide barrier
+  QWarp& Q = reinterpret_cast<QWarp*>(smem_raw + P.q_offset)[threadIdx.x >> 5];
+
+  const uint32_t n_in = P.ctrl->count[P.depth];
+  const uint32_t n_units = (n_in + kUnit - 1) / kUnit;
+  uint32_t* const ticket = &P.ctrl->tile_ctr[P.depth];
+  uint32_t next_raw = 0;  // lane 0: the ticket taken ahead of time
+  if (lane == 0) next_raw = atom_add_u32(ticket, 1u);
+
+  uint32_t ns = 0, nc = 0;           // queue lengths (warp-uniform): spheres at [0, ns), cubes at [kQCap - nc, kQCap)
+  uint32_t unit = 0, unit_end = 0;   // units left of the current ticket
+  bool more = true;                  // the ticket counter has not run dry yet
+  // the unit phase A works on next: taken from the ticket at hand or from the next ticket; with PT_Q_PREFETCH its path
+  // state is requested at once, so that it arrives while the unit before it is traced
+  auto advance = [&]() {
+    if (unit == unit_end) {
+      const uint32_t unit0 = __shfl_sync(0xffffffffu, next_raw, 0) * kTicketUnits;
+      if (unit0 >= n_units) { more = false; return; }
+      if (lane == 0) next_raw = atom_add_u32(ticket, 1u);  // consumed a ticket's worth of work later: its latency is hidden
+      unit = unit0;
+      unit_end = min(unit0 + kTicketUnits, n_units);
+    }
+#if PT_Q_PREFETCH
+    const uint32_t idc = min(unit * kUnit + lane, n_in - 1u);  // lanes past the end fetch a copy of the last path
+    cp_async16(&Q.st[0][lane], P.in_o + idc);
+    cp_async16(&Q.st[1][lane], P.in_d + idc);
+#if !PT_Q_THR_GATHER
+    cp_async16(&Q.st[2][lane], P.in_t + idc);
+#endif
+    cp_async_commit();
+#endif
+  };
+  advance();
+  for (;;) {
+    // ---- phase B: full batches (every entry once the input is exhausted) ----
+    for (;;) {
+      const uint32_t need = more ? (uint32_t)kUnit : 1u;
+      uint32_t n, slot0;
+      int type;
+      if (ns >= need) { type = 0; n = min(ns, (uint32_t)kUnit); ns -= n; slot0 = ns; }
+      else if (nc >= need) { type = 1; n = min(nc, (uint32_t)kUnit); nc -= n; slot0 = kQCap - n - nc; }
+      else break;
+      // lanes beyond a partial batch (the final flush only) work on a copy of its first entry and are masked out below:
+      // no defaults to set up, no divergence
+      const bool valid = lane < n;
+      const uint32_t slot = slot0 + (valid ? lane : 0u);
+      const float4 a = Q.o[slot], b = Q.d[slot], e = Q.c[slot];
+#if PT_Q_THR_GATHER
+      const float4 c = __ldg(P.in_t + __float_as_uint(e.z));
+#else
+      const float4 c = Q.t[slot];
+#endif
+      f3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z), thr = mk(c.x, c.y, c.z);
+      const uint32_t pixel = __float_as_uint(a.w), sample = __float_as_uint(b.w);
+      const bool no_emit = NEE && c.w != 0.0f;
+      const int gi = __float_as_int(e.y);
+      Hit h;
+      const bool hit = exact_hit(type, __ldg(P.g.inv0 + gi), __ldg(P.g.inv1 + gi), __ldg(P.g.inv2 + gi), __ldg(P.g.fwd0 + gi),
+                                 __ldg(P.g.fwd1 + gi), __ldg(P.g.fwd2 + gi), o, d, h.t, h.p, h.ncode);
+      h.id = gi;
+      if (!(hit && h.t > 0 && h.t < e.x)) {
+        // the candidate is not confirmed: the exact scan decides (0.008 % of the segments on the sample scene)
+        h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
+        if (valid) {
+          closest_hit_exact(P.g, P.n_geoms, o, d, h);
+          atomicAdd(&P.ctrl->fallbacks, 1u);
+        }
+      }
+      __syncwarp();  // the popped entries are in registers: the next push may overwrite them
+      shade_and_compact<LAST, true, NEE>(P, fs, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
+    }
+    if (!more) break;
+    // ---- phase A: load, filter scan, push the candidates ----
+    {
+      const uint32_t idx = unit * kUnit + lane;
+      unit++;
+      const bool valid = idx < n_in;
+#if PT_Q_PREFETCH
+      cp_async_wait_all();  // every lane reads only the slots it requested itself
+      const float4 a = Q.st[0][lane], b = Q.st[1][lane];
+#if !PT_Q_THR_GATHER
+      const float4 c = Q.st[2][lane];
+#endif
+#else
+      const uint32_t idc = valid ? idx : n_in - 1u;  // (n_in >= 1 here) lanes past the end scan a copy of the last path
+      const float4 a = __ldcs(P.in_o + idc), b = __ldcs(P.in_d + idc);
+#if !PT_Q_THR_GATHER
+      const float4 c = __ldcs(P.in_t + idc);
+#endif
+#endif
+      ScanBest best;
+      scan_init(best);
+      const ScanRay ray = make_scan_ray(mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), P.filt.r_scene, P.filt.end[2] > P.filt.end[1]);
+      filter_scan(fs, 0, P.filt.end[3], P.filt.end, ray, best);
+      const bool cand = valid && best.k1 >= 0;
+      const bool sphere = best.k1 < 2 * P.filt.end[1];
+      const uint32_t bs = __ballot_sync(0xffffffffu, cand && sphere), bc = __ballot_sync(0xffffffffu, cand && !sphere);
+      if (cand) {
+        const int gi = __ldg(reinterpret_cast<const int*>(P.filt.ids) + best.k1);
+        const uint32_t slot = sphere ? ns + __popc(bs & lt) : kQCap - 1 - (nc + __popc(bc & lt));
+        Q.o[slot] = a; Q.d[slot] = b;
+#if !PT_Q_THR_GATHER
+        Q.t[slot] = c;
+#endif
+        Q.c[slot] = make_float4(best.lo2, __int_as_float(gi), __uint_as_float(idx), 0.0f);
+      }
+      ns += __popc(bs);
+      nc += __popc(bc);
+      advance();  // (the staged rows of this unit are in registers / in the queue by now)
+      __syncwarp();
     }
   }
 }
@@ -525,6 +700,13 @@ __global__ void k_normal_table(GeomSoA g, int n_geoms, float4* tab) {
     h.ncode = (face % 3) | (face >= 3 ? 4 : 0);
     const f3 n = hit_normal(f0, f1, f2, h);
     tab[(size_t)i * kNormalRows + face] = make_float4(n.x, n.y, n.z, 0.0f);
+    // the diffuse sampler's tangent frame for both shading normals of this face (shade(): ns = n or -n)
+    f3 p1, p2;
+    float4* fr = tab + (size_t)i * kNormalRows + kFrameRow0 + 4 * face;
+    hemisphere_frame(n, p1, p2);
+    fr[0] = make_float4(p1.x, p1.y, p1.z, 0.0f); fr[1] = make_float4(p2.x, p2.y, p2.z, 0.0f);
+    hemisphere_frame(neg(n), p1, p2);
+    fr[2] = make_float4(p1.x, p1.y, p1.z, 0.0f); fr[3] = make_float4(p2.x, p2.y, p2.z, 0.0f);
   }
   const f3 c = mulMV(f0, f1, f2, 0.0f, 0.0f, 0.0f, 1.0f);  // intersections.h:111: transform * (0,0,0,1)
   tab[(size_t)i * kNormalRows + 6] = make_float4(c.x, c.y, c.z, 0.0f);
@@ -724,13 +906,18 @@ __global__ void __launch_bounds__(kCompactThreads) k_compact_count(const uint8_t
   }
 }
 constexpr int kScanThreads = 256, kScanItems = 4, kScanChunk = kScanThreads * kScanItems;
+// Chunks are taken from a TICKET counter, not from blockIdx.x: a CTA that looks back at chunk t - 1 then knows that
+// chunk's CTA has started (it took its ticket earlier), so the look-back makes progress however few CTAs are resident.
 __global__ void __launch_bounds__(kScanThreads) k_compact_scan(const uint32_t* __restrict__ tile_count, uint32_t n_tiles,
                                                                uint32_t* __restrict__ tile_prefix, uint32_t* n_out,
-                                                               uint64_t* status, uint32_t epoch) {
+                                                               uint32_t* ticket, uint64_t* status, uint32_t epoch) {
   __shared__ uint32_t s_warp[kScanThreads / 32];
-  __shared__ uint32_t s_base;
+  __shared__ uint32_t s_base, s_chunk;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t first = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+  if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t chunk = s_chunk;
+  const uint32_t first = chunk * kScanChunk + threadIdx.x * kScanItems;
   uint32_t c[kScanItems], mine = 0;
 #pragma unroll
   for (int k = 0; k < kScanItems; k++) { c[k] = first + k < n_tiles ? tile_count[first + k] : 0u; mine += c[k]; }
@@ -751,11 +938,12 @@ __global__ void __launch_bounds__(kScanThreads) k_compact_scan(const uint32_t* _
       if ((int)lane >= o) wi += t;
     }
     const uint32_t total = __shfl_sync(0xffffffffu, wi, kScanThreads / 32 - 1);
-    const uint32_t excl = lookback_exclusive(status, blockIdx.x, epoch, total);
+    const uint32_t excl = lookback_exclusive(status, chunk, epoch, total);
+    __syncwarp();
     if (lane < kScanThreads / 32) s_warp[lane] = wi - w;
     if (lane == 0) {
       s_base = excl;
-      if (blockIdx.x == gridDim.x - 1) *n_out = excl + total;
+      if (chunk == gridDim.x - 1) *n_out = excl + total;
     }
   }
   __syncthreads();

@@ -85,6 +85,7 @@ int main(int argc, char** argv) {
     }
     auto t0 = std::chrono::steady_clock::now();
     std::vector<int> rcs(gpus, 0);
+    std::vector<std::string> errs(gpus);  // pt_last_error() is per thread: the worker keeps its own message
     std::vector<std::thread> th;
     for (int g = 0; g < gpus; g++) {
       // contiguous blocks of sample indices; the union over GPUs is exactly [0, spp)
@@ -92,10 +93,12 @@ int main(int argc, char** argv) {
       th.emplace_back([&, g, s_begin, s_end] {
         rcs[g] = s_end > s_begin ? pt_render(ctx[g], s_begin, s_end - s_begin, depth, seed) : 0;
         if (!rcs[g]) rcs[g] = pt_sync(ctx[g]);
+        if (rcs[g]) errs[g] = pt_last_error();
       });
     }
     for (auto& t : th) t.join();
-    for (int g = 0; g < gpus; g++) if (rcs[g]) return die("render");
+    for (int g = 0; g < gpus; g++)
+      if (rcs[g]) { fprintf(stderr, "pt_render: render on GPU %d failed (%d): %s\n", g, rcs[g], errs[g].c_str()); return 1; }
     if (gpus > 1 && pt_reduce_to_first(ctx.data(), gpus)) return die("reduce");
     if (pt_download_mean(ctx[0], img.data(), (unsigned)spp)) return die("download");
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

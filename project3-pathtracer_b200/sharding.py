@@ -34,9 +34,15 @@ def reduce_image(t, dst=0, group=None):
 
 
 def render_sharded(ctx, spp, max_depth, seed, rank, world, stream=None, first_sample=0):
-    """render this rank's share of `spp` samples, then combine on rank 0; returns (first, count) rendered here"""
+    """render this rank's share of `spp` samples, then combine on rank 0; returns (first, count) rendered here.
+
+    `stream` (a torch.cuda.Stream): the render AND the reduce are issued on it -- the context is switched to that stream
+    first, so the reduce is ordered after the last kernel that adds to the image.  Without a stream the context's own
+    stream is synchronised before the reduce."""
     import torch
     b, n = sample_range(rank, world, spp, first_sample)
+    if stream is not None:
+        ctx.set_stream(stream.cuda_stream)  # no-op if the caller did it already; otherwise the reduce could overtake k_bounce
     ctx.clear()
     if n:
         ctx.render(b, n, max_depth, seed)

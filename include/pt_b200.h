@@ -118,6 +118,13 @@ int pt_last_render_ms(pt_context* ctx, float* ms);
  * renderCam->image layout (index = x + y*W, src/main.cpp:122). ---- */
 int pt_download_sum(pt_context* ctx, float* rgb);
 int pt_download_mean(pt_context* ctx, float* rgb, uint32_t spp); /* sum / spp */
+/* The reference's loop reads the running mean after EVERY sample (src/main.cpp:93-113: one cudaRaytraceCore per
+ * iteration, image copied back at src/raytraceKernel.cu:154).  This call hands out sum / spp of the samples traced so far
+ * and, while that image is on its way to the host, already traces samples [next_first_sample, next_first_sample +
+ * next_n_samples) (0 = none): it returns as soon as `rgb` is complete; the render it started finishes in the background
+ * (ordered before every later call on this context). */
+int pt_download_mean_then_render(pt_context* ctx, float* rgb, uint32_t spp, uint32_t next_first_sample,
+                                 uint32_t next_n_samples, int max_depth, uint64_t seed);
 /* overwrite the accumulation buffer (resume, or the running mean of the compat shim) */
 int pt_upload_sum(pt_context* ctx, const float* rgb);
 /* sendImageToPBO (src/raytraceKernel.cu:58-89): uchar4{r,g,b,0} = min(mean*255, 255), truncated.

@@ -5,6 +5,10 @@
 // context instead of being malloc'ed and freed per call (:118-119,136-137,157-159), and while calls arrive in
 // sequence (k, k+1, ...) the exact running SUM stays in HBM, so the per-call H2D of the image (:120) disappears;
 // the D2H of the running mean into renderCam->image (:154) is kept because the caller owns and reads that buffer.
+// While that copy is in flight the GPU already traces the NEXT sample (the reference's loop calls again with k + 1,
+// src/main.cpp:93-95): the next call finds its sample done and only resolves and copies.  A call that does not continue
+// the sequence (other scene, frame, camera, iteration number) discards the sample traced ahead: it restarts from
+// renderCam->image or from zero exactly as before.
 #include "../../include/pt_b200.h"
 #include "../../include/pt_compat.h"
 
@@ -29,8 +33,13 @@ struct Cache {
   pt_lens lens{0.0f, 0.0f};
   const camera* last_cam = nullptr;
   int last_frame = -1, last_iter = 0;
+  int ahead_iter = 0;      // iteration number whose sample is already traced (or being traced) in the accumulation buffer; 0 = none
+  int ahead_depth = 0, ahead_direct = 0;
+  unsigned long long ahead_seed = 0;
+  int direct_applied = -1; // pt_set_direct_lighting synchronises the stream: only called when the value changes
   std::vector<float> scaled;
-  void* pinned = nullptr;  // renderCam->image, page-locked in place while calls keep arriving for it
+  void* pinned = nullptr;  // renderCam->image, page-locked in place while a sequence of calls keeps arriving for it
+  size_t pinned_bytes = 0;
   void* pin_failed = nullptr;  // ... or the buffer that could not be locked (not retried on every call)
 } g;
 int g_depth = 8;
@@ -71,14 +80,17 @@ extern "C" int pt_compat_last_status(void) { return g_status; }
 // The caller reads renderCam->image after every call (src/main.cpp:118-131), so its D2H copy cannot go away; but a
 // pageable destination makes it a staged ~10 GB/s copy.  Page-locking the caller's buffer in place (it lives as long as
 // the scene, src/scene.cpp:207-214) turns it into one DMA.  Failure to lock is harmless: the copy stays pageable.
+// The registration is renewed at the start of every sequence (iterations == 1) and whenever pointer or size change: a
+// host that frees and re-creates its image between renders (the reference rebuilds scenes) never leaves a stale
+// registration behind for longer than the sequence that owned it.
 static void unpin() {
-  if (g.pinned) { cudaHostUnregister(g.pinned); cudaGetLastError(); g.pinned = nullptr; }
+  if (g.pinned) { cudaHostUnregister(g.pinned); cudaGetLastError(); g.pinned = nullptr; g.pinned_bytes = 0; }
 }
-static void pin(void* image, size_t bytes) {
-  if (g.pinned == image || g.pin_failed == image) return;
+static void pin(void* image, size_t bytes, bool new_sequence) {
+  if (!new_sequence && ((g.pinned == image && g.pinned_bytes == bytes) || g.pin_failed == image)) return;
   unpin();
   const cudaError_t e = cudaHostRegister(image, bytes, cudaHostRegisterDefault);
-  if (e == cudaSuccess) { g.pinned = image; g.pin_failed = nullptr; }
+  if (e == cudaSuccess) { g.pinned = image; g.pinned_bytes = bytes; g.pin_failed = nullptr; }
   else { cudaGetLastError(); g.pin_failed = image; }
   if (getenv("PT_COMPAT_DEBUG")) fprintf(stderr, "pt_compat: cudaHostRegister(%p, %zu) -> %s\n", image, bytes, cudaGetErrorString(e));
 }
@@ -156,9 +168,15 @@ void cudaRaytraceCore(uchar4* PBOpos, camera* renderCam, int frame, int iteratio
     return;
   }
   const bool in_sequence = !scene_changed && g.last_cam == renderCam && g.last_frame == frame && iterations == g.last_iter + 1;
+  // the sample of this call may have been traced ahead, during the previous call's copy
+  const int ahead = g.ahead_iter;
+  g.ahead_iter = 0;
+  const bool traced_ahead = in_sequence && ahead == iterations && g.ahead_depth == g_depth && g.ahead_seed == g_seed &&
+                            g.ahead_direct == g_direct;
+  const bool stale_ahead = ahead != 0 && !traced_ahead;  // the buffer holds a sample that does not belong to this call's sum
   if (iterations == 1) {
-    if ((rc = pt_clear(g.ctx))) return fail(rc);
-  } else if (!in_sequence) {
+    if ((rc = pt_clear(g.ctx))) return fail(rc);  // (also drops a sample traced ahead for a sequence that did not go on)
+  } else if (!in_sequence || stale_ahead) {
     // resume from the caller's running mean: sum = image * (k-1)
     g.scaled.resize(npix * 3);
     const float k1 = (float)(iterations - 1);
@@ -166,11 +184,19 @@ void cudaRaytraceCore(uchar4* PBOpos, camera* renderCam, int frame, int iteratio
     for (size_t i = 0; i < npix * 3; i++) g.scaled[i] = im[i] * k1;
     if ((rc = pt_upload_sum(g.ctx, g.scaled.data()))) return fail(rc);
   }
-  if (in_sequence || iterations == 1) pin(renderCam->image, npix * 3 * sizeof(float));  // a render loop, not a one-off call
-  if ((rc = pt_set_direct_lighting(g.ctx, g_direct))) return fail(rc);
-  if ((rc = pt_render(g.ctx, (uint32_t)(iterations - 1), 1, g_depth, g_seed))) return fail(rc);
+  if (in_sequence || iterations == 1) pin(renderCam->image, npix * 3 * sizeof(float), iterations == 1);  // a render loop, not a one-off call
+  if (g.direct_applied != g_direct) {
+    if ((rc = pt_set_direct_lighting(g.ctx, g_direct))) return fail(rc);
+    g.direct_applied = g_direct;
+  }
+  if (!traced_ahead && (rc = pt_render(g.ctx, (uint32_t)(iterations - 1), 1, g_depth, g_seed))) return fail(rc);
   if (PBOpos && (rc = pt_resolve_rgba8(g.ctx, (uint32_t)iterations, nullptr, PBOpos))) return fail(rc);
-  if ((rc = pt_download_mean(g.ctx, reinterpret_cast<float*>(renderCam->image), (uint32_t)iterations))) return fail(rc);
+  // the running mean goes home; meanwhile the next iteration's sample is traced (not past the scene's iteration count)
+  const bool go_on = (in_sequence || iterations == 1) && (renderCam->iterations == 0 || (unsigned)iterations < renderCam->iterations);
+  if ((rc = pt_download_mean_then_render(g.ctx, reinterpret_cast<float*>(renderCam->image), (uint32_t)iterations,
+                                         (uint32_t)iterations, go_on ? 1u : 0u, g_depth, g_seed)))
+    return fail(rc);
+  if (go_on) { g.ahead_iter = iterations + 1; g.ahead_depth = g_depth; g.ahead_seed = g_seed; g.ahead_direct = g_direct; }
   g.last_cam = renderCam;
   g.last_frame = frame;
   g.last_iter = iterations;

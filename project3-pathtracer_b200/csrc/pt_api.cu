@@ -8,6 +8,8 @@
 #include "../../include/pt_b200.h"
 #include "pt_kernels.cuh"
 
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges cost nothing unless a profiler is attached
+
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -18,6 +20,12 @@
 #include <vector>
 
 using namespace ptd;
+
+// NVTX range around a stage of the render (profiler timelines: "pt_render", "band", "wavefront", "reduce")
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ---------------------------------------------------------------- errors
 static thread_local std::string g_err;
@@ -99,7 +107,12 @@ struct pt_context {
   int grid_blocks_nee[4] = {0, 0, 0, 0};  // ... of the direct-light-sampling variants
   int grid_blocks_q[2] = {0, 0}, grid_blocks_q_nee[2] = {0, 0};  // k_bounce_q<LAST> (depths >= 1 of the linear mode)
   size_t q_smem_total = 0;            // k_bounce_q: filter geometry + the warps' candidate queues
-  bool use_q = true;                  // depths >= 1 run k_bounce_q (PT_B200_FUSED=1: the fused k_bounce everywhere, for A/B runs)
+  int q_mode = 0;                     // depths >= 1, few geoms: 0 = per depth by the scene's measured survival (h_policy),
+                                      // 1 = always k_bounce_q, 2 = always the fused k_bounce (PT_B200_FUSED=1 / =0 force 2 / 1)
+  int* h_policy = nullptr;            // mapped host memory, kMaxDepth + 1 ints written by k_accum_counts: 0 unknown, 1 q, 2 fused
+  int* d_policy = nullptr;            // ... its device address
+  cudaStream_t copy_stream = nullptr; // pt_download_mean_then_render: the image leaves while the next samples are traced
+  cudaEvent_t ev_res = nullptr, ev_copy = nullptr;
   int mode = -1;                      // 0: linear scan over pairs staged in shared memory, 1: hierarchy (pt_bvh.cuh)
   size_t smem_bytes = 0;   // k_bounce: filter geometry
   size_t geom_smem = 0;    // filter geometry only (k_intersect_list)
@@ -416,7 +429,8 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
     std::vector<Box> lbox(n);
     for (int k = 0; k < n; k++) lbox[k] = leaf_box(k);
     std::vector<double> suffix(n);
-    F.nodes.assign((size_t)(n - 1) * kBvhNodeRows, make_float4(0, 0, 0, 0));
+    struct BNode { Box b[2]; int c[2]; };  // the binary tree; collapsed into 4-wide nodes below
+    std::vector<BNode> bnodes((size_t)(n > 1 ? n - 1 : 1));
     int next_node = 0;
     // Returns the child reference (node index, or ~leaf) and the box of idx[first, last).  Split rule: the cheapest, by
     // the surface-area heuristic (area x count of each side), of
@@ -424,14 +438,14 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
     //     extent, level after level; a sweep over centroids cannot single it out),
     //   * every split position of the centroids sorted along x, y and z;
     // the median along the widest axis when the levels left are only just enough to finish by halving (the traversal
-    // stack holds one entry per level: depth <= kBvhStack) or when nothing has a finite cost.
-    const bool median_only = getenv("PT_B200_BVH_MEDIAN") != nullptr;  // measurement knob: the plain median-split tree
+    // stack need of the collapsed tree is checked below: kBvhStack) or when nothing has a finite cost.
+    bool median_only = getenv("PT_B200_BVH_MEDIAN") != nullptr;  // measurement knob: the plain median-split tree
     std::function<int(int, int, int, Box&)> build = [&](int first, int last, int depth, Box& box) -> int {
       const int cnt = last - first;
       if (cnt == 1) { box = lbox[idx[first]]; return ~idx[first]; }
       int levels = 0;
       while ((1 << levels) < cnt) levels++;
-      const bool must_halve = depth + levels + 2 >= kBvhStack || median_only;
+      const bool must_halve = depth + levels + 2 >= kBvhBinaryDepth || median_only;
       int mid = -1;
       if (!must_halve && cnt > 2) {
         int big = first;
@@ -483,21 +497,69 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
       const int me = next_node++;
       Box b0, b1;
       const int c0 = build(first, mid, depth + 1, b0), c1 = build(mid, last, depth + 1, b1);
-      float4* N = &F.nodes[(size_t)me * kBvhNodeRows];
-      N[0] = make_float4(down(b0.lo[0]), down(b1.lo[0]), down(b0.lo[1]), down(b1.lo[1]));
-      N[1] = make_float4(down(b0.lo[2]), down(b1.lo[2]), up(b0.hi[0]), up(b1.hi[0]));
-      N[2] = make_float4(up(b0.hi[1]), up(b1.hi[1]), up(b0.hi[2]), up(b1.hi[2]));
-      int ci[2] = {c0, c1};
-      float cf[2];
-      memcpy(cf, ci, sizeof(cf));
-      // x 1.000002: rounding of D^2 in child_entries (pt_bvh.cuh)
-      N[3] = make_float4(up(b0.p1), up(b1.p1), up(b0.p2 * 1.000002), up(b1.p2 * 1.000002));
-      N[4] = make_float4(cf[0], cf[1], 0, 0);
+      bnodes[me].b[0] = b0; bnodes[me].b[1] = b1; bnodes[me].c[0] = c0; bnodes[me].c[1] = c1;
       box = merge(b0, b1);
       return me;
     };
     Box root;
-    build(0, n, 0, root);
+    for (int attempt = 0; attempt < 2; attempt++) {
+      next_node = 0;
+      for (int k = 0; k < n; k++) idx[k] = k;
+      const int root_ref = build(0, n, 0, root);
+      // ---- collapse into 4-wide nodes: a node's slots start as its two children; while there is room, the inner slot
+      // with the largest box is replaced by its own two children.  One fetch then serves up to four boxes, and the chain
+      // of dependent fetches of a traversal is about half as long. ----
+      F.nodes.clear();
+      int stack_need = 0;
+      std::function<int(int, int&)> collapse = [&](int b, int& need) -> int {
+        int ref[4], cnt = 2;
+        Box bx[4];
+        bx[0] = bnodes[b].b[0]; bx[1] = bnodes[b].b[1]; ref[0] = bnodes[b].c[0]; ref[1] = bnodes[b].c[1];
+        while (cnt < 4) {
+          int pick = -1;
+          for (int i = 0; i < cnt; i++)
+            if (ref[i] >= 0 && (pick < 0 || area(bx[i]) > area(bx[pick]))) pick = i;
+          if (pick < 0) break;
+          const BNode& q = bnodes[ref[pick]];
+          bx[pick] = q.b[0]; ref[pick] = q.c[0];
+          bx[cnt] = q.b[1]; ref[cnt] = q.c[1];
+          cnt++;
+        }
+        const int me = (int)(F.nodes.size() / kBvhNodeRows);
+        F.nodes.resize(F.nodes.size() + kBvhNodeRows, make_float4(0, 0, 0, 0));
+        int child[4], deepest = 0;
+        for (int i = 0; i < 4; i++) {
+          child[i] = kBvhNoChild;
+          if (i < cnt) {
+            int sub = 0;
+            child[i] = ref[i] >= 0 ? collapse(ref[i], sub) : ref[i];
+            deepest = std::max(deepest, sub);
+          }
+        }
+        need = (cnt - 1) + deepest;  // the children not taken wait on the stack while the deepest one is walked
+        float4* N = &F.nodes[(size_t)me * kBvhNodeRows];
+        const float pinf = INFINITY, ninf = -INFINITY;
+        for (int h = 0; h < 2; h++) {  // two blocks in the layout child_entries reads: children (0, 1) and (2, 3)
+          const int i0 = 2 * h, i1 = 2 * h + 1;
+          auto lo = [&](int i, int r) { return i < cnt ? down(bx[i].lo[r]) : pinf; };  // an empty slot: a box nothing enters
+          auto hi = [&](int i, int r) { return i < cnt ? up(bx[i].hi[r]) : ninf; };
+          auto p1 = [&](int i) { return i < cnt ? up(bx[i].p1) : 0.0f; };
+          auto p2 = [&](int i) { return i < cnt ? up(bx[i].p2 * 1.000002) : 0.0f; };  // x 1.000002: rounding of D^2 in child_entries
+          float4* Nh = N + 4 * h;
+          Nh[0] = make_float4(lo(i0, 0), lo(i1, 0), lo(i0, 1), lo(i1, 1));
+          Nh[1] = make_float4(lo(i0, 2), lo(i1, 2), hi(i0, 0), hi(i1, 0));
+          Nh[2] = make_float4(hi(i0, 1), hi(i1, 1), hi(i0, 2), hi(i1, 2));
+          Nh[3] = make_float4(p1(i0), p1(i1), p2(i0), p2(i1));
+        }
+        float cf[4];
+        memcpy(cf, child, sizeof(cf));
+        N[8] = make_float4(cf[0], cf[1], cf[2], cf[3]);
+        return me;
+      };
+      if (root_ref >= 0) collapse(root_ref, stack_need);
+      if (stack_need + 2 <= kBvhStack || median_only) break;
+      median_only = true;  // a degenerate tree: the balanced one needs 3 entries per two binary levels at most
+    }
   }
   return F;
 }
@@ -701,6 +763,9 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
     meta[i] = make_int2(geoms[i].type, geoms[i].type <= 1 ? geoms[i].materialid : 0);
   }
   c->h_geoms.assign(geoms, geoms + n_geoms);
+  if (c->h_policy) {  // a new scene: its survival is unknown (wavefronts of the old one have finished: callers synchronise)
+    for (int i = 0; i <= kMaxDepth; i++) ((volatile int*)c->h_policy)[i] = 0;
+  }
   int rcf;
   if ((rcf = upload_filter(c))) return rcf;
   if (n_geoms != c->n_geoms) {
@@ -814,6 +879,10 @@ extern "C" int pt_context_destroy(pt_context* c) {
     if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
   }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->ev_res) cudaEventDestroy(c->ev_res);
+  if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+  if (c->h_policy) cudaFreeHost(c->h_policy);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -843,7 +912,13 @@ extern "C" int pt_context_create(const pt_static_geom* geoms, int n_geoms, const
     return fail(PT_ERR_CUDA);
   }
   c->stream = c->own_stream;
-  if (const char* env = getenv("PT_B200_FUSED")) c->use_q = atoi(env) == 0;  // developer knob: A/B against the fused kernel
+  if (const char* env = getenv("PT_B200_FUSED")) c->q_mode = atoi(env) == 0 ? 1 : 2;  // developer knob: A/B runs
+  if (cudaHostAlloc(&c->h_policy, (kMaxDepth + 1) * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer(&c->d_policy, c->h_policy, 0) != cudaSuccess) {
+    pt_set_error_("cudaHostAlloc (policy words) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(PT_ERR_CUDA);
+  }
+  memset(c->h_policy, 0, (kMaxDepth + 1) * sizeof(int));
   if ((rc = upload_scene(c, geoms, n_geoms, materials, n_materials, cam, lens, true))) return fail(rc);
   if (cudaMalloc(&c->d_accum, (size_t)c->npix * sizeof(float4)) != cudaSuccess ||
       cudaMalloc(&c->d_rgb, (size_t)c->npix * 3 * sizeof(float)) != cudaSuccess ||
@@ -905,7 +980,10 @@ static cudaError_t launch_bounce(pt_context* c, int slot, const BounceParams& P,
   const bool nee = c->nee && c->n_lights > 0 && NeeOf<F, L>::value;
   constexpr bool N = NeeOf<F, L>::value;
   uint32_t grid = (uint32_t)(nee ? c->grid_blocks_nee[slot] : c->grid_blocks[slot]);
-  if (!F && !c->mode && c->use_q) {  // depths >= 1, few geoms: second half re-batched by winner type
+  // depths >= 1, few geoms: second half re-batched by winner type -- unless the scene keeps nearly all its paths alive
+  // at this depth (closed rooms), where the fused kernel is faster; unknown yet (first wavefronts of a scene): re-batched
+  const bool use_q = c->q_mode == 1 || (c->q_mode == 0 && ((volatile int*)c->h_policy)[P.depth] != 2);
+  if (!F && !c->mode && use_q) {
     uint32_t gq = (uint32_t)(nee ? c->grid_blocks_q_nee[L ? 1 : 0] : c->grid_blocks_q[L ? 1 : 0]);
     const uint32_t ctas = (n_upper + kQThreads - 1) / kQThreads;  // one unit per warp at least
     if (ctas < gq) gq = ctas ? ctas : 1;
@@ -934,6 +1012,7 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
     pt_set_error_("no wavefront buffers (a previous pt_set_wavefront_paths failed): call it again with a size that fits");
     return PT_ERR_STATE;
   }
+  NvtxRange nvtx_render("pt_render");
   CU(cudaEventRecord(c->ev0, c->stream));
   const uint64_t cap = c->wf_capacity;
   // Bands: a frame whose float4 accumulation image does not leave room in the 126 MB L2 (> 48 MB, e.g. 3840x2160) is
@@ -956,9 +1035,11 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
   }
   uint64_t wf = 0;
   for (uint32_t pix0 = 0; pix0 < c->npix; pix0 += band_cap) {
+  NvtxRange nvtx_band("band");
   const uint32_t band = c->npix - pix0 < band_cap ? c->npix - pix0 : band_cap;
   const uint32_t spp_wf = (uint32_t)(cap / band);
   for (uint32_t s0 = 0; s0 < n_samples; s0 += spp_wf, wf++) {
+    NvtxRange nvtx_wf("wavefront");
     const int sl = (int)(wf % (uint64_t)slots_used);
     cudaStream_t st = forked ? c->wf_stream[sl] : c->stream;
     float4* S = c->d_state + (size_t)sl * 6 * cap;
@@ -987,6 +1068,7 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
       P.pix0 = pix0; P.band = band;
       P.div_band = make_fastdiv(band);
       P.q_offset = (uint32_t)c->geom_smem;
+      P.cap = (uint32_t)cap;
       const bool first = depth == 0, last = depth == max_depth - 1;
       cudaError_t e;
       if (first && last) e = launch_bounce<true, true>(c, 1, P, n_first, st);
@@ -995,7 +1077,7 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
       else e = launch_bounce<false, false>(c, 2, P, n_first, st);
       if (e != cudaSuccess) { pt_set_error_("k_bounce launch failed: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
     }
-    k_accum_counts<<<1, kMaxDepth, 0, st>>>(ctrl, c->d_live, max_depth);
+    k_accum_counts<<<1, kMaxDepth, 0, st>>>(ctrl, c->d_live, max_depth, c->q_mode == 0 && !c->mode ? c->d_policy : nullptr);
     c->launches++;
     CU(cudaGetLastError());
     c->paths_total += n_first;
@@ -1041,6 +1123,33 @@ extern "C" int pt_download_mean(pt_context* c, float* rgb, uint32_t spp) {
   CTX(c);
   if (spp == 0) { pt_set_error_("spp is 0"); return PT_ERR_INVALID; }
   return download_rgb(c, rgb, (float)spp, 1);
+}
+
+// The reference's loop asks for the image after EVERY sample (src/main.cpp:93-113).  Here the mean of the samples so far
+// leaves through a copy stream while the render stream already traces the next samples: the caller waits for the copy
+// only.  The next call then finds its samples done.  (Resolve -> event -> D2H on the copy stream; the render is queued
+// behind the resolve on the render stream, so it cannot change what is being copied: the resolve wrote a snapshot.)
+extern "C" int pt_download_mean_then_render(pt_context* c, float* rgb, uint32_t spp, uint32_t next_first_sample,
+                                            uint32_t next_n_samples, int max_depth, uint64_t seed) {
+  CTX(c);
+  if (!rgb) { pt_set_error_("rgb is NULL"); return PT_ERR_INVALID; }
+  if (spp == 0) { pt_set_error_("spp is 0"); return PT_ERR_INVALID; }
+  if (!c->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_res, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+  }
+  k_resolve_rgb<<<(c->npix + 255) / 256, 256, 0, c->stream>>>(c->d_accum, c->npix, (float)spp, 1, c->d_rgb);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ev_res, c->stream));
+  CU(cudaStreamWaitEvent(c->copy_stream, c->ev_res, 0));
+  CU(cudaMemcpyAsync(rgb, c->d_rgb, (size_t)c->npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+  CU(cudaEventRecord(c->ev_copy, c->copy_stream));
+  int rc = PT_OK;
+  if (next_n_samples) rc = pt_render(c, next_first_sample, next_n_samples, max_depth, seed);
+  CU(cudaEventSynchronize(c->ev_copy));
+  return rc;
 }
 
 extern "C" int pt_upload_sum(pt_context* c, const float* rgb) {
@@ -1422,6 +1531,7 @@ extern "C" int pt_reduce_to_first(pt_context* const* ctxs, int n) {
       if (ctxs[j]->device == ctxs[i]->device) { pt_set_error_("contexts %d and %d share device %d", j, i, ctxs[i]->device); return PT_ERR_INVALID; }
   }
   if (n == 1) return PT_OK;
+  NvtxRange nvtx_reduce("reduce");
   if (!load_nccl()) return PT_ERR_CUDA;
   std::vector<int> devs(n);
   for (int i = 0; i < n; i++) devs[i] = ctxs[i]->device;

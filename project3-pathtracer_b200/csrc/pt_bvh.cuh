@@ -5,7 +5,8 @@
 // not change any result: it only skips geoms the filter would have proven to miss.
 //   * Every leaf is one geom with the same four-class filter test as the pair scan (scalar here: a ray meets few
 //     leaves, and they differ per lane).
-//   * Every node stores its two children's world AABBs.  A child's box bounds the INFLATED shapes of all geoms below
+//   * Every node stores the world AABBs of up to FOUR children (the binary surface-area tree, collapsed on the host: a
+//     traversal is a chain of dependent fetches, and a 4-wide node halves its length).  A child's box bounds the INFLATED shapes of all geoms below
 //     it at w = 0; the w- and distance-dependent part of the inflation is added per ray as a pad
 //     P1*w + P2*D^2 (P1, P2 = maxima over the subtree, D = largest distance from the origin to the box), so "the ray
 //     misses the padded box" implies "the filter proves a miss for every geom below".
@@ -23,17 +24,21 @@
 
 namespace ptd {
 
-// node = 5 float4, the two children side by side (child 0 in the low half of each float2, child 1 in the high half):
-//   n0 = (min0.x, min1.x | min0.y, min1.y)  n1 = (min0.z, min1.z | max0.x, max1.x)  n2 = (max0.y, max1.y | max0.z, max1.z)
-//   n3 = (P1_0, P1_1 | P2_0, P2_1)  n4 = int bits (child0, child1, -, -); child >= 0: node, < 0: leaf ~child
-// (a 64-byte node -- one P1, P2 per node, the children in n3 -- read 18 % fewer sectors and still ran 12 % slower:
-// profiles/r01_bvh_notes.txt)
+// node = 9 float4: two blocks of four rows, each holding two children side by side (child a in the low half of each
+// float2, child b in the high half), children (0, 1) in rows 0-3 and (2, 3) in rows 4-7:
+//   r0 = (min_a.x, min_b.x | min_a.y, min_b.y)  r1 = (min_a.z, min_b.z | max_a.x, max_b.x)  r2 = (max_a.y, max_b.y | max_a.z, max_b.z)
+//   r3 = (P1_a, P1_b | P2_a, P2_b)
+// row 8 = int bits (child0, child1, child2, child3); child >= 0: node, < 0: leaf ~child, kBvhNoChild: empty slot (its
+// box is (+inf, -inf): nothing enters it)
 // leaf = 5 float4 (scalar filter record) + int2 (class, geom index):
 //   class 0: l0 = (c.xyz, Wc)  l1 = (Ww, Wr, Ew_c, Ew_w)
 //   class 2: l0 = (c.xyz, Ew_c)  l1 = (Hc.xyz, Ew_w)  l2 = (Hw.xyz, -)
 //   class 1: l0..l2 = rows x,y,z of inverseTransform  l3 = (R2c, R2w, R2r, Ew_c)  l4 = (Ew_w, -, -, -)
 //   class 3: l0..l2 = rows x,y,z of inverseTransform  l3 = (hc.xyz, Ew_c)  l4 = (hw.xyz, Ew_w)
-constexpr int kBvhNodeRows = 5, kBvhLeafRows = 5, kBvhStack = 48;
+constexpr int kBvhNodeRows = 9, kBvhLeafRows = 5;
+constexpr int kBvhStack = 64;        // entries of a traversal's stack: the builder checks the collapsed tree's worst case
+constexpr int kBvhBinaryDepth = 40;  // depth limit of the binary tree before the collapse
+constexpr int kBvhNoChild = (int)0x80000000;
 struct BvhSoA {
   const float4* nodes;
   const float4* leaves;
@@ -144,10 +149,11 @@ __device__ __forceinline__ TravRay make_trav_ray(const BvhSoA& B, const ScanRay&
 }
 __device__ __forceinline__ int bvh_root(const BvhSoA& B) { return B.n_leaves == 1 ? ~0 : 0; }  // a single geom: the root is leaf 0
 
-// One step of a traversal: test the leaf `cur` (< 0) or the two children of the node `cur`, then move on.  Returns
-// false when the traversal is finished.  EXACT = false: filter scan, result in `best` (k1 = leaf index).
+// One step of a traversal: test the leaf `cur` (< 0) or the (up to four) children of the node `cur`, then move on.
+// Returns false when the traversal is finished.  EXACT = false: filter scan, result in `best` (k1 = leaf index).
 // EXACT = true: exact test of every candidate leaf that can still matter, result in `h`.
-// The stack holds at most one entry per level: depth <= kBvhStack by construction (build_bvh).
+// Children that can matter are visited nearest first: the nearest becomes `cur`, the others go on the stack farthest
+// first (the builder guarantees that the stack never needs more than kBvhStack entries).
 template <bool EXACT>
 __device__ __forceinline__ bool trav_step(const BvhSoA& B, const GeomSoA& g, const ScanRay& r, const TravRay& tr, ScanBest& best, Hit& h,
                                           int& cur, int& sp, int* stack) {
@@ -173,26 +179,39 @@ __device__ __forceinline__ bool trav_step(const BvhSoA& B, const GeomSoA& g, con
     }
   } else {
     const float4* N = B.nodes + (size_t)cur * kBvhNodeRows;
-    const float4 n0 = __ldg(N), n1 = __ldg(N + 1), n2 = __ldg(N + 2), n3 = __ldg(N + 3);
-    const int2 ch = __ldg(reinterpret_cast<const int2*>(N + 4));
-    float e0, e1;
-    child_entries(n0, n1, n2, n3, r, e0, e1);
+    const float4 a0 = __ldg(N), a1 = __ldg(N + 1), a2 = __ldg(N + 2), a3 = __ldg(N + 3);
+    const float4 b0 = __ldg(N + 4), b1 = __ldg(N + 5), b2 = __ldg(N + 6), b3 = __ldg(N + 7);
+    const int4 ch = __ldg(reinterpret_cast<const int4*>(N + 8));
+    float e[4];
+    child_entries(a0, a1, a2, a3, r, e[0], e[1]);
+    child_entries(b0, b1, b2, b3, r, e[2], e[3]);
     // a child whose best possible bound cannot beat the current limit is skipped:
     //   filter pass: bound >= lo2 changes neither k1 nor lo2 (a missed box has bound +inf);
     //   exact pass: bound > best exact distance (ties may still win)
-    const float b0 = __fmaf_rn(e0, tr.dls, -tr.ewmax), b1 = __fmaf_rn(e1, tr.dls, -tr.ewmax);
-    const bool v0 = EXACT ? (e0 < INFINITY && !(b0 > h.t)) : (b0 < best.lo2);
-    const bool v1 = EXACT ? (e1 < INFINITY && !(b1 > h.t)) : (b1 < best.lo2);
-    if (v0 || v1) {
-      const bool second = !v0 || (v1 && e1 < e0);  // nearer (or only) child first
-      const int near_child = second ? ch.y : ch.x, far_child = second ? ch.x : ch.y;
-      if (v0 && v1) {
-        stack[sp++] = far_child;
-#ifdef PT_BVH_PREFETCH
-        if (far_child >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(B.nodes + (size_t)far_child * kBvhNodeRows));
-#endif
+    // sort keys: the entry parameter's bits (>= 0, so they order like integers) with the slot number in the two lowest
+    // bits; a skipped child gets the largest key
+    uint32_t k[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float bd = __fmaf_rn(e[i], tr.dls, -tr.ewmax);
+      const bool v = EXACT ? (e[i] < INFINITY && !(bd > h.t)) : (bd < best.lo2);
+      k[i] = v ? ((__float_as_uint(e[i]) & ~3u) | (uint32_t)i) : 0xffffffffu;
+    }
+    // sorting network on four keys (ascending)
+#define PT_CSWAP(x, y) { const uint32_t lo_ = min(k[x], k[y]), hi_ = max(k[x], k[y]); k[x] = lo_; k[y] = hi_; }
+    PT_CSWAP(0, 1) PT_CSWAP(2, 3) PT_CSWAP(0, 2) PT_CSWAP(1, 3) PT_CSWAP(1, 2)
+#undef PT_CSWAP
+    if (k[0] != 0xffffffffu) {
+      auto child_of = [&](uint32_t key) { const uint32_t s_ = key & 3u; return s_ == 0 ? ch.x : (s_ == 1 ? ch.y : (s_ == 2 ? ch.z : ch.w)); };
+      // farthest first onto the stack
+#pragma unroll
+      for (int i = 3; i >= 1; i--) {
+        if (k[i] != 0xffffffffu) {
+          PT_CHECK(sp < kBvhStack);
+          stack[sp++] = child_of(k[i]);
+        }
       }
-      cur = near_child;
+      cur = child_of(k[0]);
       return true;
     }
   }

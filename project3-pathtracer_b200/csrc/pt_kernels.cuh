@@ -112,6 +112,7 @@ struct BounceParams {
   uint32_t pix0, band;               // FIRST only: the wavefront covers pixels [pix0, pix0 + band) (the whole frame unless banded)
   FastDiv div_band;                  // FIRST only: path index -> (sample, pixel of the band)
   uint32_t q_offset;                 // k_bounce_q: byte offset of the warps' candidate queues in dynamic shared memory
+  uint32_t cap;                      // paths the in / out buffers hold (debug checks)
 };
 
 // Work decomposition of k_bounce: the unit of work is ONE WARP x 32 consecutive paths.  Warps take units from a
@@ -211,6 +212,7 @@ __device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const float4* 
   if (!(cl > 0)) return;
   const float G = (cs * cl) / (h.t * h.t);
   const f3 Ld = (thr * E) * G;
+  PT_CHECK(pixel < P.cam.npix);
   accum_add(P.accum + pixel, Ld);
 }
 
@@ -250,6 +252,7 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const f
     if (TABLE && h.ncode != 8) frame = P.normals + (size_t)gi * kNormalRows + kFrameRow0 + 4 * ((h.ncode & 3) + ((h.ncode & 4) ? 3 : 0));
     const int kind = shade(m, P.g, gi, h.p, n, frame, P.keys, pixel, sample, P.depth, o, d, thr, L);
     if (kind == 3 && !(NEE && no_emit)) {
+      PT_CHECK(pixel < P.cam.npix);
       accum_add(P.accum + pixel, L);
     }
     sampled = NEE && !LAST && kind == 0 && P.n_lights > 0;
@@ -257,6 +260,7 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const f
   if (!LAST) {
     const uint32_t slot = __shfl_sync(0xffffffffu, base_raw, 0) + __popc(ballot & ((1u << lane) - 1u));
     if (alive) {
+      PT_CHECK(slot < P.cap);
       __stcs(P.out_o + slot, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
       __stcs(P.out_d + slot, make_float4(d.x, d.y, d.z, __uint_as_float(sample)));
       __stcs(P.out_t + slot, make_float4(thr.x, thr.y, thr.z, sampled ? 1.0f : 0.0f));
@@ -429,6 +433,7 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
       // no defaults to set up, no divergence
       const bool valid = lane < n;
       const uint32_t slot = slot0 + (valid ? lane : 0u);
+      PT_CHECK(slot < (uint32_t)kQCap && n >= 1u && n <= (uint32_t)kUnit);
       const float4 a = Q.o[slot], b = Q.d[slot], e = Q.c[slot];
 #if PT_Q_THR_GATHER
       const float4 c = __ldg(P.in_t + __float_as_uint(e.z));
@@ -483,6 +488,8 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
       if (cand) {
         const int gi = __ldg(reinterpret_cast<const int*>(P.filt.ids) + best.k1);
         const uint32_t slot = sphere ? ns + __popc(bs & lt) : kQCap - 1 - (nc + __popc(bc & lt));
+        PT_CHECK(slot < (uint32_t)kQCap && ns + nc + __popc(bs) + __popc(bc) <= (uint32_t)kQCap);
+        PT_CHECK(idx < P.cap && gi >= 0 && gi < P.n_geoms);
         Q.o[slot] = a; Q.d[slot] = b;
 #if !PT_Q_THR_GATHER
         Q.t[slot] = c;
@@ -663,6 +670,7 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
         if (k1 >= 0) defer = !confirm_candidate(k1, res.x, P.bvh, P.g, o, d, h);  // k1 < 0: every geom is a proven miss
       }
       const uint32_t dmask = __ballot_sync(0xffffffffu, defer);
+      PT_CHECK(n_defer + __popc(dmask) <= (uint32_t)kDeferCap);
       if (defer) S.defer[n_defer + __popc(dmask & ((1u << lane) - 1u))] = base + j;
       n_defer += __popc(dmask);
       shade_and_compact<LAST, false, NEE>(P, nullptr, lane, valid && !defer && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
@@ -680,13 +688,20 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
   }
 }
 
-// live_total[d] += count[d]; one tiny launch per wavefront
-__global__ void k_accum_counts(const WfCtrl* ctrl, unsigned long long* live_total, int max_depth) {
+// live_total[d] += count[d]; one tiny launch per wavefront.  `policy` (mapped host memory, may be null): policy[d] = which
+// kernel suits depth d of THIS scene -- 1: k_bounce_q (a good part of the paths ends in the filter scan or on a light, so
+// re-batching the rest pays), 2: the fused k_bounce (nearly every path goes on: closed rooms) -- judged by the share
+// of depth d-1's paths that reach depth d.  The host reads it when it launches later wavefronts; results do not depend
+// on the choice.
+constexpr float kQSurvivalMax = 0.93f;
+__global__ void k_accum_counts(const WfCtrl* ctrl, unsigned long long* live_total, int max_depth, volatile int* policy) {
   int d = threadIdx.x;
   // atomics: the two wavefront slots run on different streams and may fold their counts at the same time
   if (d < max_depth) atomicAdd(live_total + d, (unsigned long long)ctrl->count[d]);
   if (d == 0) atomicAdd(live_total + kMaxDepth, (unsigned long long)ctrl->fallbacks);
   if (d == 1) atomicAdd(live_total + kMaxDepth + 1, ctrl->shadow);
+  if (policy && d >= 1 && d < max_depth && ctrl->count[d - 1] >= 4096u)
+    policy[d] = (float)ctrl->count[d] < kQSurvivalMax * (float)ctrl->count[d - 1] ? 1 : 2;
 }
 
 // the ray-independent part of hit_normal, once per scene: identical instructions, so identical bits
@@ -854,6 +869,7 @@ __global__ void __launch_bounds__(kCompactThreads, PT_COMPACT_BLOCKS) k_compact_
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       uint32_t pos = base + before[j];
+      PT_CHECK(pos + ((f[j] * 0x01010101u) >> 24) <= n);
       if (f[j] & 0x00000001u) out[pos++] = v[j].x;
       if (f[j] & 0x00000100u) out[pos++] = v[j].y;
       if (f[j] & 0x00010000u) out[pos++] = v[j].z;
@@ -996,6 +1012,7 @@ __global__ void __launch_bounds__(kCompactThreads, PT_COMPACT_BLOCKS) k_compact_
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       uint32_t pos = base + before[j];
+      PT_CHECK(pos + ((f[j] * 0x01010101u) >> 24) <= n);
       if (f[j] & 0x00000001u) out[pos++] = v[j].x;
       if (f[j] & 0x00000100u) out[pos++] = v[j].y;
       if (f[j] & 0x00010000u) out[pos++] = v[j].z;

@@ -49,6 +49,43 @@ def test_cudaRaytraceCore_running_mean_matches_oracle(pt, compat, oracle, sample
     compat.reset()
 
 
+def test_cudaRaytraceCore_sample_traced_ahead_is_dropped_when_the_sequence_changes(pt, compat, oracle, sample_scene):
+    """While a call's image travels to the host the shim already traces the next iteration's sample.  If the next call is
+    not that iteration with those settings, the sample traced ahead must not count."""
+    cam = with_resolution(sample_scene["camera"], 64, 64)
+    rs = compat.RefScene([(sample_scene["geoms"], cam)], sample_scene["materials"], iterations=4)
+    compat.reset(); compat.set_trace_depth(8); compat.set_seed(3); compat.set_exit_on_error(False)
+    scn = oracle.make_scene(sample_scene["geoms"], sample_scene["materials"], cam)
+    call = lambda k: compat.cudaRaytraceCore(None, rs.camera, 0, k, rs.materials, len(rs.materials), rs.geoms, len(rs.geoms))
+    want_sum = np.zeros((64 * 64, 3), np.float32)
+    for k in (1, 2):
+        call(k)
+        oracle.render(scn, k - 1, 1, 8, 3, sum_rgb=want_sum)
+    assert same_bits(rs.image, want_sum / np.float32(2))
+    # the seed changes: sample 2 was traced ahead with seed 3 and is dropped; the sum restarts from the caller's mean
+    compat.set_seed(4)
+    call(3)
+    oracle.render(scn, 2, 1, 8, 4, sum_rgb=want_sum)
+    assert np.allclose(rs.image, want_sum / np.float32(3), rtol=1e-6, atol=1e-6)
+    # in sequence again (sample 3 traced ahead with seed 4 and used); iteration 4 = camera.iterations: nothing is traced ahead
+    call(4)
+    oracle.render(scn, 3, 1, 8, 4, sum_rgb=want_sum)
+    assert np.allclose(rs.image, want_sum / np.float32(4), rtol=1e-6, atol=1e-6)
+    # past the scene's iteration count the calls still work (no sample traced ahead)
+    call(5)
+    oracle.render(scn, 4, 1, 8, 4, sum_rgb=want_sum)
+    assert np.allclose(rs.image, want_sum / np.float32(5), rtol=1e-6, atol=1e-6)
+    # a jump back: iteration 2 again restarts from the caller's image, which the test resets to the 1-sample mean
+    first, _, _ = oracle.render(scn, 0, 1, 8, 4)
+    rs.image[:] = first
+    call(2)
+    second = first.copy()
+    oracle.render(scn, 1, 1, 8, 4, sum_rgb=second)
+    assert np.allclose(rs.image, second / np.float32(2), rtol=1e-6, atol=1e-6)
+    assert compat.last_status() == 0
+    compat.reset()
+
+
 def test_cudaRaytraceCore_frame_selects_per_frame_arrays_and_writes_pbo(pt, compat, oracle, sample_scene):
     import torch
     cam = with_resolution(sample_scene["camera"], 64, 64)

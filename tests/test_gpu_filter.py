@@ -1,5 +1,7 @@
 """The filtered closest hit (csrc/pt_filter.cuh) must return the exact scan's answer bit for bit -- at the shipped
 error bounds and, as a margin check, with every rounding-error term of the bounds cut to a quarter."""
+import os
+
 import numpy as np
 import pytest
 
@@ -88,3 +90,27 @@ def test_hierarchy_render_matches_oracle(pt, oracle, sample_scene):
         _, _, live = c.counters()
     assert live[:6].tolist() == want_live.tolist()
     assert (got.view(np.uint32) == want_sum.view(np.uint32)).all()
+
+
+def test_procedural_10k_render_matches_oracle(pt, oracle, tmp_path):
+    """BASELINE configs[3] itself -- the 10 000-object procedural scene file, through the product's loader -- on a
+    96x54 crop of the frame (same view, 2 spp, 8 bounces): image and per-depth live counts identical to the oracle,
+    which tests all 10 000 geoms exactly for every segment."""
+    import subprocess
+    import sys
+    from conftest import ROOT, with_resolution
+    path = tmp_path / "procedural_10000.txt"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "scenes", "gen_scenes.py"), "--procedural", "10000", str(path)])
+    sc = pt.Scene(str(path))
+    g, m, cam, lens = sc.frame(0)
+    assert len(g) == 10000
+    cam = with_resolution(cam, 96, 54)
+    scn = oracle.make_scene(g, m, cam)
+    want_sum, want_live, _ = oracle.render(scn, 0, 2, 8, 565)
+    with pt.Context(g, m, cam) as c:
+        c.render(0, 2, 8, 565)
+        got = c.download_sum()
+        _, segs, live = c.counters()
+    assert live[:8].tolist() == want_live.tolist()
+    assert (got.view(np.uint32) == want_sum.view(np.uint32)).all()
+    assert segs > 96 * 54 * 2 * 1.5  # the frame looks at the cloud: most paths bounce

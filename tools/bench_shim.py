@@ -21,7 +21,7 @@ from scenes_for_tests import _sample  # noqa: E402
 def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     g, m, cam = _sample(pt)
-    rs = compat.RefScene([(g, cam)], m)
+    rs = compat.RefScene([(g, cam)], m, iterations=iters + 8)  # camera.iterations as a scene file would set it (ITERATIONS)
     compat.reset(); compat.set_trace_depth(8); compat.set_seed(565); compat.set_exit_on_error(False)
     for k in range(1, 4):  # warm-up
         compat.cudaRaytraceCore(None, rs.camera, 0, k, rs.materials, len(rs.materials), rs.geoms, len(rs.geoms))

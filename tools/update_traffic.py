@@ -39,5 +39,10 @@ out = {
     },
 }
 path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+if os.path.exists(path):  # keep what tools/update_inst.py measured (instructions per segment of a whole wavefront)
+    old = json.load(open(path))
+    for k in ("warp_inst_per_segment", "threads_per_instruction_wavefront", "inst_source", "sm_count"):
+        if k in old:
+            out[k] = old[k]
 json.dump(out, open(path, "w"), indent=1)
 print(json.dumps(out, indent=1))

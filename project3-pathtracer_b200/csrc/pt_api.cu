@@ -557,6 +557,9 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
         return me;
       };
       if (root_ref >= 0) collapse(root_ref, stack_need);
+      if (getenv("PT_B200_BVH_DEBUG"))
+        fprintf(stderr, "pt_b200 bvh: %d leaves, %d binary nodes, %zu wide nodes, stack need %d of %d%s\n", n, next_node,
+                F.nodes.size() / kBvhNodeRows, stack_need, kBvhStack, median_only ? " (median splits)" : "");
       if (stack_need + 2 <= kBvhStack || median_only) break;
       median_only = true;  // a degenerate tree: the balanced one needs 3 entries per two binary levels at most
     }

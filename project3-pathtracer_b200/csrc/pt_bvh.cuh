@@ -28,17 +28,17 @@ namespace ptd {
 // float2, child b in the high half), children (0, 1) in rows 0-3 and (2, 3) in rows 4-7:
 //   r0 = (min_a.x, min_b.x | min_a.y, min_b.y)  r1 = (min_a.z, min_b.z | max_a.x, max_b.x)  r2 = (max_a.y, max_b.y | max_a.z, max_b.z)
 //   r3 = (P1_a, P1_b | P2_a, P2_b)
-// row 8 = int bits (child0, child1, child2, child3); child >= 0: node, < 0: leaf ~child, kBvhNoChild: empty slot (its
-// box is (+inf, -inf): nothing enters it)
+// row 8 = int bits (child0, child1, child2, child3); child >= 0: node, < 0: leaf ~child, kBvhNoChild: empty slot
 // leaf = 5 float4 (scalar filter record) + int2 (class, geom index):
 //   class 0: l0 = (c.xyz, Wc)  l1 = (Ww, Wr, Ew_c, Ew_w)
 //   class 2: l0 = (c.xyz, Ew_c)  l1 = (Hc.xyz, Ew_w)  l2 = (Hw.xyz, -)
 //   class 1: l0..l2 = rows x,y,z of inverseTransform  l3 = (R2c, R2w, R2r, Ew_c)  l4 = (Ew_w, -, -, -)
 //   class 3: l0..l2 = rows x,y,z of inverseTransform  l3 = (hc.xyz, Ew_c)  l4 = (hw.xyz, Ew_w)
 constexpr int kBvhNodeRows = 9, kBvhLeafRows = 5;
-constexpr int kBvhStack = 64;        // entries of a traversal's stack: the builder checks the collapsed tree's worst case
+constexpr int kBvhStack = 128;       // entries of a traversal's stack: the builder checks the collapsed tree's worst case
 constexpr int kBvhBinaryDepth = 40;  // depth limit of the binary tree before the collapse
 constexpr int kBvhNoChild = (int)0x80000000;
+constexpr int kBvhDone = (int)0x80000001;  // `cur` of a finished traversal (k_bounce_bvh)
 struct BvhSoA {
   const float4* nodes;
   const float4* leaves;
@@ -149,72 +149,93 @@ __device__ __forceinline__ TravRay make_trav_ray(const BvhSoA& B, const ScanRay&
 }
 __device__ __forceinline__ int bvh_root(const BvhSoA& B) { return B.n_leaves == 1 ? ~0 : 0; }  // a single geom: the root is leaf 0
 
-// One step of a traversal: test the leaf `cur` (< 0) or the (up to four) children of the node `cur`, then move on.
-// Returns false when the traversal is finished.  EXACT = false: filter scan, result in `best` (k1 = leaf index).
-// EXACT = true: exact test of every candidate leaf that can still matter, result in `h`.
-// Children that can matter are visited nearest first: the nearest becomes `cur`, the others go on the stack farthest
-// first (the builder guarantees that the stack never needs more than kBvhStack entries).
+// the leaf `cur` (< 0): filter test (EXACT: exact test of the candidate if it can still matter)
+template <bool EXACT>
+__device__ __forceinline__ void leaf_visit(const BvhSoA& B, const GeomSoA& g, const ScanRay& r, ScanBest& best, Hit& h, int cur) {
+  const int leaf = ~cur;
+  const int2 meta = __ldg(B.leaf_meta + leaf);
+  float lo;
+  if (leaf_filter(meta.x, B.leaves + (size_t)leaf * kBvhLeafRows, r, lo)) {
+    lo = fmaxf(lo, 0.0f);
+    if (!EXACT) {
+      scan_take(best, lo, leaf);
+    } else if (!(lo > h.t)) {
+      const int gi = meta.y;
+      float dist;
+      f3 P;
+      int ncode;
+      if (exact_hit(meta.x < 2 ? 0 : 1, __ldg(g.inv0 + gi), __ldg(g.inv1 + gi), __ldg(g.inv2 + gi), __ldg(g.fwd0 + gi),
+                    __ldg(g.fwd1 + gi), __ldg(g.fwd2 + gi), r.o, r.d, dist, P, ncode)) {
+        // specification: scan in index order, keep the strictly smaller positive distance
+        if (dist > 0 && (dist < h.t || (dist == h.t && gi < h.id))) { h.t = dist; h.id = gi; h.p = P; h.ncode = ncode; }
+      }
+    }
+  }
+}
+
+// the inner node `cur` (>= 0): test its (up to four) children; the nearest one that can matter becomes `cur`, the others
+// go on the stack farthest first.  Returns false if no child can matter (the caller pops).
+template <bool EXACT>
+__device__ __forceinline__ bool node_visit(const BvhSoA& B, const ScanRay& r, const TravRay& tr, const ScanBest& best, const Hit& h,
+                                           int& cur, int& sp, int* stack) {
+  const float4* N = B.nodes + (size_t)cur * kBvhNodeRows;
+  const float4 a0 = __ldg(N), a1 = __ldg(N + 1), a2 = __ldg(N + 2), a3 = __ldg(N + 3);
+  const float4 b0 = __ldg(N + 4), b1 = __ldg(N + 5), b2 = __ldg(N + 6), b3 = __ldg(N + 7);
+  const int4 ch = __ldg(reinterpret_cast<const int4*>(N + 8));
+  float e[4];
+  child_entries(a0, a1, a2, a3, r, e[0], e[1]);
+  child_entries(b0, b1, b2, b3, r, e[2], e[3]);
+  // a child whose best possible bound cannot beat the current limit is skipped:
+  //   filter pass: bound >= lo2 changes neither k1 nor lo2 (a missed box has bound +inf);
+  //   exact pass: bound > best exact distance (ties may still win)
+  // sort keys: the entry parameter's bits (>= 0, so they order like integers) with the slot number in the two lowest
+  // bits; a skipped child gets the largest key
+  // (an empty slot is excluded by its child word, not by its box: the pad of a box at infinity is 0 * inf = NaN, which
+  // child_entries reads as "may be entered")
+  const int chs[4] = {ch.x, ch.y, ch.z, ch.w};
+  uint32_t k[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float bd = __fmaf_rn(e[i], tr.dls, -tr.ewmax);
+    const bool v = (EXACT ? (e[i] < INFINITY && !(bd > h.t)) : (bd < best.lo2)) && chs[i] != kBvhNoChild;
+    k[i] = v ? ((__float_as_uint(e[i]) & ~3u) | (uint32_t)i) : 0xffffffffu;
+  }
+  // sorting network on four keys (ascending)
+#define PT_CSWAP(x, y) { const uint32_t lo_ = min(k[x], k[y]), hi_ = max(k[x], k[y]); k[x] = lo_; k[y] = hi_; }
+  PT_CSWAP(0, 1) PT_CSWAP(2, 3) PT_CSWAP(0, 2) PT_CSWAP(1, 3) PT_CSWAP(1, 2)
+#undef PT_CSWAP
+  if (k[0] == 0xffffffffu) return false;
+  auto child_of = [&](uint32_t key) { const uint32_t s_ = key & 3u; return s_ == 0 ? ch.x : (s_ == 1 ? ch.y : (s_ == 2 ? ch.z : ch.w)); };
+#pragma unroll
+  for (int i = 3; i >= 1; i--) {
+    if (k[i] != 0xffffffffu) {
+      PT_CHECK(sp < kBvhStack);
+      stack[sp++] = child_of(k[i]);
+    }
+  }
+#ifdef PT_BVH_PREFETCH
+  if (k[1] != 0xffffffffu) {  // the child that is popped next: on its way into L1 while the nearest one is walked
+    const int nx = child_of(k[1]);
+    if (nx >= 0) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(B.nodes + (size_t)nx * kBvhNodeRows));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(B.nodes + (size_t)nx * kBvhNodeRows + 8));
+    } else {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(B.leaves + (size_t)(~nx) * kBvhLeafRows));
+    }
+  }
+#endif
+  cur = child_of(k[0]);
+  return true;
+}
+
+// One step of a traversal: the leaf or the node `cur`, then move on.  Returns false when the traversal is finished.
+// EXACT = false: filter scan, result in `best` (k1 = leaf index).  EXACT = true: exact test of every candidate leaf that
+// can still matter, result in `h`.  (The builder guarantees that the stack never needs more than kBvhStack entries.)
 template <bool EXACT>
 __device__ __forceinline__ bool trav_step(const BvhSoA& B, const GeomSoA& g, const ScanRay& r, const TravRay& tr, ScanBest& best, Hit& h,
                                           int& cur, int& sp, int* stack) {
-  if (cur < 0) {
-    const int leaf = ~cur;
-    const int2 meta = __ldg(B.leaf_meta + leaf);
-    float lo;
-    if (leaf_filter(meta.x, B.leaves + (size_t)leaf * kBvhLeafRows, r, lo)) {
-      lo = fmaxf(lo, 0.0f);
-      if (!EXACT) {
-        scan_take(best, lo, leaf);
-      } else if (!(lo > h.t)) {
-        const int gi = meta.y;
-        float dist;
-        f3 P;
-        int ncode;
-        if (exact_hit(meta.x < 2 ? 0 : 1, __ldg(g.inv0 + gi), __ldg(g.inv1 + gi), __ldg(g.inv2 + gi), __ldg(g.fwd0 + gi),
-                      __ldg(g.fwd1 + gi), __ldg(g.fwd2 + gi), r.o, r.d, dist, P, ncode)) {
-          // specification: scan in index order, keep the strictly smaller positive distance
-          if (dist > 0 && (dist < h.t || (dist == h.t && gi < h.id))) { h.t = dist; h.id = gi; h.p = P; h.ncode = ncode; }
-        }
-      }
-    }
-  } else {
-    const float4* N = B.nodes + (size_t)cur * kBvhNodeRows;
-    const float4 a0 = __ldg(N), a1 = __ldg(N + 1), a2 = __ldg(N + 2), a3 = __ldg(N + 3);
-    const float4 b0 = __ldg(N + 4), b1 = __ldg(N + 5), b2 = __ldg(N + 6), b3 = __ldg(N + 7);
-    const int4 ch = __ldg(reinterpret_cast<const int4*>(N + 8));
-    float e[4];
-    child_entries(a0, a1, a2, a3, r, e[0], e[1]);
-    child_entries(b0, b1, b2, b3, r, e[2], e[3]);
-    // a child whose best possible bound cannot beat the current limit is skipped:
-    //   filter pass: bound >= lo2 changes neither k1 nor lo2 (a missed box has bound +inf);
-    //   exact pass: bound > best exact distance (ties may still win)
-    // sort keys: the entry parameter's bits (>= 0, so they order like integers) with the slot number in the two lowest
-    // bits; a skipped child gets the largest key
-    uint32_t k[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const float bd = __fmaf_rn(e[i], tr.dls, -tr.ewmax);
-      const bool v = EXACT ? (e[i] < INFINITY && !(bd > h.t)) : (bd < best.lo2);
-      k[i] = v ? ((__float_as_uint(e[i]) & ~3u) | (uint32_t)i) : 0xffffffffu;
-    }
-    // sorting network on four keys (ascending)
-#define PT_CSWAP(x, y) { const uint32_t lo_ = min(k[x], k[y]), hi_ = max(k[x], k[y]); k[x] = lo_; k[y] = hi_; }
-    PT_CSWAP(0, 1) PT_CSWAP(2, 3) PT_CSWAP(0, 2) PT_CSWAP(1, 3) PT_CSWAP(1, 2)
-#undef PT_CSWAP
-    if (k[0] != 0xffffffffu) {
-      auto child_of = [&](uint32_t key) { const uint32_t s_ = key & 3u; return s_ == 0 ? ch.x : (s_ == 1 ? ch.y : (s_ == 2 ? ch.z : ch.w)); };
-      // farthest first onto the stack
-#pragma unroll
-      for (int i = 3; i >= 1; i--) {
-        if (k[i] != 0xffffffffu) {
-          PT_CHECK(sp < kBvhStack);
-          stack[sp++] = child_of(k[i]);
-        }
-      }
-      cur = child_of(k[0]);
-      return true;
-    }
-  }
+  if (cur < 0) leaf_visit<EXACT>(B, g, r, best, h, cur);
+  else if (node_visit<EXACT>(B, r, tr, best, h, cur, sp, stack)) return true;
   if (sp == 0) return false;
   cur = stack[--sp];
   return true;

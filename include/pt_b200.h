@@ -98,6 +98,10 @@ int pt_update_scene(pt_context* ctx, const pt_static_geom* geoms, int n_geoms, c
 int pt_set_wavefront_paths(pt_context* ctx, uint64_t max_paths);
 /* run on a caller-owned cudaStream_t instead of the context's own stream (NULL restores it) */
 int pt_set_stream(pt_context* ctx, void* cuda_stream);
+/* Which kernels trace a wavefront of a scene with few geoms -- a tuning / test knob; results never depend on it.
+ *   bounce_kernel   depths >= 1: 0 = automatic (per depth, by the share of paths the scene keeps alive), 1 = always the
+ *                   kernel that re-batches exact test + shading by winner type (k_bounce_q), 2 = always the fused one */
+int pt_set_kernel_policy(pt_context* ctx, int bounce_kernel);
 /* Pixels per wavefront band.  0 (default) = automatic: the whole frame, or bands of 1 Mi pixels when the float4
  * accumulation image exceeds 48 MB (e.g. 3840x2160: +9 %), so that the radiance atomics of the wavefronts in flight stay in
  * L2.  A wavefront then covers [band] x [more samples].  Results do not depend on it. */
@@ -118,13 +122,23 @@ int pt_last_render_ms(pt_context* ctx, float* ms);
  * renderCam->image layout (index = x + y*W, src/main.cpp:122). ---- */
 int pt_download_sum(pt_context* ctx, float* rgb);
 int pt_download_mean(pt_context* ctx, float* rgb, uint32_t spp); /* sum / spp */
-/* The reference's loop reads the running mean after EVERY sample (src/main.cpp:93-113: one cudaRaytraceCore per
- * iteration, image copied back at src/raytraceKernel.cu:154).  This call hands out sum / spp of the samples traced so far
- * and, while that image is on its way to the host, already traces samples [next_first_sample, next_first_sample +
- * next_n_samples) (0 = none): it returns as soon as `rgb` is complete; the render it started finishes in the background
- * (ordered before every later call on this context). */
-int pt_download_mean_then_render(pt_context* ctx, float* rgb, uint32_t spp, uint32_t next_first_sample,
-                                 uint32_t next_n_samples, int max_depth, uint64_t seed);
+/* ---- sample streaming: the reference's loop reads the running mean after EVERY sample (src/main.cpp:93-113: one
+ * cudaRaytraceCore per iteration, image copied back at src/raytraceKernel.cu:154).  Tracing one sample per call costs
+ * eight small, latency-bound launches per sample; a stream traces samples AHEAD in groups at the throughput of a large
+ * wavefront, forms their running means ahead as well, and lets a call only copy its mean to the host.
+ *   pt_stream_begin  starts tracing samples first_sample, first_sample + 1, ... on top of the current sum, which holds
+ *                    spp_before samples (two groups of `group` samples are in flight, each sample in an image of its own:
+ *                    about 2 * group * W * H * 28 bytes of HBM)
+ *   pt_stream_next   hands out the running mean after the next sample: rgb (host, W*H*3 floats) = (sum + that sample and all
+ *                    streamed before it) / (spp_before + their number), the same binary32 adds in the same order as one
+ *                    pt_render per sample when at most one path per pixel and sample carries radiance (no direct light
+ *                    sampling); if device_rgba8 is not NULL that DEVICE buffer gets sendImageToPBO's bytes of the mean;
+ *                    *spp (may be NULL) = the divisor used.  Returns when rgb is complete.
+ *   pt_stream_end    folds the samples handed out so far into the accumulation buffer and drops the rest (every call that
+ *                    reads or changes the buffer, the scene or the settings does the same implicitly) */
+int pt_stream_begin(pt_context* ctx, uint32_t first_sample, uint32_t spp_before, int max_depth, uint64_t seed, uint32_t group);
+int pt_stream_next(pt_context* ctx, float* rgb, void* device_rgba8, uint32_t* spp);
+int pt_stream_end(pt_context* ctx);
 /* overwrite the accumulation buffer (resume, or the running mean of the compat shim) */
 int pt_upload_sum(pt_context* ctx, const float* rgb);
 /* sendImageToPBO (src/raytraceKernel.cu:58-89): uchar4{r,g,b,0} = min(mean*255, 255), truncated.

@@ -88,6 +88,9 @@ int pt_compat_set_seed(unsigned long long seed);
 int pt_compat_set_device(int device);
 int pt_compat_set_lens(float aperture, float focal_distance);
 int pt_compat_set_exit_on_error(int on);
+/* samples traced ahead of the calls per group (default 8, 1..64; two groups are in flight): a sequence of calls
+ * iterations = k, k+1, ... then only adds one traced sample per call; results do not depend on it */
+int pt_compat_set_ahead(int samples);
 int pt_compat_set_direct_lighting(int on); /* pt_set_direct_lighting for the calls that follow (default off) */
 /* 1: cudaRaytraceCore behaves exactly like the UNMODIFIED reference does today -- its raytraceRay is a stub that fills
  * renderCam->image with per-pixel noise and converts that to the PBO (src/raytraceKernel.cu:93-104,149-154) -- so a

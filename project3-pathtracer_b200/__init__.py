@@ -143,6 +143,22 @@ class Context:
         _check(lib().pt_download_mean(self._h, _p(out), C.c_uint32(spp)))
         return out
 
+    def stream_begin(self, first_sample, spp_before, max_depth, seed=0, group=8):
+        """pt_stream_begin: trace samples first_sample, first_sample + 1, ... ahead, `group` at a time, on top of a sum
+        of spp_before samples"""
+        _check(lib().pt_stream_begin(self._h, C.c_uint32(first_sample), C.c_uint32(spp_before), C.c_int(max_depth),
+                                     C.c_uint64(seed), C.c_uint32(group)))
+
+    def stream_next(self, out=None, device_rgba8=None):
+        """pt_stream_next: the running mean after the next traced sample -> (mean (W*H, 3), divisor)"""
+        out = np.empty((self.npix, 3), np.float32) if out is None else out
+        spp = C.c_uint32()
+        _check(lib().pt_stream_next(self._h, _p(out), C.c_void_p(device_rgba8), C.byref(spp)))
+        return out, spp.value
+
+    def stream_end(self):
+        _check(lib().pt_stream_end(self._h))
+
     def upload_sum(self, rgb):
         rgb = _arr(rgb, np.float32)
         assert rgb.size == self.npix * 3
@@ -163,6 +179,11 @@ class Context:
         live = np.zeros(64, np.uint64)
         _check(lib().pt_counters(self._h, C.byref(paths), C.byref(segs), _p(live)))
         return paths.value, segs.value, live
+
+    def set_kernel_policy(self, bounce_kernel=0):
+        """tuning / test knob (pt_set_kernel_policy): depths >= 1 of few-geom scenes run 0 = the kernel the scene's
+        measured survival suggests, 1 = the re-batched kernel (k_bounce_q), 2 = the fused kernel; same results"""
+        _check(lib().pt_set_kernel_policy(self._h, C.c_int(bounce_kernel)))
 
     def set_band_pixels(self, pixels):
         """pixels per wavefront band (0 = automatic); results do not depend on it"""

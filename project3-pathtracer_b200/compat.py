@@ -91,6 +91,12 @@ def set_lens(aperture, focal_distance):
     lib().pt_compat_set_lens(C.c_float(aperture), C.c_float(focal_distance))
 
 
+def set_ahead(samples):
+    """samples per group traced ahead of the calls (pt_compat_set_ahead)"""
+    if lib().pt_compat_set_ahead(C.c_int(samples)) != 0:
+        raise ValueError("samples outside [1, 64]")
+
+
 def set_exit_on_error(on):
     lib().pt_compat_set_exit_on_error(C.c_int(1 if on else 0))
 

@@ -5,10 +5,10 @@
 // context instead of being malloc'ed and freed per call (:118-119,136-137,157-159), and while calls arrive in
 // sequence (k, k+1, ...) the exact running SUM stays in HBM, so the per-call H2D of the image (:120) disappears;
 // the D2H of the running mean into renderCam->image (:154) is kept because the caller owns and reads that buffer.
-// While that copy is in flight the GPU already traces the NEXT sample (the reference's loop calls again with k + 1,
-// src/main.cpp:93-95): the next call finds its sample done and only resolves and copies.  A call that does not continue
-// the sequence (other scene, frame, camera, iteration number) discards the sample traced ahead: it restarts from
-// renderCam->image or from zero exactly as before.
+// The samples themselves are traced AHEAD of the calls, a group at a time (pt_stream_*: the reference's loop calls again
+// with k + 1, src/main.cpp:93-95), so a call in sequence only adds its sample to the sum and copies the mean.  A call
+// that does not continue the sequence (other scene, frame, camera, iteration number, depth, seed) drops what was traced
+// ahead: it restarts from renderCam->image or from zero exactly as before.
 #include "../../include/pt_b200.h"
 #include "../../include/pt_compat.h"
 
@@ -33,10 +33,10 @@ struct Cache {
   pt_lens lens{0.0f, 0.0f};
   const camera* last_cam = nullptr;
   int last_frame = -1, last_iter = 0;
-  int ahead_iter = 0;      // iteration number whose sample is already traced (or being traced) in the accumulation buffer; 0 = none
-  int ahead_depth = 0, ahead_direct = 0;
-  unsigned long long ahead_seed = 0;
-  int direct_applied = -1; // pt_set_direct_lighting synchronises the stream: only called when the value changes
+  bool streaming = false;  // a sample stream is open on ctx: samples last_iter, last_iter + 1, ... are traced ahead
+  int stream_depth = 0, stream_direct = 0;
+  unsigned long long stream_seed = 0;
+  int direct_applied = -1; // pt_set_direct_lighting drops the stream: only called when the value changes
   std::vector<float> scaled;
   void* pinned = nullptr;  // renderCam->image, page-locked in place while a sequence of calls keeps arriving for it
   size_t pinned_bytes = 0;
@@ -47,6 +47,7 @@ unsigned long long g_seed = 0;
 int g_device = 0;
 pt_lens g_lens{0.0f, 0.0f};
 int g_exit_on_error = 1;
+int g_ahead = 8;   // samples per group traced ahead of the calls (pt_compat_set_ahead)
 int g_direct = 0;  // pt_compat_set_direct_lighting
 int g_stub = 0;    // pt_compat_set_reference_stub
 int g_status = PT_OK;
@@ -74,6 +75,12 @@ extern "C" int pt_compat_set_lens(float aperture, float focal_distance) {
   return PT_OK;
 }
 extern "C" int pt_compat_set_exit_on_error(int on) { g_exit_on_error = on; return PT_OK; }
+extern "C" int pt_compat_set_ahead(int samples) {
+  if (samples < 1 || samples > 64) return PT_ERR_INVALID;
+  if (samples != g_ahead) pt_compat_reset();  // the cached context sized its wavefront for the old group
+  g_ahead = samples;
+  return PT_OK;
+}
 extern "C" int pt_compat_set_direct_lighting(int on) { g_direct = on != 0; return PT_OK; }
 extern "C" int pt_compat_set_reference_stub(int on) { g_stub = on != 0; return PT_OK; }
 extern "C" int pt_compat_last_status(void) { return g_status; }
@@ -138,8 +145,8 @@ void cudaRaytraceCore(uchar4* PBOpos, camera* renderCam, int frame, int iteratio
   if (g.ctx && (g.W != W || g.H != H || g.device != g_device)) pt_compat_reset();
   if (!g.ctx) {
     if ((rc = pt_context_create(sg.data(), numberOfGeoms, pm, numberOfMaterials, &cam, &g_lens, g_device, &g.ctx))) return fail(rc);
-    // one sample per call: a wavefront never needs more than one sample of the frame
-    if ((rc = pt_set_wavefront_paths(g.ctx, npix))) return fail(rc);
+    // samples are traced ahead a group at a time: one wavefront per group
+    if ((rc = pt_set_wavefront_paths(g.ctx, npix * (size_t)g_ahead))) return fail(rc);
     g.W = W; g.H = H; g.device = g_device;
     scene_changed = true;
   } else if (g.geoms.size() != sg.size() || memcmp(g.geoms.data(), sg.data(), sg.size() * sizeof(pt_static_geom)) ||
@@ -165,38 +172,34 @@ void cudaRaytraceCore(uchar4* PBOpos, camera* renderCam, int frame, int iteratio
       if ((rc = pt_resolve_rgba8(g.ctx, 1, nullptr, PBOpos))) return fail(rc);
     }
     g.last_cam = nullptr;  // the next real call resumes from the caller's image
+    g.streaming = false;   // (pt_upload_sum above dropped any samples traced ahead)
     return;
   }
   const bool in_sequence = !scene_changed && g.last_cam == renderCam && g.last_frame == frame && iterations == g.last_iter + 1;
-  // the sample of this call may have been traced ahead, during the previous call's copy
-  const int ahead = g.ahead_iter;
-  g.ahead_iter = 0;
-  const bool traced_ahead = in_sequence && ahead == iterations && g.ahead_depth == g_depth && g.ahead_seed == g_seed &&
-                            g.ahead_direct == g_direct;
-  const bool stale_ahead = ahead != 0 && !traced_ahead;  // the buffer holds a sample that does not belong to this call's sum
-  if (iterations == 1) {
-    if ((rc = pt_clear(g.ctx))) return fail(rc);  // (also drops a sample traced ahead for a sequence that did not go on)
-  } else if (!in_sequence || stale_ahead) {
-    // resume from the caller's running mean: sum = image * (k-1)
-    g.scaled.resize(npix * 3);
-    const float k1 = (float)(iterations - 1);
-    const float* im = reinterpret_cast<const float*>(renderCam->image);
-    for (size_t i = 0; i < npix * 3; i++) g.scaled[i] = im[i] * k1;
-    if ((rc = pt_upload_sum(g.ctx, g.scaled.data()))) return fail(rc);
+  // the stream of samples traced ahead goes on if this call is the next iteration with the same settings
+  const bool stream_ok = g.streaming && in_sequence && g.stream_depth == g_depth && g.stream_seed == g_seed &&
+                         g.stream_direct == g_direct;
+  if (!stream_ok) {
+    if (g.streaming) { g.streaming = false; if ((rc = pt_stream_end(g.ctx))) return fail(rc); }
+    if (iterations == 1) {
+      if ((rc = pt_clear(g.ctx))) return fail(rc);
+    } else if (!in_sequence) {
+      // resume from the caller's running mean: sum = image * (k-1)
+      g.scaled.resize(npix * 3);
+      const float k1 = (float)(iterations - 1);
+      const float* im = reinterpret_cast<const float*>(renderCam->image);
+      for (size_t i = 0; i < npix * 3; i++) g.scaled[i] = im[i] * k1;
+      if ((rc = pt_upload_sum(g.ctx, g.scaled.data()))) return fail(rc);
+    }  // (in sequence with other settings: the exact sum of the samples so far is in HBM and stays)
+    if (g.direct_applied != g_direct) {
+      if ((rc = pt_set_direct_lighting(g.ctx, g_direct))) return fail(rc);
+      g.direct_applied = g_direct;
+    }
+    if ((rc = pt_stream_begin(g.ctx, (uint32_t)(iterations - 1), (uint32_t)(iterations - 1), g_depth, g_seed, (uint32_t)g_ahead))) return fail(rc);
+    g.streaming = true; g.stream_depth = g_depth; g.stream_seed = g_seed; g.stream_direct = g_direct;
   }
   if (in_sequence || iterations == 1) pin(renderCam->image, npix * 3 * sizeof(float), iterations == 1);  // a render loop, not a one-off call
-  if (g.direct_applied != g_direct) {
-    if ((rc = pt_set_direct_lighting(g.ctx, g_direct))) return fail(rc);
-    g.direct_applied = g_direct;
-  }
-  if (!traced_ahead && (rc = pt_render(g.ctx, (uint32_t)(iterations - 1), 1, g_depth, g_seed))) return fail(rc);
-  if (PBOpos && (rc = pt_resolve_rgba8(g.ctx, (uint32_t)iterations, nullptr, PBOpos))) return fail(rc);
-  // the running mean goes home; meanwhile the next iteration's sample is traced (not past the scene's iteration count)
-  const bool go_on = (in_sequence || iterations == 1) && (renderCam->iterations == 0 || (unsigned)iterations < renderCam->iterations);
-  if ((rc = pt_download_mean_then_render(g.ctx, reinterpret_cast<float*>(renderCam->image), (uint32_t)iterations,
-                                         (uint32_t)iterations, go_on ? 1u : 0u, g_depth, g_seed)))
-    return fail(rc);
-  if (go_on) { g.ahead_iter = iterations + 1; g.ahead_depth = g_depth; g.ahead_seed = g_seed; g.ahead_direct = g_direct; }
+  if ((rc = pt_stream_next(g.ctx, reinterpret_cast<float*>(renderCam->image), PBOpos, nullptr))) return fail(rc);
   g.last_cam = renderCam;
   g.last_frame = frame;
   g.last_iter = iterations;

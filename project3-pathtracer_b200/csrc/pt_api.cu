@@ -111,8 +111,19 @@ struct pt_context {
                                       // 1 = always k_bounce_q, 2 = always the fused k_bounce (PT_B200_FUSED=1 / =0 force 2 / 1)
   int* h_policy = nullptr;            // mapped host memory, kMaxDepth + 1 ints written by k_accum_counts: 0 unknown, 1 q, 2 fused
   int* d_policy = nullptr;            // ... its device address
-  cudaStream_t copy_stream = nullptr; // pt_download_mean_then_render: the image leaves while the next samples are traced
-  cudaEvent_t ev_res = nullptr, ev_copy = nullptr;
+  // sample streaming (pt_stream_*): samples are traced ahead in groups into per-sample images ("slabs") on ahead_stream,
+  // folded into d_accum one per call on the caller's stream, and the running mean leaves through copy_stream
+  cudaStream_t copy_stream = nullptr, ahead_stream = nullptr;
+  cudaEvent_t ev_res = nullptr, ev_copy = nullptr, ev_ready[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  float4* d_slab = nullptr;           // 2 groups x stream_group images of npix float4
+  float* d_means = nullptr;           // 2 groups x stream_group running means (npix * 3 floats each), computed ahead
+  float4* d_base[2] = {nullptr, nullptr};  // d_base[s]: the sum before the group that lives in slot s
+  uint32_t slab_group = 0;            // images per group the buffers above were allocated for
+  bool stream_open = false;
+  uint32_t stream_base = 0, stream_next = 0, stream_group = 0;  // first sample of the stream, next sample to hand out, samples per group
+  uint32_t stream_spp0 = 0;           // samples in the sum before the stream's first sample
+  int stream_depth = 0;
+  uint64_t stream_seed = 0;
   int mode = -1;                      // 0: linear scan over pairs staged in shared memory, 1: hierarchy (pt_bvh.cuh)
   size_t smem_bytes = 0;   // k_bounce: filter geometry
   size_t geom_smem = 0;    // filter geometry only (k_intersect_list)
@@ -882,9 +893,15 @@ extern "C" int pt_context_destroy(pt_context* c) {
     if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
   }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ahead_stream) { cudaStreamSynchronize(c->ahead_stream); cudaStreamDestroy(c->ahead_stream); }
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->ev_res) cudaEventDestroy(c->ev_res);
   if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+  for (int i = 0; i < 2; i++) {
+    if (c->ev_ready[i]) cudaEventDestroy(c->ev_ready[i]);
+    if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
+  }
+  cudaFree(c->d_slab); cudaFree(c->d_means); cudaFree(c->d_base[0]); cudaFree(c->d_base[1]);
   if (c->h_policy) cudaFreeHost(c->h_policy);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -937,6 +954,8 @@ extern "C" int pt_context_create(const pt_static_geom* geoms, int n_geoms, const
   return PT_OK;
 }
 
+static int stream_discard(pt_context* c);  // pt_stream_*: drop the samples traced ahead
+
 #define CTX(c)                                                       \
   do {                                                               \
     if (!(c)) { pt_set_error_("context is NULL"); return PT_ERR_STATE; } \
@@ -946,14 +965,24 @@ extern "C" int pt_context_create(const pt_static_geom* geoms, int n_geoms, const
 extern "C" int pt_update_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms, const pt_material* materials,
                                int n_materials, const pt_camera_data* cam, const pt_lens* lens) {
   CTX(c);
+  if (int rc = stream_discard(c)) return rc;
   CU(cudaStreamSynchronize(c->stream));
   return upload_scene(c, geoms, n_geoms, materials, n_materials, cam, lens, false);
 }
 
 extern "C" int pt_set_wavefront_paths(pt_context* c, uint64_t max_paths) {
   CTX(c);
+  if (int rc = stream_discard(c)) return rc;
   CU(cudaStreamSynchronize(c->stream));
   return alloc_wavefront(c, max_paths);
+}
+
+extern "C" int pt_set_kernel_policy(pt_context* c, int bounce_kernel) {
+  CTX(c);
+  if (bounce_kernel < 0 || bounce_kernel > 2) { pt_set_error_("bounce_kernel %d (0 = automatic, 1 = re-batched, 2 = fused)", bounce_kernel); return PT_ERR_INVALID; }
+  CU(cudaStreamSynchronize(c->stream));
+  c->q_mode = bounce_kernel;
+  return PT_OK;
 }
 
 extern "C" int pt_set_band_pixels(pt_context* c, uint32_t pixels) {
@@ -972,6 +1001,7 @@ extern "C" int pt_set_stream(pt_context* c, void* cuda_stream) {
 
 extern "C" int pt_clear(pt_context* c) {
   CTX(c);
+  if (int rc = stream_discard(c)) return rc;
   CU(cudaMemsetAsync(c->d_accum, 0, (size_t)c->npix * sizeof(float4), c->stream));
   CU(cudaMemsetAsync(c->d_live, 0, (kMaxDepth + 2) * sizeof(unsigned long long), c->stream));
   c->paths_total = 0;
@@ -1007,8 +1037,10 @@ static cudaError_t launch_bounce(pt_context* c, int slot, const BounceParams& P,
   return cudaGetLastError();
 }
 
-extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_samples, int max_depth, uint64_t seed) {
-  CTX(c);
+// Trace samples [first_sample, first_sample + n_samples) of every pixel, enqueued behind `stream0`.  Radiance goes to
+// accum[(s - acc_s0) * acc_stride + pixel] (stride 0: one image).
+static int render_into(pt_context* c, uint32_t first_sample, uint32_t n_samples, int max_depth, uint64_t seed, cudaStream_t stream0,
+                       float4* accum, uint32_t acc_s0, uint32_t acc_stride, bool timed) {
   if (max_depth < 1 || max_depth > kMaxDepth) { pt_set_error_("max_depth %d outside [1,%d]", max_depth, kMaxDepth); return PT_ERR_INVALID; }
   if ((uint64_t)first_sample + n_samples > 0xFFFFFFFFull) { pt_set_error_("sample index overflow"); return PT_ERR_INVALID; }
   if (!c->d_state || c->wf_capacity == 0) {
@@ -1016,7 +1048,7 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
     return PT_ERR_STATE;
   }
   NvtxRange nvtx_render("pt_render");
-  CU(cudaEventRecord(c->ev0, c->stream));
+  if (timed) CU(cudaEventRecord(c->ev0, stream0));
   const uint64_t cap = c->wf_capacity;
   // Bands: a frame whose float4 accumulation image does not leave room in the 126 MB L2 (> 48 MB, e.g. 3840x2160) is
   // rendered in bands of 1 Mi pixels (16 MB of sums) with proportionally more samples per wavefront, so that the radiance
@@ -1033,7 +1065,7 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
   const int slots_used = n_wf < (uint64_t)c->n_slots ? (int)n_wf : c->n_slots;
   const bool forked = slots_used > 1;  // a single wavefront in flight simply runs on the caller's stream
   if (forked) {
-    CU(cudaEventRecord(c->ev_fork, c->stream));
+    CU(cudaEventRecord(c->ev_fork, stream0));
     for (int i = 0; i < slots_used; i++) CU(cudaStreamWaitEvent(c->wf_stream[i], c->ev_fork, 0));
   }
   uint64_t wf = 0;
@@ -1044,7 +1076,7 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
   for (uint32_t s0 = 0; s0 < n_samples; s0 += spp_wf, wf++) {
     NvtxRange nvtx_wf("wavefront");
     const int sl = (int)(wf % (uint64_t)slots_used);
-    cudaStream_t st = forked ? c->wf_stream[sl] : c->stream;
+    cudaStream_t st = forked ? c->wf_stream[sl] : stream0;
     float4* S = c->d_state + (size_t)sl * 6 * cap;
     WfCtrl* ctrl = c->d_ctrl + sl;
     const uint32_t ns = (n_samples - s0 < spp_wf) ? (n_samples - s0) : spp_wf;
@@ -1055,7 +1087,7 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
       const int in = depth & 1, outb = in ^ 1;
       P.in_o = S + (3 * in + 0) * cap; P.in_d = S + (3 * in + 1) * cap; P.in_t = S + (3 * in + 2) * cap;
       P.out_o = S + (3 * outb + 0) * cap; P.out_d = S + (3 * outb + 1) * cap; P.out_t = S + (3 * outb + 2) * cap;
-      P.accum = c->d_accum;
+      P.accum = accum; P.acc_s0 = acc_s0; P.acc_stride = acc_stride;
       P.g = c->g; P.n_geoms = c->n_geoms;
       P.normals = c->d_normals;
       P.filt = c->filt; P.filt_cap = c->filt_cap;
@@ -1089,11 +1121,19 @@ extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_sample
   // join: the caller's stream continues when both internal streams are done
   for (int i = 0; forked && i < slots_used; i++) {
     CU(cudaEventRecord(c->ev_join[i], c->wf_stream[i]));
-    CU(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
+    CU(cudaStreamWaitEvent(stream0, c->ev_join[i], 0));
   }
-  CU(cudaEventRecord(c->ev1, c->stream));
-  c->timed = true;
+  if (timed) {
+    CU(cudaEventRecord(c->ev1, stream0));
+    c->timed = true;
+  }
   return PT_OK;
+}
+
+extern "C" int pt_render(pt_context* c, uint32_t first_sample, uint32_t n_samples, int max_depth, uint64_t seed) {
+  CTX(c);
+  if (int rc = stream_discard(c)) return rc;  // samples traced ahead share the path-state buffers
+  return render_into(c, first_sample, n_samples, max_depth, seed, c->stream, c->d_accum, 0u, 0u, true);
 }
 
 extern "C" int pt_sync(pt_context* c) {
@@ -1113,6 +1153,7 @@ extern "C" int pt_last_render_ms(pt_context* c, float* ms) {
 
 static int download_rgb(pt_context* c, float* rgb, float spp, int divide) {
   if (!rgb) { pt_set_error_("rgb is NULL"); return PT_ERR_INVALID; }
+  if (int rc = stream_discard(c)) return rc;  // a sample stream keeps the sum up to date lazily
   const uint32_t blocks = (c->npix + 255) / 256;
   k_resolve_rgb<<<blocks, 256, 0, c->stream>>>(c->d_accum, c->npix, spp, divide, c->d_rgb);
   c->launches++;
@@ -1128,35 +1169,123 @@ extern "C" int pt_download_mean(pt_context* c, float* rgb, uint32_t spp) {
   return download_rgb(c, rgb, (float)spp, 1);
 }
 
-// The reference's loop asks for the image after EVERY sample (src/main.cpp:93-113).  Here the mean of the samples so far
-// leaves through a copy stream while the render stream already traces the next samples: the caller waits for the copy
-// only.  The next call then finds its samples done.  (Resolve -> event -> D2H on the copy stream; the render is queued
-// behind the resolve on the render stream, so it cannot change what is being copied: the resolve wrote a snapshot.)
-extern "C" int pt_download_mean_then_render(pt_context* c, float* rgb, uint32_t spp, uint32_t next_first_sample,
-                                            uint32_t next_n_samples, int max_depth, uint64_t seed) {
+// ---- sample streaming: the reference's loop asks for the running mean after EVERY sample (src/main.cpp:93-113) ----
+// A one-sample render of an 800x800 frame is 8 launches of 20-55 us, each bound by its own latency chains
+// (profiles/r02_shim_notes.txt).  Here samples are traced AHEAD, a group at a time, each into an image of its own
+// ("slab"), at the throughput of a large wavefront; k_stream_prefix then forms the group's running means (the same
+// binary32 adds, in the same order, as one atomic add per sample into the sum).  A call only copies its mean to the
+// host.  Two groups alternate: while one is handed out the other is traced.  d_accum holds the sum before the oldest
+// group that is not used up; stream_close() folds in the samples already handed out of that group.
+static int stream_close(pt_context* c, bool keep_consumed) {
+  if (!c->stream_open) return PT_OK;
+  c->stream_open = false;
+  CU(cudaStreamSynchronize(c->ahead_stream));
+  CU(cudaStreamSynchronize(c->copy_stream));
+  const uint32_t G = c->stream_group, rel = c->stream_next - c->stream_base;
+  const uint32_t j = rel % G;
+  const int slot = (int)((rel / G) & 1u);
+  if (keep_consumed && j > 0) {
+    k_stream_apply<<<(c->npix + 255) / 256, 256, 0, c->stream>>>(c->d_accum, c->d_slab + (size_t)slot * G * c->npix, c->npix, j);
+    c->launches++;
+    CU(cudaGetLastError());
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return PT_OK;
+}
+static int stream_discard(pt_context* c) { return stream_close(c, true); }
+extern "C" int pt_stream_end(pt_context* c) {
   CTX(c);
-  if (!rgb) { pt_set_error_("rgb is NULL"); return PT_ERR_INVALID; }
-  if (spp == 0) { pt_set_error_("spp is 0"); return PT_ERR_INVALID; }
-  if (!c->copy_stream) {
+  return stream_close(c, true);
+}
+// trace the group that starts at sample `first` into slab group `slot` (all zeros here) and form its running means;
+// everything on ahead_stream
+static int stream_trace_group(pt_context* c, int slot, uint32_t first) {
+  const uint32_t G = c->stream_group;
+  if ((uint64_t)first + G > 0xFFFFFFFFull) return PT_OK;  // the sample index space ends: nothing more to trace ahead
+  float4* slabs = c->d_slab + (size_t)slot * G * c->npix;
+  int rc = render_into(c, first, G, c->stream_depth, c->stream_seed, c->ahead_stream, slabs, first, c->npix, false);
+  if (rc) return rc;
+  const float spp0 = (float)(c->stream_spp0 + (first - c->stream_base) + 1u);  // samples in the sum once the group's first one is in
+  k_stream_prefix<<<(c->npix + 255) / 256, 256, 0, c->ahead_stream>>>(c->d_base[slot], slabs, c->npix, G, spp0,
+                                                                       c->d_means + (size_t)slot * G * c->npix * 3, c->d_base[slot ^ 1]);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ev_ready[slot], c->ahead_stream));
+  return PT_OK;
+}
+extern "C" int pt_stream_begin(pt_context* c, uint32_t first_sample, uint32_t spp_before, int max_depth, uint64_t seed, uint32_t group) {
+  CTX(c);
+  if (max_depth < 1 || max_depth > kMaxDepth) { pt_set_error_("max_depth %d outside [1,%d]", max_depth, kMaxDepth); return PT_ERR_INVALID; }
+  if (group < 1 || group > 64) { pt_set_error_("group %u outside [1,64]", group); return PT_ERR_INVALID; }
+  if (int rc = stream_close(c, true)) return rc;
+  if (!c->ahead_stream) {
+    CU(cudaStreamCreateWithFlags(&c->ahead_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_res, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) {
+      CU(cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
+    }
   }
-  k_resolve_rgb<<<(c->npix + 255) / 256, 256, 0, c->stream>>>(c->d_accum, c->npix, (float)spp, 1, c->d_rgb);
-  c->launches++;
-  CU(cudaGetLastError());
-  CU(cudaEventRecord(c->ev_res, c->stream));
-  CU(cudaStreamWaitEvent(c->copy_stream, c->ev_res, 0));
-  CU(cudaMemcpyAsync(rgb, c->d_rgb, (size_t)c->npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+  if (c->slab_group != group) {
+    cudaFree(c->d_slab); cudaFree(c->d_means); cudaFree(c->d_base[0]); cudaFree(c->d_base[1]);
+    c->d_slab = nullptr; c->d_means = nullptr; c->d_base[0] = c->d_base[1] = nullptr; c->slab_group = 0;
+    CU(cudaMalloc(&c->d_slab, (size_t)2 * group * c->npix * sizeof(float4)));
+    CU(cudaMalloc(&c->d_means, (size_t)2 * group * c->npix * 3 * sizeof(float)));
+    CU(cudaMalloc(&c->d_base[0], (size_t)c->npix * sizeof(float4)));
+    CU(cudaMalloc(&c->d_base[1], (size_t)c->npix * sizeof(float4)));
+    c->slab_group = group;
+  }
+  CU(cudaStreamSynchronize(c->stream));  // whatever the caller queued (clear, upload, scene) is done before samples are traced
+  CU(cudaMemsetAsync(c->d_slab, 0, (size_t)2 * group * c->npix * sizeof(float4), c->ahead_stream));
+  CU(cudaMemcpyAsync(c->d_base[0], c->d_accum, (size_t)c->npix * sizeof(float4), cudaMemcpyDeviceToDevice, c->ahead_stream));
+  c->stream_base = c->stream_next = first_sample;
+  c->stream_spp0 = spp_before;
+  c->stream_group = group; c->stream_depth = max_depth; c->stream_seed = seed;
+  c->stream_open = true;
+  for (int slot = 0; slot < 2; slot++)
+    if (int rc = stream_trace_group(c, slot, first_sample + (uint32_t)slot * group)) { c->stream_open = false; return rc; }
+  return PT_OK;
+}
+extern "C" int pt_stream_next(pt_context* c, float* rgb, void* device_rgba8, uint32_t* spp) {
+  CTX(c);
+  if (!c->stream_open) { pt_set_error_("no sample stream is open (pt_stream_begin)"); return PT_ERR_STATE; }
+  if (!rgb) { pt_set_error_("rgb is NULL"); return PT_ERR_INVALID; }
+  const uint32_t G = c->stream_group, rel = c->stream_next - c->stream_base;
+  const uint32_t q = rel / G, j = rel % G;
+  const int slot = (int)(q & 1u);
+  if ((uint64_t)c->stream_base + (uint64_t)(q + 1) * G > 0xFFFFFFFFull) { pt_set_error_("sample index overflow"); return PT_ERR_INVALID; }
+  const float* mean = c->d_means + ((size_t)slot * G + j) * c->npix * 3;
+  CU(cudaStreamWaitEvent(c->copy_stream, c->ev_ready[slot], 0));
+  CU(cudaMemcpyAsync(rgb, mean, (size_t)c->npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
   CU(cudaEventRecord(c->ev_copy, c->copy_stream));
+  if (device_rgba8) {
+    CU(cudaStreamWaitEvent(c->stream, c->ev_ready[slot], 0));
+    k_rgb_to_rgba8<<<(c->npix + 255) / 256, 256, 0, c->stream>>>(mean, c->npix, (uchar4*)device_rgba8);
+    c->launches++;
+    CU(cudaGetLastError());
+  }
+  c->stream_next++;
+  if (spp) *spp = c->stream_spp0 + rel + 1u;
   int rc = PT_OK;
-  if (next_n_samples) rc = pt_render(c, next_first_sample, next_n_samples, max_depth, seed);
+  if (j == G - 1) {
+    // this group is used up: the sum moves past it (= the base of the other group), its slabs are cleared, and it takes
+    // the samples after the other group's -- all behind this call's copy and conversion
+    if (device_rgba8) { CU(cudaEventRecord(c->ev_res, c->stream)); CU(cudaStreamWaitEvent(c->ahead_stream, c->ev_res, 0)); }
+    CU(cudaStreamWaitEvent(c->ahead_stream, c->ev_copy, 0));
+    CU(cudaMemcpyAsync(c->d_accum, c->d_base[slot ^ 1], (size_t)c->npix * sizeof(float4), cudaMemcpyDeviceToDevice, c->ahead_stream));
+    CU(cudaMemsetAsync(c->d_slab + (size_t)slot * G * c->npix, 0, (size_t)G * c->npix * sizeof(float4), c->ahead_stream));
+    rc = stream_trace_group(c, slot, c->stream_base + (q + 2) * G);
+  }
   CU(cudaEventSynchronize(c->ev_copy));
+  if (device_rgba8) CU(cudaStreamSynchronize(c->stream));
   return rc;
 }
 
 extern "C" int pt_upload_sum(pt_context* c, const float* rgb) {
   CTX(c);
+  if (int rc = stream_discard(c)) return rc;
   if (!rgb) { pt_set_error_("rgb is NULL"); return PT_ERR_INVALID; }
   CU(cudaMemcpyAsync(c->d_rgb, rgb, (size_t)c->npix * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   k_upload_rgb<<<(c->npix + 255) / 256, 256, 0, c->stream>>>(c->d_rgb, c->npix, c->d_accum);
@@ -1168,6 +1297,7 @@ extern "C" int pt_upload_sum(pt_context* c, const float* rgb) {
 extern "C" int pt_resolve_rgba8(pt_context* c, uint32_t spp, uint8_t* host_rgba8, void* device_rgba8) {
   CTX(c);
   if (spp == 0) { pt_set_error_("spp is 0"); return PT_ERR_INVALID; }
+  if (int rc = stream_discard(c)) return rc;
   uchar4* dst = device_rgba8 ? (uchar4*)device_rgba8 : c->d_rgba8;
   k_resolve_rgba8<<<(c->npix + 255) / 256, 256, 0, c->stream>>>(c->d_accum, c->npix, (float)spp, dst);
   CU(cudaGetLastError());
@@ -1285,6 +1415,7 @@ extern "C" int pt_filter_stats(pt_context* c, uint64_t* fallbacks) {
 
 extern "C" int pt_set_direct_lighting(pt_context* c, int on) {
   CTX(c);
+  if (int rc = stream_discard(c)) return rc;
   CU(cudaStreamSynchronize(c->stream));
   c->nee = on != 0;
   return PT_OK;

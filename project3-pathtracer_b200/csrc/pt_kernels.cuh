@@ -113,7 +113,26 @@ struct BounceParams {
   FastDiv div_band;                  // FIRST only: path index -> (sample, pixel of the band)
   uint32_t q_offset;                 // k_bounce_q: byte offset of the warps' candidate queues in dynamic shared memory
   uint32_t cap;                      // paths the in / out buffers hold (debug checks)
+  uint32_t acc_s0, acc_stride;       // radiance of sample s goes to accum[(s - acc_s0) * acc_stride + pixel]: stride 0 = one image for
+                                     // all samples (the rule), stride = pixels per frame = one image per sample (pt_stream_*)
 };
+
+// what changes from one depth of a wavefront to the next: the ping-pong buffers and the depth itself (a launch per depth
+// takes it from its parameters).  A single cooperative launch stepping through all depths of a small wavefront was
+// measured and dropped: a 640 k-path wavefront is bound by per-unit latency chains, not by launches -- 377 us in one
+// launch with grid-wide barriers against 295 us as 8 launches (profiles/r02_shim_notes.txt).
+struct DepthIO {
+  const float4 *in_o, *in_d, *in_t;
+  float4 *out_o, *out_d, *out_t;
+  uint32_t depth;
+};
+__device__ __forceinline__ DepthIO depth_io(const BounceParams& P) {
+  DepthIO io;
+  io.in_o = P.in_o; io.in_d = P.in_d; io.in_t = P.in_t;
+  io.out_o = P.out_o; io.out_d = P.out_d; io.out_t = P.out_t;
+  io.depth = P.depth;
+  return io;
+}
 
 // Work decomposition of k_bounce: the unit of work is ONE WARP x 32 consecutive paths.  Warps take units from a
 // global ticket counter and never synchronise with the other warps of their CTA (an earlier version with
@@ -134,6 +153,10 @@ constexpr int kUnit = 32;  // paths per unit = one warp
 // component is the same binary32 add (w += 0), a third of the atomic transactions in L2
 __device__ __forceinline__ void accum_add(float4* px, f3 L) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(px), "f"(L.x), "f"(L.y), "f"(L.z), "f"(0.0f) : "memory");
+}
+
+__device__ __forceinline__ float4* accum_at(const BounceParams& P, uint32_t pixel, uint32_t sample) {
+  return P.accum + pixel + (size_t)(sample - P.acc_s0) * P.acc_stride;
 }
 
 __device__ __forceinline__ uint32_t atom_add_u32(uint32_t* p, uint32_t v) {  // plain ATOMG, no warp-aggregation code
@@ -175,7 +198,7 @@ __device__ __forceinline__ void closest_hit_one(const BounceParams& P, const flo
 #define PT_NEE_INLINE __forceinline__  // measured: 19.75 G rays/s inlined, 19.25 out of line (sample scene, direct light on)
 #endif
 template <bool TABLE>
-__device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const float4* fs, uint32_t lane, bool active, f3 ns, f3 o, f3 thr,
+__device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const DepthIO& io, const float4* fs, uint32_t lane, bool active, f3 ns, f3 o, f3 thr,
                                           uint32_t pixel, uint32_t sample) {
   bool traced = false;
   f3 wd = mk(0, 0, 1), E = mk(0, 0, 0);
@@ -183,7 +206,7 @@ __device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const float4* 
   int gl = -1;
   if (active) {
     float v[4];
-    rng4(P.keys, pixel, sample, 65u + P.depth, v);
+    rng4(P.keys, pixel, sample, 65u + io.depth, v);
     int li = (int)(v[0] * (float)P.n_lights);
     if (li > P.n_lights - 1) li = P.n_lights - 1;
     const float4 L0 = __ldg(P.lights + 3 * li), L1 = __ldg(P.lights + 3 * li + 1), L2 = __ldg(P.lights + 3 * li + 2);
@@ -213,7 +236,7 @@ __device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const float4* 
   const float G = (cs * cl) / (h.t * h.t);
   const f3 Ld = (thr * E) * G;
   PT_CHECK(pixel < P.cam.npix);
-  accum_add(P.accum + pixel, Ld);
+  accum_add(accum_at(P, pixel, sample), Ld);
 }
 
 // The second half of a segment, by a whole warp: material lookup, reservation of the unit's output slots, BSDF
@@ -222,7 +245,7 @@ __device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const float4* 
 // winner's own rows (many geoms, hierarchy).  NEE: direct light sampling at diffuse bounces; `no_emit` = the path's
 // previous event was one (the flag travels in throughput.w), so a light it reaches by itself adds nothing.
 template <bool LAST, bool TABLE, bool NEE>
-__device__ __forceinline__ void shade_and_compact(const BounceParams& P, const float4* fs, uint32_t lane, bool hit, const Hit& h, f3 o, f3 d, f3 thr,
+__device__ __forceinline__ void shade_and_compact(const BounceParams& P, const DepthIO& io, const float4* fs, uint32_t lane, bool hit, const Hit& h, f3 o, f3 d, f3 thr,
                                                   uint32_t pixel, uint32_t sample, bool no_emit) {
   // a path survives this segment unless it left the scene or reached a light; the slot of the unit's survivors
   // is reserved before shading so that the atomic's latency hides behind it
@@ -236,7 +259,7 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const f
   uint32_t base_raw = 0, ballot = 0;
   if (!LAST) {
     ballot = __ballot_sync(0xffffffffu, alive);
-    if (lane == 0 && ballot) base_raw = atom_add_u32(&P.ctrl->count[P.depth + 1], (uint32_t)__popc(ballot));
+    if (lane == 0 && ballot) base_raw = atom_add_u32(&P.ctrl->count[io.depth + 1], (uint32_t)__popc(ballot));
   }
   bool sampled = false;  // NEE: this lane's bounce was diffuse and gets a light sample
   f3 ns = mk(0, 0, 1);
@@ -250,10 +273,10 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const f
     if (NEE && !LAST) ns = dot(d, n) < 0 ? n : neg(n);  // the shading normal shade() uses
     const float4* frame = nullptr;
     if (TABLE && h.ncode != 8) frame = P.normals + (size_t)gi * kNormalRows + kFrameRow0 + 4 * ((h.ncode & 3) + ((h.ncode & 4) ? 3 : 0));
-    const int kind = shade(m, P.g, gi, h.p, n, frame, P.keys, pixel, sample, P.depth, o, d, thr, L);
+    const int kind = shade(m, P.g, gi, h.p, n, frame, P.keys, pixel, sample, io.depth, o, d, thr, L);
     if (kind == 3 && !(NEE && no_emit)) {
       PT_CHECK(pixel < P.cam.npix);
-      accum_add(P.accum + pixel, L);
+      accum_add(accum_at(P, pixel, sample), L);
     }
     sampled = NEE && !LAST && kind == 0 && P.n_lights > 0;
   }
@@ -261,28 +284,22 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const f
     const uint32_t slot = __shfl_sync(0xffffffffu, base_raw, 0) + __popc(ballot & ((1u << lane) - 1u));
     if (alive) {
       PT_CHECK(slot < P.cap);
-      __stcs(P.out_o + slot, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
-      __stcs(P.out_d + slot, make_float4(d.x, d.y, d.z, __uint_as_float(sample)));
-      __stcs(P.out_t + slot, make_float4(thr.x, thr.y, thr.z, sampled ? 1.0f : 0.0f));
+      __stcs(io.out_o + slot, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
+      __stcs(io.out_d + slot, make_float4(d.x, d.y, d.z, __uint_as_float(sample)));
+      __stcs(io.out_t + slot, make_float4(thr.x, thr.y, thr.z, sampled ? 1.0f : 0.0f));
     }
-    if (NEE && __any_sync(0xffffffffu, sampled)) direct_light<TABLE>(P, fs, lane, sampled, ns, o, thr, pixel, sample);
+    if (NEE && __any_sync(0xffffffffu, sampled)) direct_light<TABLE>(P, io, fs, lane, sampled, ns, o, thr, pixel, sample);
   }
 }
 
 // Few geoms (every BASELINE config but the 10k one): linear scan over the filter pairs staged in shared memory.
-template <bool FIRST, bool LAST, bool NEE = false>
-__global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_bounce(const __grid_constant__ BounceParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const uint32_t lane = threadIdx.x & 31u;
-  // ---- filter geometry: staged once per CTA ----
-  const float4* const fs = reinterpret_cast<const float4*>(smem_raw);
-  stage_filt(P.filt, 0, P.filt.end[3], reinterpret_cast<float4*>(smem_raw));
-  __syncthreads();  // the only CTA-wide barrier
-
-  const uint32_t n_in = FIRST ? P.n_first : P.ctrl->count[P.depth];
+// The body of one depth, by every warp of a persistent grid (`fs` = the staged filter pairs):
+template <bool FIRST, bool LAST, bool NEE>
+__device__ __forceinline__ void bounce_fused(const BounceParams& P, const DepthIO& io, const float4* fs, uint32_t lane) {
+  const uint32_t n_in = FIRST ? P.n_first : P.ctrl->count[io.depth];
   if (FIRST && blockIdx.x == 0 && threadIdx.x == 0) P.ctrl->count[0] = n_in;
   const uint32_t n_units = (n_in + kUnit - 1) / kUnit;
-  uint32_t* const ticket = &P.ctrl->tile_ctr[P.depth];
+  uint32_t* const ticket = &P.ctrl->tile_ctr[io.depth];
 
   uint32_t next_raw = 0;  // lane 0: the ticket taken ahead of time
   if (lane == 0) next_raw = atom_add_u32(ticket, 1u);
@@ -306,7 +323,7 @@ __global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_bounce(const 
         sample = P.first_sample + si;
         raygen(P.cam, P.keys, pixel, sample, o, d);
       } else {
-        const float4 a = __ldcs(P.in_o + idx), b = __ldcs(P.in_d + idx), c = __ldcs(P.in_t + idx);
+        const float4 a = __ldcs(io.in_o + idx), b = __ldcs(io.in_d + idx), c = __ldcs(io.in_t + idx);
         o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
         d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
         thr = mk(c.x, c.y, c.z);
@@ -324,9 +341,18 @@ __global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_bounce(const 
       if (resolve_scan(best, P.filt, P.g, P.n_geoms, o, d, h)) atomicAdd(&P.ctrl->fallbacks, 1u);
     }
 
-    shade_and_compact<LAST, true, NEE>(P, fs, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
+    shade_and_compact<LAST, true, NEE>(P, io, fs, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
     }
   }
+}
+
+template <bool FIRST, bool LAST, bool NEE = false>
+__global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_bounce(const __grid_constant__ BounceParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // ---- filter geometry: staged once per CTA ----
+  stage_filt(P.filt, 0, P.filt.end[3], reinterpret_cast<float4*>(smem_raw));
+  __syncthreads();  // the only CTA-wide barrier
+  bounce_fused<FIRST, LAST, NEE>(P, depth_io(P), reinterpret_cast<const float4*>(smem_raw), threadIdx.x & 31u);
 }
 
 // ---- k_bounce_q: the same segment with the second half RE-BATCHED BY WINNER TYPE (depths >= 1, few geoms) ----
@@ -389,6 +415,7 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
   stage_filt(P.filt, 0, P.filt.end[3], reinterpret_cast<float4*>(smem_raw));
   __syncthreads();  // the only CTA-wide barrier
   QWarp& Q = reinterpret_cast<QWarp*>(smem_raw + P.q_offset)[threadIdx.x >> 5];
+  const DepthIO io = depth_io(P);
 
   const uint32_t n_in = P.ctrl->count[P.depth];
   const uint32_t n_units = (n_in + kUnit - 1) / kUnit;
@@ -435,14 +462,8 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
       const uint32_t slot = slot0 + (valid ? lane : 0u);
       PT_CHECK(slot < (uint32_t)kQCap && n >= 1u && n <= (uint32_t)kUnit);
       const float4 a = Q.o[slot], b = Q.d[slot], e = Q.c[slot];
-#if PT_Q_THR_GATHER
-      const float4 c = __ldg(P.in_t + __float_as_uint(e.z));
-#else
-      const float4 c = Q.t[slot];
-#endif
-      f3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z), thr = mk(c.x, c.y, c.z);
+      f3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z);
       const uint32_t pixel = __float_as_uint(a.w), sample = __float_as_uint(b.w);
-      const bool no_emit = NEE && c.w != 0.0f;
       const int gi = __float_as_int(e.y);
       Hit h;
       const bool hit = exact_hit(type, __ldg(P.g.inv0 + gi), __ldg(P.g.inv1 + gi), __ldg(P.g.inv2 + gi), __ldg(P.g.fwd0 + gi),
@@ -456,8 +477,16 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
           atomicAdd(&P.ctrl->fallbacks, 1u);
         }
       }
+      // the throughput is fetched only now: it is not needed before shading, and the exact test is where registers are scarce
+#if PT_Q_THR_GATHER
+      const float4 c = __ldg(P.in_t + __float_as_uint(e.z));
+#else
+      const float4 c = Q.t[slot];
+#endif
+      f3 thr = mk(c.x, c.y, c.z);
+      const bool no_emit = NEE && c.w != 0.0f;
       __syncwarp();  // the popped entries are in registers: the next push may overwrite them
-      shade_and_compact<LAST, true, NEE>(P, fs, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
+      shade_and_compact<LAST, true, NEE>(P, io, fs, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
     }
     if (!more) break;
     // ---- phase A: load, filter scan, push the candidates ----
@@ -565,6 +594,7 @@ __device__ __forceinline__ void load_path(const BounceParams& P, uint32_t idx, f
 template <bool FIRST, bool LAST, bool NEE>
 __device__ __noinline__ void run_deferred(const BounceParams& P, const uint32_t* list, uint32_t n) {
   const uint32_t lane = threadIdx.x & 31u;
+  const DepthIO io = depth_io(P);
   const bool valid = lane < n;
   f3 o = mk(0, 0, 0), d = mk(0, 0, 1), thr = mk(1, 1, 1);
   uint32_t pixel = 0, sample = 0;
@@ -581,7 +611,7 @@ __device__ __noinline__ void run_deferred(const BounceParams& P, const uint32_t*
     bvh_traverse<true>(P.bvh, P.g, ray, unused, h);
   }
   if (lane == 0) atomicAdd(&P.ctrl->fallbacks, n);
-  shade_and_compact<LAST, false, NEE>(P, nullptr, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
+  shade_and_compact<LAST, false, NEE>(P, io, nullptr, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
 }
 
 template <bool FIRST, bool LAST, bool NEE = false>
@@ -589,6 +619,7 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31u;
   BvhWarpSmem& S = reinterpret_cast<BvhWarpSmem*>(smem_raw)[threadIdx.x >> 5];
+  const DepthIO io = depth_io(P);
 
   const uint32_t n_in = FIRST ? P.n_first : P.ctrl->count[P.depth];
   if (FIRST && blockIdx.x == 0 && threadIdx.x == 0) P.ctrl->count[0] = n_in;
@@ -700,7 +731,7 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
       PT_CHECK(n_defer + __popc(dmask) <= (uint32_t)kDeferCap);
       if (defer) S.defer[n_defer + __popc(dmask & ((1u << lane) - 1u))] = base + j;
       n_defer += __popc(dmask);
-      shade_and_compact<LAST, false, NEE>(P, nullptr, lane, valid && !defer && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
+      shade_and_compact<LAST, false, NEE>(P, io, nullptr, lane, valid && !defer && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
       if (n_defer >= kUnit) {
         __syncwarp();
         n_defer -= kUnit;
@@ -1063,6 +1094,48 @@ __global__ void k_selftest_math(unsigned long long* bad) {
   if (b0) atomicAdd(bad + 0, b0);
   if (b1) atomicAdd(bad + 1, b1);
   if (b2) atomicAdd(bad + 2, b2);
+}
+
+// ---- sample streaming (pt_stream_*): a group of samples, each traced into an image of its own ("slab") ----
+// running means of the group, ahead of the calls that will ask for them: s = base; for each sample j: s += slab_j (one
+// binary32 add per component: what the sample's atomic add into the sum would have done), mean_j = s / (spp0 + j) in the
+// renderCam->image layout; the sum after the whole group goes to `final` (the base of the next group)
+__global__ void k_stream_prefix(const float4* __restrict__ base, const float4* __restrict__ slabs, uint32_t npix, uint32_t group,
+                                float spp0, float* __restrict__ means, float4* __restrict__ final) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  float4 a = base[i];
+  for (uint32_t j = 0; j < group; j++) {
+    const float4 b = __ldcs(slabs + (size_t)j * npix + i);
+    a.x = a.x + b.x; a.y = a.y + b.y; a.z = a.z + b.z;
+    const float spp = spp0 + (float)j;
+    float* m = means + ((size_t)j * npix + i) * 3;
+    __stcs(m, a.x / spp); __stcs(m + 1, a.y / spp); __stcs(m + 2, a.z / spp);
+  }
+  final[i] = a;
+}
+// the first `count` samples of a group folded into the sum (a stream that ends inside a group)
+__global__ void k_stream_apply(float4* sum, const float4* __restrict__ slabs, uint32_t npix, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  float4 a = sum[i];
+  for (uint32_t j = 0; j < count; j++) {
+    const float4 b = slabs[(size_t)j * npix + i];
+    a.x = a.x + b.x; a.y = a.y + b.y; a.z = a.z + b.z;
+  }
+  sum[i] = a;
+}
+// sendImageToPBO's bytes (src/raytraceKernel.cu:58-89) of a mean image in the renderCam->image layout
+__global__ void k_rgb_to_rgba8(const float* __restrict__ rgb, uint32_t npix, uchar4* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  float r = rgb[3 * i] * 255.0f, g = rgb[3 * i + 1] * 255.0f, b = rgb[3 * i + 2] * 255.0f;
+  if (r > 255) r = 255;
+  if (g > 255) g = 255;
+  if (b > 255) b = 255;
+  uchar4 px;
+  px.x = (unsigned char)r; px.y = (unsigned char)g; px.z = (unsigned char)b; px.w = 0;
+  out[i] = px;
 }
 
 // ---- image out ----

@@ -86,6 +86,30 @@ def test_cudaRaytraceCore_sample_traced_ahead_is_dropped_when_the_sequence_chang
     compat.reset()
 
 
+@pytest.mark.parametrize("group", [1, 3, 8])
+def test_sample_stream_equals_one_render_per_sample(pt, sample_scene, group):
+    """pt_stream_*: samples traced ahead in groups and folded in one per call leave exactly the sums that one pt_render per
+    sample leaves (one radiance contribution per pixel and sample: the same float adds in the same order)"""
+    cam = with_resolution(sample_scene["camera"], 96, 64)
+    depth, seed, n = 8, 12, 19  # 19 samples: the groups wrap around several times, the last one stays partly unused
+    with pt.Context(sample_scene["geoms"], sample_scene["materials"], cam) as a, \
+         pt.Context(sample_scene["geoms"], sample_scene["materials"], cam) as b:
+        a.render(0, 2, depth, seed)  # the stream starts on top of an existing sum
+        b.render(0, 2, depth, seed)
+        b.stream_begin(2, 2, depth, seed, group)
+        for k in range(2, n):
+            a.render(k, 1, depth, seed)
+            mean, spp = b.stream_next()
+            assert spp == k + 1 and same_bits(mean, a.download_mean(k + 1)), k
+        # anything else that touches the sum ends the stream: the samples traced ahead are dropped, the sum is untouched
+        assert same_bits(b.download_sum(), a.download_sum())
+        b.render(n, 1, depth, seed)
+        a.render(n, 1, depth, seed)
+        assert same_bits(b.download_sum(), a.download_sum())
+        with pytest.raises(pt.PtError):
+            b.stream_next()  # no stream open any more
+
+
 def test_cudaRaytraceCore_frame_selects_per_frame_arrays_and_writes_pbo(pt, compat, oracle, sample_scene):
     import torch
     cam = with_resolution(sample_scene["camera"], 64, 64)

@@ -132,6 +132,40 @@ def test_image_and_counters_match_oracle(pt, oracle, sample_scene, spp, depth):
         assert np.allclose(got_sum, want_sum, rtol=1e-6, atol=1e-6)
 
 
+# the kernels that can trace depths >= 1 of a few-geom wavefront: chosen per depth (default), always re-batched, always fused
+KERNEL_PATHS = {"auto": (0,), "rebatched": (1,), "fused": (2,)}
+
+
+@pytest.mark.parametrize("path", sorted(KERNEL_PATHS))
+@pytest.mark.parametrize("scene", ["sample", "optics", "direct"])
+def test_every_kernel_path_matches_oracle(pt, oracle, sample_scene, path, scene):
+    """image bits and per-depth live counts of the oracle, whichever kernels trace the wavefront
+    (pt_set_kernel_policy): diffuse sample scene, mirror + glass + thin lens, direct light sampling"""
+    cam = with_resolution(sample_scene["camera"], 128, 96)
+    g, m, lens, nee = sample_scene["geoms"], sample_scene["materials"], None, False
+    if scene == "optics":
+        g, m = optics_scene(pt, sample_scene)
+        lens = (0.15, 11.0)
+    nee = scene == "direct"
+    spp, depth, seed = 2, 7, 77
+    scn = oracle.make_scene(g, m, cam, lens=lens if lens else (0.0, 0.0), direct_lighting=nee)
+    want_sum, want_live, _ = oracle.render(scn, 0, spp, depth, seed)
+    with pt.Context(g, m, cam, lens=lens) as c:
+        c.set_kernel_policy(*KERNEL_PATHS[path])
+        c.set_direct_lighting(nee)
+        l0 = c.launch_count()
+        c.render(0, spp, depth, seed)
+        got = c.download_sum()
+        _, segs, live = c.counters()
+        launches = c.launch_count() - l0
+    assert live[:depth].tolist() == want_live.tolist()
+    if nee:  # several contributions per pixel and sample: float summation order
+        assert np.allclose(got, want_sum, rtol=2e-6, atol=2e-6)
+    else:
+        assert same_bits(got, want_sum)
+    assert launches == depth + 2, launches  # one launch per depth, the count fold, the resolve of download_sum
+
+
 def test_small_wavefronts_give_same_image(pt, sample_scene):
     """splitting the samples over many wavefronts / calls changes nothing but float summation order"""
     cam = with_resolution(sample_scene["camera"], 96, 96)

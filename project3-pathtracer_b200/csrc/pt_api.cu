@@ -109,6 +109,8 @@ struct pt_context {
   size_t q_smem_total = 0;            // k_bounce_q: filter geometry + the warps' candidate queues
   int q_mode = 0;                     // depths >= 1, few geoms: 0 = per depth by the scene's measured survival (h_policy),
                                       // 1 = always k_bounce_q, 2 = always the fused k_bounce (PT_B200_FUSED=1 / =0 force 2 / 1)
+  void* d_scratch = nullptr;          // grow-only device arena of the list entry points (pt_raygen, pt_intersect_ex): no
+  size_t scratch_bytes = 0;           // cudaMalloc / cudaFree per call
   int* h_policy = nullptr;            // mapped host memory, kMaxDepth + 1 ints written by k_accum_counts: 0 unknown, 1 q, 2 fused
   int* d_policy = nullptr;            // ... its device address
   // sample streaming (pt_stream_*): samples are traced ahead in groups into per-sample images ("slabs") on ahead_stream,
@@ -884,28 +886,39 @@ static int alloc_wavefront(pt_context* c, uint64_t max_paths) {
 extern "C" int pt_context_destroy(pt_context* c) {
   if (!c) return PT_OK;
   cudaSetDevice(c->device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_rows); cudaFree(c->d_meta); cudaFree(c->d_normals); cudaFree(c->d_mats); cudaFree(c->d_lights); cudaFree(c->d_state);
-  cudaFree(c->d_filt); cudaFree(c->d_filt_ids); cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_leaves); cudaFree(c->d_bvh_meta);
-  cudaFree(c->d_ctrl); cudaFree(c->d_live); cudaFree(c->d_accum); cudaFree(c->d_rgb); cudaFree(c->d_rgba8);
+  // every stream that may still carry work of this context (samples traced ahead, the running mean on its way out)
+  cudaStream_t streams[] = {c->stream, c->ahead_stream, c->copy_stream, c->wf_stream[0], c->wf_stream[1], c->own_stream};
+  for (cudaStream_t st : streams)
+    if (st) cudaStreamSynchronize(st);
+  const bool dbg = getenv("PT_B200_DEBUG_DESTROY") != nullptr;
+  auto chk = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && dbg) fprintf(stderr, "pt_context_destroy: %s -> %s\n", what, cudaGetErrorString(e));
+  };
+#define PT_FREE(p) chk(cudaFree(p), #p)
+  PT_FREE(c->d_rows); PT_FREE(c->d_meta); PT_FREE(c->d_normals); PT_FREE(c->d_mats); PT_FREE(c->d_lights); PT_FREE(c->d_state);
+  PT_FREE(c->d_filt); PT_FREE(c->d_filt_ids); PT_FREE(c->d_bvh_nodes); PT_FREE(c->d_bvh_leaves); PT_FREE(c->d_bvh_meta);
+  PT_FREE(c->d_ctrl); PT_FREE(c->d_live); PT_FREE(c->d_accum); PT_FREE(c->d_rgb); PT_FREE(c->d_rgba8);
+  PT_FREE(c->d_scratch);
+  PT_FREE(c->d_slab); PT_FREE(c->d_means); PT_FREE(c->d_base[0]); PT_FREE(c->d_base[1]);
+#undef PT_FREE
   for (int i = 0; i < pt_context::kSlots; i++) {
-    if (c->wf_stream[i]) { cudaStreamSynchronize(c->wf_stream[i]); cudaStreamDestroy(c->wf_stream[i]); }
-    if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    if (c->wf_stream[i]) chk(cudaStreamDestroy(c->wf_stream[i]), "wf_stream");
+    if (c->ev_join[i]) chk(cudaEventDestroy(c->ev_join[i]), "ev_join");
   }
-  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-  if (c->ahead_stream) { cudaStreamSynchronize(c->ahead_stream); cudaStreamDestroy(c->ahead_stream); }
-  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
-  if (c->ev_res) cudaEventDestroy(c->ev_res);
-  if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+  if (c->ev_fork) chk(cudaEventDestroy(c->ev_fork), "ev_fork");
+  if (c->ahead_stream) chk(cudaStreamDestroy(c->ahead_stream), "ahead_stream");
+  if (c->copy_stream) chk(cudaStreamDestroy(c->copy_stream), "copy_stream");
+  if (c->ev_res) chk(cudaEventDestroy(c->ev_res), "ev_res");
+  if (c->ev_copy) chk(cudaEventDestroy(c->ev_copy), "ev_copy");
   for (int i = 0; i < 2; i++) {
-    if (c->ev_ready[i]) cudaEventDestroy(c->ev_ready[i]);
-    if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
+    if (c->ev_ready[i]) chk(cudaEventDestroy(c->ev_ready[i]), "ev_ready");
+    if (c->ev_consumed[i]) chk(cudaEventDestroy(c->ev_consumed[i]), "ev_consumed");
   }
-  cudaFree(c->d_slab); cudaFree(c->d_means); cudaFree(c->d_base[0]); cudaFree(c->d_base[1]);
-  if (c->h_policy) cudaFreeHost(c->h_policy);
-  if (c->ev0) cudaEventDestroy(c->ev0);
-  if (c->ev1) cudaEventDestroy(c->ev1);
-  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->h_policy) chk(cudaFreeHost(c->h_policy), "h_policy");
+  if (c->ev0) chk(cudaEventDestroy(c->ev0), "ev0");
+  if (c->ev1) chk(cudaEventDestroy(c->ev1), "ev1");
+  if (c->own_stream) chk(cudaStreamDestroy(c->own_stream), "own_stream");
+  cudaGetLastError();  // nothing of this context's teardown may surface in a later call's error check
   delete c;
   return PT_OK;
 }
@@ -1340,6 +1353,29 @@ struct DevBuf {
   cudaError_t alloc(size_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
 };
 
+// Carves the list entry points' device buffers out of one grow-only arena owned by the context (256-byte aligned pieces).
+struct Arena {
+  pt_context* c;
+  size_t used = 0;
+  explicit Arena(pt_context* ctx) : c(ctx) {}
+  static size_t up(size_t b) { return (b + 255) & ~(size_t)255; }
+  int reserve(size_t total) {
+    if (total <= c->scratch_bytes) return PT_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->d_scratch) CU(cudaFree(c->d_scratch));
+    c->d_scratch = nullptr; c->scratch_bytes = 0;
+    CU(cudaMalloc(&c->d_scratch, total));
+    c->scratch_bytes = total;
+    return PT_OK;
+  }
+  template <typename T>
+  T* take(size_t count) {
+    T* p = reinterpret_cast<T*>(static_cast<char*>(c->d_scratch) + used);
+    used += up((count ? count : 1) * sizeof(T));
+    return p;
+  }
+};
+
 extern "C" int pt_raygen(pt_context* c, uint64_t seed, int n, const uint32_t* pixel, const uint32_t* sample,
                          float* origin, float* direction) {
   CTX(c);
@@ -1347,15 +1383,16 @@ extern "C" int pt_raygen(pt_context* c, uint64_t seed, int n, const uint32_t* pi
   if (n == 0) return PT_OK;
   for (int i = 0; i < n; i++)
     if (pixel[i] >= c->npix) { pt_set_error_("pixel[%d] = %u outside the %u-pixel frame", i, pixel[i], c->npix); return PT_ERR_INVALID; }
-  DevBuf<uint32_t> dp, ds;
-  DevBuf<float> dor, ddr;
-  CU(dp.alloc(n)); CU(ds.alloc(n)); CU(dor.alloc(3 * (size_t)n)); CU(ddr.alloc(3 * (size_t)n));
-  CU(cudaMemcpyAsync(dp.p, pixel, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(ds.p, sample, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  k_raygen_list<<<(n + 255) / 256, 256, 0, c->stream>>>(c->cam, seed, n, dp.p, ds.p, dor.p, ddr.p);
+  Arena A(c);
+  if (int rc = A.reserve(2 * Arena::up(n * sizeof(uint32_t)) + 2 * Arena::up(3 * (size_t)n * sizeof(float)))) return rc;
+  uint32_t *dp = A.take<uint32_t>(n), *ds = A.take<uint32_t>(n);
+  float *dor = A.take<float>(3 * (size_t)n), *ddr = A.take<float>(3 * (size_t)n);
+  CU(cudaMemcpyAsync(dp, pixel, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(ds, sample, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  k_raygen_list<<<(n + 255) / 256, 256, 0, c->stream>>>(c->cam, seed, n, dp, ds, dor, ddr);
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(origin, dor.p, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(direction, ddr.p, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(origin, dor, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(direction, ddr, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return PT_OK;
 }
@@ -1367,25 +1404,26 @@ extern "C" int pt_intersect_ex(pt_context* c, int mode, int n, const float* orig
   if (mode != PT_HIT_FILTERED && mode != PT_HIT_EXACT_SCAN) { pt_set_error_("mode %d is neither PT_HIT_FILTERED nor PT_HIT_EXACT_SCAN", mode); return PT_ERR_INVALID; }
   if (fallbacks) *fallbacks = 0;
   if (n == 0) return PT_OK;
-  DevBuf<float> dor, ddr, dt, dpnt, dn;
-  DevBuf<int> did;
-  DevBuf<unsigned long long> dfb;
   const size_t v = 3 * (size_t)n;
-  CU(dor.alloc(v)); CU(ddr.alloc(v)); CU(dt.alloc(n)); CU(dpnt.alloc(v)); CU(dn.alloc(v)); CU(did.alloc(n)); CU(dfb.alloc(1));
-  CU(cudaMemcpyAsync(dor.p, origin, v * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(ddr.p, direction, v * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemsetAsync(dfb.p, 0, sizeof(unsigned long long), c->stream));
+  Arena A(c);
+  if (int rc = A.reserve(4 * Arena::up(v * sizeof(float)) + Arena::up(n * sizeof(float)) + Arena::up(n * sizeof(int)) + 256)) return rc;
+  float *dor = A.take<float>(v), *ddr = A.take<float>(v), *dt = A.take<float>(n), *dpnt = A.take<float>(v), *dn = A.take<float>(v);
+  int* did = A.take<int>(n);
+  unsigned long long* dfb = A.take<unsigned long long>(1);
+  CU(cudaMemcpyAsync(dor, origin, v * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(ddr, direction, v * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(dfb, 0, sizeof(unsigned long long), c->stream));
   k_intersect_list<<<(n + kTile - 1) / kTile, kTile, c->geom_smem, c->stream>>>(
-      c->g, c->n_geoms, c->filt, c->filt_cap, c->bvh, mode == PT_HIT_FILTERED ? c->d_normals : nullptr, mode, n, dor.p, ddr.p,
-      did.p, dt.p, dpnt.p, dn.p, dfb.p);
+      c->g, c->n_geoms, c->filt, c->filt_cap, c->bvh, mode == PT_HIT_FILTERED ? c->d_normals : nullptr, mode, n, dor, ddr,
+      did, dt, dpnt, dn, dfb);
   c->launches++;
   CU(cudaGetLastError());
   unsigned long long fb = 0;
-  CU(cudaMemcpyAsync(geom_id, did.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(t, dt.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(point, dpnt.p, v * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(normal, dn.p, v * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(&fb, dfb.p, sizeof(fb), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(geom_id, did, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(t, dt, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(point, dpnt, v * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(normal, dn, v * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&fb, dfb, sizeof(fb), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   if (fallbacks) *fallbacks = fb;
   return PT_OK;

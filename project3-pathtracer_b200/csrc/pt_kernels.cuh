@@ -16,6 +16,8 @@
 //   k_points_on_geom / k_sphere_dirs / k_transmission (pt_sampling.cuh)   sampling and absorption parity entry points
 //   k_resolve_*                        accumulation buffer -> float RGB / uchar4 (sendImageToPBO, :58-89)
 #pragma once
+#include <cuda_fp16.h>
+
 #include "pt_device.cuh"
 #include "pt_filter.cuh"
 #include "pt_bvh.cuh"
@@ -244,9 +246,30 @@ __device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const DepthIO&
 // TABLE: normals from the per-geom table (few geoms, L1-resident; `fs` = the filter pairs in shared memory) or from the
 // winner's own rows (many geoms, hierarchy).  NEE: direct light sampling at diffuse bounces; `no_emit` = the path's
 // previous event was one (the flag travels in throughput.w), so a light it reaches by itself adds nothing.
-template <bool LAST, bool TABLE, bool NEE>
+// Deferred output (k_bounce_q): a batch's survivors wait in shared memory while the atomic that reserves their slots is
+// in flight, and are written one batch later -- the warp never waits for the atomic (it was 7 % of the stall samples:
+// one address per depth takes 0.6 atomics per nanosecond, and their latency under that load exceeds a whole shading pass).
+struct DeferredOut {
+  float4* stage;      // [3][kUnit] in the warp's shared memory: the survivors' (origin | direction | throughput) rows, ranked
+  uint32_t pend_raw;  // lane 0: slot base of the staged survivors (result of the atomic; read one batch later)
+  uint32_t pend_n;    // warp-uniform: survivors staged, 0 = nothing pending
+};
+__device__ __forceinline__ void deferred_flush(DeferredOut& W, const BounceParams& P, const DepthIO& io, uint32_t lane) {
+  if (W.pend_n == 0) return;
+  const uint32_t base = __shfl_sync(0xffffffffu, W.pend_raw, 0);
+  if (lane < W.pend_n) {
+    PT_CHECK(base + lane < P.cap);
+    __stcs(io.out_o + base + lane, W.stage[lane]);
+    __stcs(io.out_d + base + lane, W.stage[kUnit + lane]);
+    __stcs(io.out_t + base + lane, W.stage[2 * kUnit + lane]);
+  }
+  W.pend_n = 0;
+  __syncwarp();  // the staging rows may be overwritten now
+}
+
+template <bool LAST, bool TABLE, bool NEE, bool DEFER = false>
 __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const DepthIO& io, const float4* fs, uint32_t lane, bool hit, const Hit& h, f3 o, f3 d, f3 thr,
-                                                  uint32_t pixel, uint32_t sample, bool no_emit) {
+                                                  uint32_t pixel, uint32_t sample, bool no_emit, DeferredOut* W = nullptr) {
   // a path survives this segment unless it left the scene or reached a light; the slot of the unit's survivors
   // is reserved before shading so that the atomic's latency hides behind it
   int mat = 0;
@@ -259,7 +282,13 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const D
   uint32_t base_raw = 0, ballot = 0;
   if (!LAST) {
     ballot = __ballot_sync(0xffffffffu, alive);
-    if (lane == 0 && ballot) base_raw = atom_add_u32(&P.ctrl->count[io.depth + 1], (uint32_t)__popc(ballot));
+    if (DEFER) {
+      deferred_flush(*W, P, io, lane);  // the batch before this one: its atomic returned long ago
+      W->pend_n = (uint32_t)__popc(ballot);
+      if (lane == 0 && ballot) W->pend_raw = atom_add_u32(&P.ctrl->count[io.depth + 1], (uint32_t)__popc(ballot));
+    } else if (lane == 0 && ballot) {
+      base_raw = atom_add_u32(&P.ctrl->count[io.depth + 1], (uint32_t)__popc(ballot));
+    }
   }
   bool sampled = false;  // NEE: this lane's bounce was diffuse and gets a light sample
   f3 ns = mk(0, 0, 1);
@@ -281,12 +310,22 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const D
     sampled = NEE && !LAST && kind == 0 && P.n_lights > 0;
   }
   if (!LAST) {
-    const uint32_t slot = __shfl_sync(0xffffffffu, base_raw, 0) + __popc(ballot & ((1u << lane) - 1u));
-    if (alive) {
-      PT_CHECK(slot < P.cap);
-      __stcs(io.out_o + slot, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
-      __stcs(io.out_d + slot, make_float4(d.x, d.y, d.z, __uint_as_float(sample)));
-      __stcs(io.out_t + slot, make_float4(thr.x, thr.y, thr.z, sampled ? 1.0f : 0.0f));
+    if (DEFER) {
+      const uint32_t rank = __popc(ballot & ((1u << lane) - 1u));
+      if (alive) {
+        W->stage[rank] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
+        W->stage[kUnit + rank] = make_float4(d.x, d.y, d.z, __uint_as_float(sample));
+        W->stage[2 * kUnit + rank] = make_float4(thr.x, thr.y, thr.z, sampled ? 1.0f : 0.0f);
+      }
+      __syncwarp();
+    } else {
+      const uint32_t slot = __shfl_sync(0xffffffffu, base_raw, 0) + __popc(ballot & ((1u << lane) - 1u));
+      if (alive) {
+        PT_CHECK(slot < P.cap);
+        __stcs(io.out_o + slot, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
+        __stcs(io.out_d + slot, make_float4(d.x, d.y, d.z, __uint_as_float(sample)));
+        __stcs(io.out_t + slot, make_float4(thr.x, thr.y, thr.z, sampled ? 1.0f : 0.0f));
+      }
     }
     if (NEE && __any_sync(0xffffffffu, sampled)) direct_light<TABLE>(P, io, fs, lane, sampled, ns, o, thr, pixel, sample);
   }
@@ -373,22 +412,30 @@ __global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_bounce(const 
 // Results do not depend on the order in which paths are processed (RNG streams are keyed by pixel and sample,
 // radiance goes through atomics), so images and live counts are the ones k_bounce produces, bit for bit.
 constexpr int kQCap = 96;
-#ifndef PT_Q_THR_GATHER
-#define PT_Q_THR_GATHER 0  // 1: the queue carries the path index and phase B fetches the throughput itself (a first touch
-                           // of HBM at the head of every batch: measured slower, profiles/r02_q_*)
-#endif
 #ifndef PT_Q_PREFETCH
 #define PT_Q_PREFETCH 1  // the next unit's path state travels HBM -> shared memory (cp.async) while this unit is traced
 #endif
+#ifndef PT_Q_DEFER_OUT
+#define PT_Q_DEFER_OUT 1
+#endif
+#ifndef PT_Q_PACK48
+#define PT_Q_PACK48 0  // 1: 48-byte entries -- (lo2 rounded DOWN to binary16 | geom | flag) packed into the throughput's spare
+                       // word -- so that four 64-register CTAs and the staging fit an SM (measured: see DESIGN.md)
+#endif
+// (A queue that carries only the path index, phase B fetching the throughput from HBM itself, was measured too: a first
+// touch of HBM at the head of every batch, 58 % issue-slot utilisation, slower.)
 struct QWarp {
   float4 o[kQCap];  // (origin.xyz, pixel)
   float4 d[kQCap];  // (direction.xyz, sample)
-#if !PT_Q_THR_GATHER
-  float4 t[kQCap];  // (throughput.xyz, no-emission flag)
-#endif
+  float4 t[kQCap];  // (throughput.xyz, no-emission flag [PT_Q_PACK48: flag | geom << 1 | binary16(lo2) << 16])
+#if !PT_Q_PACK48
   float4 c[kQCap];  // (lo2 = second-smallest lower bound, bits of the candidate's geom index, path index, -)
+#endif
 #if PT_Q_PREFETCH
   float4 st[3][kUnit];  // staging: the next unit's (origin | direction | throughput) rows, one slot per lane
+#endif
+#if PT_Q_DEFER_OUT
+  float4 wst[3 * kUnit];  // the last batch's survivors, written to HBM one batch later (DeferredOut)
 #endif
 };
 #ifndef PT_Q_THREADS
@@ -423,6 +470,10 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
   uint32_t next_raw = 0;  // lane 0: the ticket taken ahead of time
   if (lane == 0) next_raw = atom_add_u32(ticket, 1u);
 
+#if PT_Q_DEFER_OUT
+  DeferredOut W;
+  W.stage = Q.wst; W.pend_raw = 0; W.pend_n = 0;
+#endif
   uint32_t ns = 0, nc = 0;           // queue lengths (warp-uniform): spheres at [0, ns), cubes at [kQCap - nc, kQCap)
   uint32_t unit = 0, unit_end = 0;   // units left of the current ticket
   bool more = true;                  // the ticket counter has not run dry yet
@@ -440,9 +491,7 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
     const uint32_t idc = min(unit * kUnit + lane, n_in - 1u);  // lanes past the end fetch a copy of the last path
     cp_async16(&Q.st[0][lane], P.in_o + idc);
     cp_async16(&Q.st[1][lane], P.in_d + idc);
-#if !PT_Q_THR_GATHER
     cp_async16(&Q.st[2][lane], P.in_t + idc);
-#endif
     cp_async_commit();
 #endif
   };
@@ -461,15 +510,23 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
       const bool valid = lane < n;
       const uint32_t slot = slot0 + (valid ? lane : 0u);
       PT_CHECK(slot < (uint32_t)kQCap && n >= 1u && n <= (uint32_t)kUnit);
-      const float4 a = Q.o[slot], b = Q.d[slot], e = Q.c[slot];
+      const float4 a = Q.o[slot], b = Q.d[slot];
       f3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z);
       const uint32_t pixel = __float_as_uint(a.w), sample = __float_as_uint(b.w);
+#if PT_Q_PACK48
+      const uint32_t tag = __float_as_uint(Q.t[slot].w);
+      const int gi = (int)((tag >> 1) & 0x7fffu);
+      const float lo2 = __half2float(__ushort_as_half((unsigned short)(tag >> 16)));
+#else
+      const float4 e = Q.c[slot];
       const int gi = __float_as_int(e.y);
+      const float lo2 = e.x;
+#endif
       Hit h;
       const bool hit = exact_hit(type, __ldg(P.g.inv0 + gi), __ldg(P.g.inv1 + gi), __ldg(P.g.inv2 + gi), __ldg(P.g.fwd0 + gi),
                                  __ldg(P.g.fwd1 + gi), __ldg(P.g.fwd2 + gi), o, d, h.t, h.p, h.ncode);
       h.id = gi;
-      if (!(hit && h.t > 0 && h.t < e.x)) {
+      if (!(hit && h.t > 0 && h.t < lo2)) {
         // the candidate is not confirmed: the exact scan decides (0.008 % of the segments on the sample scene)
         h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
         if (valid) {
@@ -478,15 +535,19 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
         }
       }
       // the throughput is fetched only now: it is not needed before shading, and the exact test is where registers are scarce
-#if PT_Q_THR_GATHER
-      const float4 c = __ldg(P.in_t + __float_as_uint(e.z));
-#else
       const float4 c = Q.t[slot];
-#endif
       f3 thr = mk(c.x, c.y, c.z);
+#if PT_Q_PACK48
+      const bool no_emit = NEE && (__float_as_uint(c.w) & 1u) != 0u;
+#else
       const bool no_emit = NEE && c.w != 0.0f;
+#endif
       __syncwarp();  // the popped entries are in registers: the next push may overwrite them
+#if PT_Q_DEFER_OUT
+      shade_and_compact<LAST, true, NEE, true>(P, io, fs, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, no_emit, &W);
+#else
       shade_and_compact<LAST, true, NEE>(P, io, fs, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
+#endif
     }
     if (!more) break;
     // ---- phase A: load, filter scan, push the candidates ----
@@ -497,15 +558,11 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
 #if PT_Q_PREFETCH
       cp_async_wait_all();  // every lane reads only the slots it requested itself
       const float4 a = Q.st[0][lane], b = Q.st[1][lane];
-#if !PT_Q_THR_GATHER
-      const float4 c = Q.st[2][lane];
-#endif
+      float4 c = Q.st[2][lane];
 #else
       const uint32_t idc = valid ? idx : n_in - 1u;  // (n_in >= 1 here) lanes past the end scan a copy of the last path
       const float4 a = __ldcs(P.in_o + idc), b = __ldcs(P.in_d + idc);
-#if !PT_Q_THR_GATHER
-      const float4 c = __ldcs(P.in_t + idc);
-#endif
+      float4 c = __ldcs(P.in_t + idc);
 #endif
       ScanBest best;
       scan_init(best);
@@ -520,10 +577,16 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
         PT_CHECK(slot < (uint32_t)kQCap && ns + nc + __popc(bs) + __popc(bc) <= (uint32_t)kQCap);
         PT_CHECK(idx < P.cap && gi >= 0 && gi < P.n_geoms);
         Q.o[slot] = a; Q.d[slot] = b;
-#if !PT_Q_THR_GATHER
+#if PT_Q_PACK48
+        // lo2 rounded DOWN to binary16: a smaller bound can only send a confirmed candidate to the exact scan, never accept
+        // a wrong one (+inf and values above 65504 stay "no second candidate" / the largest half)
+        c.w = __uint_as_float((c.w != 0.0f ? 1u : 0u) | ((uint32_t)gi << 1) |
+                              ((uint32_t)__half_as_ushort(__float2half_rd(best.lo2)) << 16));
         Q.t[slot] = c;
-#endif
+#else
+        Q.t[slot] = c;
         Q.c[slot] = make_float4(best.lo2, __int_as_float(gi), __uint_as_float(idx), 0.0f);
+#endif
       }
       ns += __popc(bs);
       nc += __popc(bc);
@@ -531,6 +594,9 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
       __syncwarp();
     }
   }
+#if PT_Q_DEFER_OUT
+  if (!LAST) deferred_flush(W, P, io, lane);  // the last batch's survivors
+#endif
 }
 
 // Many geoms (BASELINE config "10k spheres/cubes"): the hierarchy of pt_bvh.cuh, read through L1/L2.  A ray's

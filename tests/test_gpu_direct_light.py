@@ -19,8 +19,8 @@ def lit_scene(pt, sample_scene):
     light = int(g[8]["materialid"])
     g[8] = build_geom(pt, 1, light, (0, 8, 0), (20, 30, 40), (3, 0.5, 2))
     g[5] = build_geom(pt, 0, light, (-2, 5, 2), (0, 0, 0), (1.5, 1.5, 1.5))
-    m[4]["hasReflective"] = 1.0  # a mirror sphere: specular events clear the no-emission flag
-    m[4]["specularColor"] = [0.9, 0.9, 0.9]
+    m[3]["hasReflective"] = 1.0  # sphere 6 becomes a mirror: specular events clear the no-emission flag
+    m[3]["specularColor"] = [0.9, 0.9, 0.9]
     return g, m
 
 
@@ -93,12 +93,18 @@ def test_off_by_default_and_no_lights(pt, oracle, sample_scene):
 
 def test_same_expected_image_less_noise(pt, sample_scene):
     """the estimator is unbiased (same mean image as plain path tracing) and, with small lights that few sampled
-    directions find by chance, converges much faster"""
+    directions find by chance, converges much faster.
+
+    Noise = difference of two independent estimates of the frame.  Its RMS is dominated by a few fireflies and swings
+    between 0.4 and 0.7 of plain path tracing's from one sample count to the next (round 1 asserted < 0.6, measured 0.69
+    and loosened the bound to fit); the robust statistic is the MEAN ABSOLUTE difference: the CPU oracle gives
+    0.19 / 0.18 of plain path tracing's at 128 / 512 spp (same estimator, same RNG streams), the bar is 0.35."""
     g, m = lit_scene(pt, sample_scene)
     light = int(g[8]["materialid"])
     g[8] = build_geom(pt, 1, light, (0, 8, 0), (20, 30, 40), (0.6, 0.1, 0.4))
     g[5] = build_geom(pt, 0, light, (-2, 5, 2), (0, 0, 0), (0.3, 0.3, 0.3))
     m[light]["emittance"] = 400.0
+    m[3]["hasReflective"] = 0.0  # all diffuse here (the oracle figures above are for this scene)
     cam = with_resolution(sample_scene["camera"], 64, 64)
     spp = 4096
     out = {}
@@ -110,7 +116,9 @@ def test_same_expected_image_less_noise(pt, sample_scene):
             c.clear()
             c.render(spp, spp, 8, 1)  # an independent second estimate: their difference measures the noise
             b = c.download_mean(spp)
-        out[nee] = (a, float(np.sqrt(np.mean((a - b) ** 2))))
+        d = np.abs(a - b).sum(axis=1)
+        out[nee] = (a, float(d.mean()), float(np.sqrt(np.mean((a - b) ** 2))))
     lum = float(out[False][0].mean())
     assert abs(float(out[True][0].mean()) - lum) < 0.02 * lum
-    assert out[True][1] < 0.85 * out[False][1]  # measured 0.69 (RMS is dominated by the caustics of the mirror sphere)
+    assert out[True][1] < 0.35 * out[False][1], (out[True][1:], out[False][1:])
+    assert out[True][2] < out[False][2]  # and the firefly-dominated RMS is at least not worse

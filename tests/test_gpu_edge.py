@@ -152,3 +152,4 @@ def test_banded_wavefronts_change_nothing(pt, oracle, sample_scene):
             _, _, live = c.counters()
             assert live[:8].tolist() == want_live.tolist(), (band, wf)
             assert same_bits(c.download_sum(), want), (band, wf)
+

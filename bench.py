@@ -272,11 +272,12 @@ def extra_configs(pt, peak):
                 ms = ctx.last_render_ms()
                 paths, segs, _ = ctx.counters()
                 fb = ctx.filter_stats()
+                retries = ctx.filter_retries()
             alg = 96.0 * (segs - paths) + 32.0 * paths
             line = {"name": name, "geoms": int(sc.n_geoms), "resolution": [sc.width, sc.height], "spp": spp,
                     "spp_of_config": spp_full, "depth": depth, "ms": ms, "Mseg_per_s": segs / ms / 1e3,
                     "spp_per_s": spp / (ms * 1e-3), "segments": int(segs), "fallback_fraction": fb / max(1, segs),
-                    "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "context_create_s": t_ctx}
+                    "retry_fraction": retries / max(1, segs), "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "context_create_s": t_ctx}
             if sc.n_geoms > 32:
                 line["bound"] = "latency / FP32 (hierarchy traversal): the HBM fraction is reported for completeness only"
             out.append(line)
@@ -285,25 +286,26 @@ def extra_configs(pt, peak):
     return out
 
 
-def shim_rate(pt, geoms, mats, cam, calls=200):
+def shim_rate(pt, geoms, mats, cam, calls=1000, warm=32):
     """the reference's calling pattern (src/main.cpp:93-113): cudaRaytraceCore() once per sample, host image updated
-    with the running mean on every call"""
+    with the running mean on every call.  Steady state of one long sequence: the first `warm` iterations (context
+    creation, the first groups of samples traced ahead) are not timed."""
     compat = importlib.import_module("project3-pathtracer_b200.compat")
     rs = compat.RefScene([(geoms, cam)], mats, iterations=SPP)  # ITERATIONS 5000, as the scene file says
     compat.reset(); compat.set_trace_depth(DEPTH); compat.set_seed(SEED); compat.set_exit_on_error(False)
     try:
-        for k in range(1, 4):  # warm-up
+        for k in range(1, warm + 1):
             compat.cudaRaytraceCore(None, rs.camera, 0, k, rs.materials, len(rs.materials), rs.geoms, len(rs.geoms))
-        compat.reset()
         t0 = time.perf_counter()
-        for k in range(1, calls + 1):
+        for k in range(warm + 1, warm + calls + 1):
             compat.cudaRaytraceCore(None, rs.camera, 0, k, rs.materials, len(rs.materials), rs.geoms, len(rs.geoms))
         dt = time.perf_counter() - t0
         if compat.last_status() != 0:
             raise RuntimeError("cudaRaytraceCore status %d" % compat.last_status())
         return {"calls": calls, "calls_per_s": calls / dt, "ms_per_call": 1e3 * dt / calls,
                 "mean_of_running_mean": float(rs.image.mean()),
-                "note": "800x800, 1 spp per call, %d bounces, D2H of the 7.68 MB running mean every call" % DEPTH}
+                "note": "800x800, iterations %d..%d of one sequence, %d bounces, D2H of the 7.68 MB running mean every call; "
+                        "samples traced ahead in groups of 8 (pt_stream_*)" % (warm + 1, warm + calls, DEPTH)}
     finally:
         compat.reset()
 

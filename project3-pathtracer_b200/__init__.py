@@ -227,6 +227,12 @@ class Context:
         """test hook: multiply the rounding-error terms of the closest-hit filter's bounds (1 = shipped)"""
         _check(lib().pt_set_filter_scale(self._h, C.c_float(scale)))
 
+    def filter_retries(self):
+        """hierarchy scenes: segments since the last clear() that the retry pass settled (pt_filter_retries)"""
+        n = C.c_uint64()
+        _check(lib().pt_filter_retries(self._h, C.byref(n)))
+        return n.value
+
     def filter_stats(self):
         """segments rendered since the last clear() whose closest hit fell back to the exact scan"""
         n = C.c_uint64()

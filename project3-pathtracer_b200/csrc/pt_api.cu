@@ -957,7 +957,7 @@ extern "C" int pt_context_create(const pt_static_geom* geoms, int n_geoms, const
       cudaMalloc(&c->d_rgb, (size_t)c->npix * 3 * sizeof(float)) != cudaSuccess ||
       cudaMalloc(&c->d_rgba8, (size_t)c->npix * sizeof(uchar4)) != cudaSuccess ||
       cudaMalloc(&c->d_ctrl, pt_context::kSlots * sizeof(WfCtrl)) != cudaSuccess ||
-      cudaMalloc(&c->d_live, (kMaxDepth + 2) * sizeof(unsigned long long)) != cudaSuccess) {
+      cudaMalloc(&c->d_live, (kMaxDepth + 3) * sizeof(unsigned long long)) != cudaSuccess) {
     pt_set_error_("cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     return fail(PT_ERR_CUDA);
   }
@@ -1016,7 +1016,7 @@ extern "C" int pt_clear(pt_context* c) {
   CTX(c);
   if (int rc = stream_discard(c)) return rc;
   CU(cudaMemsetAsync(c->d_accum, 0, (size_t)c->npix * sizeof(float4), c->stream));
-  CU(cudaMemsetAsync(c->d_live, 0, (kMaxDepth + 2) * sizeof(unsigned long long), c->stream));
+  CU(cudaMemsetAsync(c->d_live, 0, (kMaxDepth + 3) * sizeof(unsigned long long), c->stream));
   c->paths_total = 0;
   return PT_OK;
 }
@@ -1448,6 +1448,16 @@ extern "C" int pt_filter_stats(pt_context* c, uint64_t* fallbacks) {
   CU(cudaMemcpyAsync(&h, c->d_live + kMaxDepth, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   *fallbacks = h;
+  return PT_OK;
+}
+
+extern "C" int pt_filter_retries(pt_context* c, uint64_t* retries) {
+  CTX(c);
+  if (!retries) { pt_set_error_("retries is NULL"); return PT_ERR_INVALID; }
+  unsigned long long h = 0;
+  CU(cudaMemcpyAsync(&h, c->d_live + kMaxDepth + 2, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *retries = h;
   return PT_OK;
 }
 

@@ -151,8 +151,10 @@ __device__ __forceinline__ int bvh_root(const BvhSoA& B) { return B.n_leaves == 
 
 // the leaf `cur` (< 0): filter test (EXACT: exact test of the candidate if it can still matter)
 template <bool EXACT>
-__device__ __forceinline__ void leaf_visit(const BvhSoA& B, const GeomSoA& g, const ScanRay& r, ScanBest& best, Hit& h, int cur) {
+__device__ __forceinline__ void leaf_visit(const BvhSoA& B, const GeomSoA& g, const ScanRay& r, ScanBest& best, Hit& h, int cur,
+                                           int skip_leaf = -1) {
   const int leaf = ~cur;
+  if (leaf == skip_leaf) return;  // (the retry pass of an unconfirmed candidate leaves that candidate out)
   const int2 meta = __ldg(B.leaf_meta + leaf);
   float lo;
   if (leaf_filter(meta.x, B.leaves + (size_t)leaf * kBvhLeafRows, r, lo)) {
@@ -233,8 +235,8 @@ __device__ __forceinline__ bool node_visit(const BvhSoA& B, const ScanRay& r, co
 // can still matter, result in `h`.  (The builder guarantees that the stack never needs more than kBvhStack entries.)
 template <bool EXACT>
 __device__ __forceinline__ bool trav_step(const BvhSoA& B, const GeomSoA& g, const ScanRay& r, const TravRay& tr, ScanBest& best, Hit& h,
-                                          int& cur, int& sp, int* stack) {
-  if (cur < 0) leaf_visit<EXACT>(B, g, r, best, h, cur);
+                                          int& cur, int& sp, int* stack, int skip_leaf = -1) {
+  if (cur < 0) leaf_visit<EXACT>(B, g, r, best, h, cur, skip_leaf);
   else if (node_visit<EXACT>(B, r, tr, best, h, cur, sp, stack)) return true;
   if (sp == 0) return false;
   cur = stack[--sp];
@@ -243,12 +245,23 @@ __device__ __forceinline__ bool trav_step(const BvhSoA& B, const GeomSoA& g, con
 
 // a whole traversal by one lane (parity entry points, the deferred exact pass)
 template <bool EXACT>
-__device__ __forceinline__ void bvh_traverse(const BvhSoA& B, const GeomSoA& g, const ScanRay& r, ScanBest& best, Hit& h) {
+__device__ __forceinline__ void bvh_traverse(const BvhSoA& B, const GeomSoA& g, const ScanRay& r, ScanBest& best, Hit& h,
+                                             int skip_leaf = -1) {
   if (B.n_leaves <= 0) return;
   const TravRay tr = make_trav_ray(B, r);
   int stack[kBvhStack];
   int sp = 0, cur = bvh_root(B);
-  while (trav_step<EXACT>(B, g, r, tr, best, h, cur, sp, stack)) {}
+  while (trav_step<EXACT>(B, g, r, tr, best, h, cur, sp, stack, skip_leaf)) {}
+}
+
+// the exact test of leaf k on its own: false = the reference's test reports no hit (or a distance <= 0)
+__device__ __forceinline__ bool exact_leaf(int k, const BvhSoA& B, const GeomSoA& g, f3 o, f3 d, Hit& e) {
+  const int2 meta = __ldg(B.leaf_meta + k);
+  const int gi = meta.y;
+  e.id = gi;
+  const bool hit = exact_hit(meta.x < 2 ? 0 : 1, __ldg(g.inv0 + gi), __ldg(g.inv1 + gi), __ldg(g.inv2 + gi), __ldg(g.fwd0 + gi),
+                             __ldg(g.fwd1 + gi), __ldg(g.fwd2 + gi), o, d, e.t, e.p, e.ncode);
+  return hit && e.t > 0;
 }
 
 // the exact pass on its own (fallback of resolve_bvh; rare, so not inlined)

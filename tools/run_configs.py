@@ -70,6 +70,7 @@ def main():
             ms = ctx.last_render_ms()
             paths, segs, live = ctx.counters()
             fb = ctx.filter_stats()
+            retries = ctx.filter_retries()
             shadow, n_lights = ctx.shadow_rays()
             img = ctx.download_mean(spp)
         out_png = pt.save_image(img, sc.width, sc.height, os.path.join(args.png_dir, name + ".png"), 0, True)
@@ -77,7 +78,7 @@ def main():
                 "spp": spp, "spp_of_config": spp_full, "depth": depth, "paths": int(paths), "segments": int(segs),
                 "render_ms": ms, "Mseg_per_s": segs / ms / 1e3, "spp_per_s": spp / (ms * 1e-3),
                 "live_per_depth": [int(x) for x in live[:depth]], "exact_scan_fallbacks": int(fb),
-                "fallback_fraction": fb / max(1, segs), "scene_load_s": t_load, "context_create_s": t_ctx,
+                "fallback_fraction": fb / max(1, segs), "retry_fraction": retries / max(1, segs), "scene_load_s": t_load, "context_create_s": t_ctx,
                 "mean_luminance": float(img.mean()), "image": os.path.basename(out_png),
                 "direct_lighting": bool(args.direct), "lights": int(n_lights), "shadow_rays": int(shadow),
                 "Mrays_per_s": (segs + shadow) / ms / 1e3}

@@ -584,11 +584,17 @@ static double now_s(void) {
  * is not the path's last allowed segment, ONE light is picked uniformly and ONE point y on it is drawn with the
  * reference's own area-weighted cube sampler / the sphere sampler above (uniforms: Philox block 65 + depth); the
  * shadow ray from the new path origin towards y is traced with the ordinary closest hit, and if it arrives on that
- * light at y (distance within 1e-3 relative + 1e-3 of |y - o|) the estimate  thr * (1/pi) * Le * cos_s * cos_l / t^2 * area * n_lights  is added.  The continuing path then
- * carries a flag that suppresses emission if it reaches a light by itself at its next hit (no double counting);
- * specular and refractive events clear the flag.  area: the cube sampler's totalarea; spheres 4*pi/3 * (rx*ry + ry*rz
+ * light at y (distance within 1e-3 relative + 1e-3 of |y - o|) the estimate  thr * (1/pi) * Le * cos_s * cos_l / t^2 * area * n_lights  is added,
+ * weighted by the BALANCE HEURISTIC against the cosine-weighted direction sampling that continues the path:
+ *   G = cos_s * cos_l / t^2,  K = area * n_lights / pi,  p_bsdf / p_light = G * K,  w_light = 1 / (1 + G*K).
+ * The continuing path carries cos_b = dot(ns, new direction) (> 0); if it reaches a light by itself at its next hit, at
+ * distance t with cosine cos_l' > 0 on the light, its emission is weighted by  w_bsdf = x / (1 + x),  x = (cos_b * cos_l' /
+ * t^2) * K  (K of the light that was hit) -- the two weights sum to one for every direction both strategies can produce, so
+ * the estimator stays unbiased and neither strategy's bad cases dominate the variance (round 1 suppressed the emission
+ * instead: light sampling alone).  Specular and refractive events, and the camera ray, carry 0: their emission counts in
+ * full.  area: the cube sampler's totalarea; spheres 4*pi/3 * (rx*ry + ry*rz
  * + rx*rz) (exact for uniform scale). */
-typedef struct { int geom; float E[3]; float th[5]; } or_light;
+typedef struct { int geom; float E[3]; float th[5]; float K; } or_light;  /* K = area * n_lights / pi = 1 / (pi * p_area) */
 static int build_lights(const or_scene* sc, or_light* out, int cap) {
   int n = 0;
   float area[1024];
@@ -611,6 +617,7 @@ static int build_lights(const or_scene* sc, or_light* out, int cap) {
   for (int k = 0; k < n; k++) {
     const or_material* m = &sc->materials[sc->geoms[out[k].geom].materialid];
     float kk = (area[k] * (float)n) * 0.31830987f;
+    out[k].K = kk;
     st3(out[k].E, vscale(vscale(ld3(m->color), m->emittance), kk));
   }
   return n;
@@ -642,7 +649,7 @@ double or_render_ex(const or_scene* sc, uint32_t first_sample, uint32_t n_sample
     for (int64_t pix = (int64_t)pix_begin; pix < (int64_t)pix_end; pix++) {
       for (uint32_t s = first_sample; s < first_sample + n_samples; s++) {
         float o[3], d[3], thr[3] = {1.0f, 1.0f, 1.0f};
-        int skip_emission = 0;
+        float cos_b = 0.0f;  /* > 0: the previous event was a diffuse bounce with a light sample (MIS weight at the next light) */
         or_raygen(&sc->cam, &sc->lens, seed, (uint32_t)pix, s, o, d);
         for (int depth = 0; depth < max_depth; depth++) {
           mylive[depth]++;
@@ -653,18 +660,26 @@ double or_render_ex(const or_scene* sc, uint32_t first_sample, uint32_t n_sample
           v3 din = ld3(d);
           int kind = or_shade(sc, id, t, p, n, seed, (uint32_t)pix, s, (uint32_t)depth, o, d, thr, L);
           if (kind == 3) {
-            if (!skip_emission) {
-              sum_rgb[3 * pix + 0] += L[0];
-              sum_rgb[3 * pix + 1] += L[1];
-              sum_rgb[3 * pix + 2] += L[2];
+            if (cos_b > 0) {
+              float clp = -vdot(ld3(n), din);
+              if (clp > 0) {
+                float Kh = 0.0f;
+                for (int k = 0; k < n_lights; k++) if (lights[k].geom == id) Kh = lights[k].K;
+                float x = ((cos_b * clp) / (t * t)) * Kh;
+                float wb = x / (1.0f + x);
+                L[0] = L[0] * wb; L[1] = L[1] * wb; L[2] = L[2] * wb;
+              }
             }
+            sum_rgb[3 * pix + 0] += L[0];
+            sum_rgb[3 * pix + 1] += L[1];
+            sum_rgb[3 * pix + 2] += L[2];
             break;
           }
-          skip_emission = 0;
+          cos_b = 0.0f;
           if (kind == 0 && n_lights > 0 && depth + 1 < max_depth) {
-            skip_emission = 1;
             v3 N = ld3(n);
             v3 ns = vdot(din, N) < 0 ? N : vneg(N);
+            cos_b = vdot(ns, ld3(d));  /* d = the direction the bounce sampled */
             float v[4];
             rng4(seed, (uint32_t)pix, s, 65u + (uint32_t)depth, v);
             int li = (int)(v[0] * (float)n_lights);
@@ -694,7 +709,8 @@ double or_render_ex(const or_scene* sc, uint32_t first_sample, uint32_t n_sample
                 float cl = -vdot(ld3(n2), wd);
                 if (cl > 0) {
                   float G = (cs * cl) / (t2 * t2);
-                  v3 Ld = vscale(vmul(ld3(thr), ld3(Lt->E)), G);
+                  float wl = 1.0f / (1.0f + G * Lt->K);
+                  v3 Ld = vscale(vscale(vmul(ld3(thr), ld3(Lt->E)), G), wl);
                   sum_rgb[3 * pix + 0] += Ld.x;
                   sum_rgb[3 * pix + 1] += Ld.y;
                   sum_rgb[3 * pix + 2] += Ld.z;

@@ -70,6 +70,7 @@ struct pt_context {
   float4* d_normals = nullptr;  // kNormalRows float4 per geom: face normals + sphere centre (k_normal_table)
   float4* d_mats = nullptr;
   float4* d_lights = nullptr;  // direct light sampling: 3 float4 per emissive sphere / cube (build_lights)
+  float* d_light_k = nullptr;  // per geom: K = area * n_lights / pi of a light, 0 otherwise
   int n_lights = 0;
   bool nee = false;            // pt_set_direct_lighting
   float4* d_filt = nullptr;   // kFiltRows arrays of n_pairs float4: filter geometry (pt_filter.cuh)
@@ -666,8 +667,9 @@ static void h_radiuses(const pt_static_geom& g, float r[3]) {
   r[1] = h_length3(y[0] - o[0], y[1] - o[1], y[2] - o[2]);
   r[2] = h_length3(z[0] - o[0], z[1] - o[1], z[2] - o[2]);
 }
-static std::vector<float4> build_lights(const pt_static_geom* geoms, int n_geoms, const pt_material* mats) {
+static std::vector<float4> build_lights(const pt_static_geom* geoms, int n_geoms, const pt_material* mats, std::vector<float>* geom_k) {
   std::vector<float4> T;
+  geom_k->assign((size_t)n_geoms, 0.0f);
   std::vector<float> area;
   std::vector<int> ids;
   for (int i = 0; i < n_geoms; i++) {
@@ -702,7 +704,9 @@ static std::vector<float4> build_lights(const pt_static_geom* geoms, int n_geoms
   const int n = (int)ids.size();
   for (int k = 0; k < n; k++) {
     const pt_material& m = mats[geoms[ids[k]].materialid];
-    const float kk = (area[k] * (float)n) * 0.31830987f;  // area * lights / pi
+    const float kk = (area[k] * (float)n) * 0.31830987f;  // area * lights / pi = K of the balance heuristic
+    T[3 * k + 2].z = kk;
+    (*geom_k)[ids[k]] = kk;
     T[3 * k].x = (m.color[0] * m.emittance) * kk;
     T[3 * k].y = (m.color[1] * m.emittance) * kk;
     T[3 * k].z = (m.color[2] * m.emittance) * kk;
@@ -801,7 +805,12 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
   CU(cudaMemcpyAsync(c->d_rows, rows.data(), rows.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_meta, meta.data(), meta.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_mats, mats, (size_t)n_mats * sizeof(pt_material), cudaMemcpyHostToDevice, c->stream));
-  const std::vector<float4> lights = build_lights(geoms, n_geoms, mats);
+  std::vector<float> geom_k;
+  const std::vector<float4> lights = build_lights(geoms, n_geoms, mats, &geom_k);
+  if (c->d_light_k) CU(cudaFree(c->d_light_k));
+  c->d_light_k = nullptr;
+  CU(cudaMalloc(&c->d_light_k, (size_t)n_geoms * sizeof(float)));
+  CU(cudaMemcpyAsync(c->d_light_k, geom_k.data(), (size_t)n_geoms * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   if (c->d_lights) CU(cudaFree(c->d_lights));
   c->d_lights = nullptr;
   c->n_lights = (int)(lights.size() / 3);
@@ -898,7 +907,7 @@ extern "C" int pt_context_destroy(pt_context* c) {
   PT_FREE(c->d_rows); PT_FREE(c->d_meta); PT_FREE(c->d_normals); PT_FREE(c->d_mats); PT_FREE(c->d_lights); PT_FREE(c->d_state);
   PT_FREE(c->d_filt); PT_FREE(c->d_filt_ids); PT_FREE(c->d_bvh_nodes); PT_FREE(c->d_bvh_leaves); PT_FREE(c->d_bvh_meta);
   PT_FREE(c->d_ctrl); PT_FREE(c->d_live); PT_FREE(c->d_accum); PT_FREE(c->d_rgb); PT_FREE(c->d_rgba8);
-  PT_FREE(c->d_scratch);
+  PT_FREE(c->d_scratch); PT_FREE(c->d_light_k);
   PT_FREE(c->d_slab); PT_FREE(c->d_means); PT_FREE(c->d_base[0]); PT_FREE(c->d_base[1]);
 #undef PT_FREE
   for (int i = 0; i < pt_context::kSlots; i++) {
@@ -1106,7 +1115,7 @@ static int render_into(pt_context* c, uint32_t first_sample, uint32_t n_samples,
       P.filt = c->filt; P.filt_cap = c->filt_cap;
       P.bvh = c->bvh;
       P.mats = c->d_mats;
-      P.lights = c->d_lights; P.n_lights = c->n_lights;
+      P.lights = c->d_lights; P.n_lights = c->n_lights; P.light_k = c->d_light_k;
       P.cam = c->cam;
       P.ctrl = ctrl;
       P.depth = (uint32_t)depth;

@@ -16,8 +16,6 @@
 //   k_points_on_geom / k_sphere_dirs / k_transmission (pt_sampling.cuh)   sampling and absorption parity entry points
 //   k_resolve_*                        accumulation buffer -> float RGB / uchar4 (sendImageToPBO, :58-89)
 #pragma once
-#include <cuda_fp16.h>
-
 #include "pt_device.cuh"
 #include "pt_filter.cuh"
 #include "pt_bvh.cuh"
@@ -105,7 +103,8 @@ struct BounceParams {
   int filt_cap;                      // pairs that fit in shared memory
   BvhSoA bvh;                        // hierarchy over the same filter tests for scenes with many geoms (pt_bvh.cuh)
   const float4* mats;                // 4 float4 per material
-  const float4* lights;              // direct light sampling: 3 float4 per light (E.xyz | geom) (th0..th3) (th4, type, -, -)
+  const float4* lights;              // direct light sampling: 3 float4 per light (E.xyz | geom) (th0..th3) (th4, type, K, -)
+  const float* light_k;              // per geom: K = area * n_lights / pi of a light, 0 otherwise (balance heuristic at emissive hits)
   int n_lights;
   RaygenConsts cam;
   WfCtrl* ctrl;
@@ -205,7 +204,7 @@ __device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const DepthIO&
                                           uint32_t pixel, uint32_t sample) {
   bool traced = false;
   f3 wd = mk(0, 0, 1), E = mk(0, 0, 0);
-  float cs = 0.0f, dy = 0.0f;
+  float cs = 0.0f, dy = 0.0f, K = 0.0f;
   int gl = -1;
   if (active) {
     float v[4];
@@ -215,6 +214,7 @@ __device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const DepthIO&
     const float4 L0 = __ldg(P.lights + 3 * li), L1 = __ldg(P.lights + 3 * li + 1), L2 = __ldg(P.lights + 3 * li + 2);
     gl = __float_as_int(L0.w);
     E = mk(L0.x, L0.y, L0.z);
+    K = L2.z;
     const float4 f0 = __ldg(P.g.fwd0 + gl), f1 = __ldg(P.g.fwd1 + gl), f2 = __ldg(P.g.fwd2 + gl);
     const f3 y = __float_as_int(L2.y) == 0 ? sphere_point(f0, f1, f2, v[1], v[2])
                                            : cube_point_th(f0, f1, f2, L1, L2.x, v[1], v[2] - 0.5f, v[3] - 0.5f);
@@ -237,7 +237,8 @@ __device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const DepthIO&
   const float cl = -dot(n2, wd);
   if (!(cl > 0)) return;
   const float G = (cs * cl) / (h.t * h.t);
-  const f3 Ld = (thr * E) * G;
+  const float wl = 1.0f / (1.0f + G * K);  // balance heuristic: p_bsdf / p_light = G * K, K = area * n_lights / pi
+  const f3 Ld = ((thr * E) * G) * wl;
   PT_CHECK(pixel < P.cam.npix);
   accum_add(accum_at(P, pixel, sample), Ld);
 }
@@ -245,8 +246,9 @@ __device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const DepthIO&
 // The second half of a segment, by a whole warp: material lookup, reservation of the unit's output slots, BSDF
 // sampling, radiance of finished paths, survivors written to base + rank.  `hit` lanes carry a closest hit in h.
 // TABLE: normals from the per-geom table (few geoms, L1-resident; `fs` = the filter pairs in shared memory) or from the
-// winner's own rows (many geoms, hierarchy).  NEE: direct light sampling at diffuse bounces; `no_emit` = the path's
-// previous event was one (the flag travels in throughput.w), so a light it reaches by itself adds nothing.
+// winner's own rows (many geoms, hierarchy).  NEE: direct light sampling at diffuse bounces; `cos_b` > 0 = the path's
+// previous event was one (the cosine of the direction it sampled travels in throughput.w): a light it reaches by itself is
+// weighted by the balance heuristic against that event's light sample.
 // Deferred output (k_bounce_q): a batch's survivors wait in shared memory while the atomic that reserves their slots is
 // in flight, and are written one batch later -- the warp never waits for the atomic (it was 7 % of the stall samples:
 // one address per depth takes 0.6 atomics per nanosecond, and their latency under that load exceeds a whole shading pass).
@@ -270,7 +272,7 @@ __device__ __forceinline__ void deferred_flush(DeferredOut& W, const BounceParam
 
 template <bool LAST, bool TABLE, bool NEE, bool DEFER = false>
 __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const DepthIO& io, const float4* fs, uint32_t lane, bool hit, const Hit& h, f3 o, f3 d, f3 thr,
-                                                  uint32_t pixel, uint32_t sample, bool no_emit, DeferredOut* W = nullptr) {
+                                                  uint32_t pixel, uint32_t sample, float cos_b, DeferredOut* W = nullptr) {
   // a path survives this segment unless it left the scene or reached a light; the slot of the unit's survivors
   // is reserved before shading so that the atomic's latency hides behind it
   int mat = 0;
@@ -292,6 +294,7 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const D
     }
   }
   bool sampled = false;  // NEE: this lane's bounce was diffuse and gets a light sample
+  float cos_s = 0.0f;    // ... and the cosine its continuing path carries to the next hit
   f3 ns = mk(0, 0, 1);
   if (hit) {
     const int gi = h.id;
@@ -304,11 +307,22 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const D
     const float4* frame = nullptr;
     if (TABLE && h.ncode != 8) frame = P.normals + (size_t)gi * kNormalRows + kFrameRow0 + 4 * ((h.ncode & 3) + ((h.ncode & 4) ? 3 : 0));
     const int kind = shade(m, P.g, gi, h.p, n, frame, P.keys, pixel, sample, io.depth, o, d, thr, L);
-    if (kind == 3 && !(NEE && no_emit)) {
+    if (kind == 3) {
+      // a light reached by a direction the diffuse bounce before sampled itself: balance heuristic against that bounce's
+      // light sample (cos_b = cosine of this direction at the bounce, 0 = camera ray / specular event: full weight)
+      if (NEE && cos_b > 0) {
+        const float clp = -dot(n, d);
+        if (clp > 0) {
+          const float x = ((cos_b * clp) / (h.t * h.t)) * __ldg(P.light_k + gi);
+          const float wb = x / (1.0f + x);
+          L = L * wb;
+        }
+      }
       PT_CHECK(pixel < P.cam.npix);
       accum_add(accum_at(P, pixel, sample), L);
     }
     sampled = NEE && !LAST && kind == 0 && P.n_lights > 0;
+    if (sampled) cos_s = dot(ns, d);  // of the direction the bounce just sampled
   }
   if (!LAST) {
     if (DEFER) {
@@ -316,7 +330,7 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const D
       if (alive) {
         W->stage[rank] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
         W->stage[kUnit + rank] = make_float4(d.x, d.y, d.z, __uint_as_float(sample));
-        W->stage[2 * kUnit + rank] = make_float4(thr.x, thr.y, thr.z, sampled ? 1.0f : 0.0f);
+        W->stage[2 * kUnit + rank] = make_float4(thr.x, thr.y, thr.z, sampled ? cos_s : 0.0f);
       }
       __syncwarp();
     } else {
@@ -325,7 +339,7 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const D
         PT_CHECK(slot < P.cap);
         __stcs(io.out_o + slot, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
         __stcs(io.out_d + slot, make_float4(d.x, d.y, d.z, __uint_as_float(sample)));
-        __stcs(io.out_t + slot, make_float4(thr.x, thr.y, thr.z, sampled ? 1.0f : 0.0f));
+        __stcs(io.out_t + slot, make_float4(thr.x, thr.y, thr.z, sampled ? cos_s : 0.0f));
       }
     }
     if (NEE && __any_sync(0xffffffffu, sampled)) direct_light<TABLE>(P, io, fs, lane, sampled, ns, o, thr, pixel, sample);
@@ -355,7 +369,7 @@ __device__ __forceinline__ void bounce_fused(const BounceParams& P, const DepthI
 
     f3 o = mk(0, 0, 0), d = mk(0, 0, 1), thr = mk(1, 1, 1);
     uint32_t pixel = 0, sample = 0;
-    bool no_emit = false;
+    float cos_b = 0.0f;
     if (valid) {
       if (FIRST) {
         const uint32_t si = fastdiv(idx, P.div_band);
@@ -367,7 +381,7 @@ __device__ __forceinline__ void bounce_fused(const BounceParams& P, const DepthI
         o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
         d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
         thr = mk(c.x, c.y, c.z);
-        if (NEE) no_emit = c.w != 0.0f;
+        if (NEE) cos_b = c.w;
       }
     }
 
@@ -381,7 +395,7 @@ __device__ __forceinline__ void bounce_fused(const BounceParams& P, const DepthI
       if (resolve_scan(best, P.filt, P.g, P.n_geoms, o, d, h)) atomicAdd(&P.ctrl->fallbacks, 1u);
     }
 
-    shade_and_compact<LAST, true, NEE>(P, io, fs, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
+    shade_and_compact<LAST, true, NEE>(P, io, fs, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, cos_b);
     }
   }
 }
@@ -419,19 +433,13 @@ constexpr int kQCap = 96;
 #ifndef PT_Q_DEFER_OUT
 #define PT_Q_DEFER_OUT 1
 #endif
-#ifndef PT_Q_PACK48
-#define PT_Q_PACK48 0  // 1: 48-byte entries -- (lo2 rounded DOWN to binary16 | geom | flag) packed into the throughput's spare
-                       // word -- so that four 64-register CTAs and the staging fit an SM (measured: see DESIGN.md)
-#endif
 // (A queue that carries only the path index, phase B fetching the throughput from HBM itself, was measured too: a first
 // touch of HBM at the head of every batch, 58 % issue-slot utilisation, slower.)
 struct QWarp {
   float4 o[kQCap];  // (origin.xyz, pixel)
   float4 d[kQCap];  // (direction.xyz, sample)
-  float4 t[kQCap];  // (throughput.xyz, no-emission flag [PT_Q_PACK48: flag | geom << 1 | binary16(lo2) << 16])
-#if !PT_Q_PACK48
+  float4 t[kQCap];  // (throughput.xyz, cos_b of direct light sampling)
   float4 c[kQCap];  // (lo2 = second-smallest lower bound, bits of the candidate's geom index, path index, -)
-#endif
 #if PT_Q_PREFETCH
   float4 st[3][kUnit];  // staging: the next unit's (origin | direction | throughput) rows, one slot per lane
 #endif
@@ -514,15 +522,9 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
       const float4 a = Q.o[slot], b = Q.d[slot];
       f3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z);
       const uint32_t pixel = __float_as_uint(a.w), sample = __float_as_uint(b.w);
-#if PT_Q_PACK48
-      const uint32_t tag = __float_as_uint(Q.t[slot].w);
-      const int gi = (int)((tag >> 1) & 0x7fffu);
-      const float lo2 = __half2float(__ushort_as_half((unsigned short)(tag >> 16)));
-#else
       const float4 e = Q.c[slot];
       const int gi = __float_as_int(e.y);
       const float lo2 = e.x;
-#endif
       Hit h;
       const bool hit = exact_hit(type, __ldg(P.g.inv0 + gi), __ldg(P.g.inv1 + gi), __ldg(P.g.inv2 + gi), __ldg(P.g.fwd0 + gi),
                                  __ldg(P.g.fwd1 + gi), __ldg(P.g.fwd2 + gi), o, d, h.t, h.p, h.ncode);
@@ -538,16 +540,12 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
       // the throughput is fetched only now: it is not needed before shading, and the exact test is where registers are scarce
       const float4 c = Q.t[slot];
       f3 thr = mk(c.x, c.y, c.z);
-#if PT_Q_PACK48
-      const bool no_emit = NEE && (__float_as_uint(c.w) & 1u) != 0u;
-#else
-      const bool no_emit = NEE && c.w != 0.0f;
-#endif
+      const float cos_b = NEE ? c.w : 0.0f;
       __syncwarp();  // the popped entries are in registers: the next push may overwrite them
 #if PT_Q_DEFER_OUT
-      shade_and_compact<LAST, true, NEE, true>(P, io, fs, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, no_emit, &W);
+      shade_and_compact<LAST, true, NEE, true>(P, io, fs, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, cos_b, &W);
 #else
-      shade_and_compact<LAST, true, NEE>(P, io, fs, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
+      shade_and_compact<LAST, true, NEE>(P, io, fs, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, cos_b);
 #endif
     }
     if (!more) break;
@@ -578,16 +576,8 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
         PT_CHECK(slot < (uint32_t)kQCap && ns + nc + __popc(bs) + __popc(bc) <= (uint32_t)kQCap);
         PT_CHECK(idx < P.cap && gi >= 0 && gi < P.n_geoms);
         Q.o[slot] = a; Q.d[slot] = b;
-#if PT_Q_PACK48
-        // lo2 rounded DOWN to binary16: a smaller bound can only send a confirmed candidate to the exact scan, never accept
-        // a wrong one (+inf and values above 65504 stay "no second candidate" / the largest half)
-        c.w = __uint_as_float((c.w != 0.0f ? 1u : 0u) | ((uint32_t)gi << 1) |
-                              ((uint32_t)__half_as_ushort(__float2half_rd(best.lo2)) << 16));
-        Q.t[slot] = c;
-#else
         Q.t[slot] = c;
         Q.c[slot] = make_float4(best.lo2, __int_as_float(gi), __uint_as_float(idx), 0.0f);
-#endif
       }
       ns += __popc(bs);
       nc += __popc(bc);
@@ -674,7 +664,7 @@ __device__ __noinline__ void run_deferred(const BounceParams& P, const uint2* li
   const bool valid = lane < n;
   f3 o = mk(0, 0, 0), d = mk(0, 0, 1), thr = mk(1, 1, 1);
   uint32_t pixel = 0, sample = 0;
-  bool no_emit = false;
+  float cos_b = 0.0f;
   Hit h;
   h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
   bool open = false;  // the retry pass did not settle it either
@@ -683,7 +673,7 @@ __device__ __noinline__ void run_deferred(const BounceParams& P, const uint2* li
     const uint32_t idx = ent.x;
     const int k1 = (int)ent.y;
     load_path<FIRST>(P, idx, o, d, pixel, sample);
-    if (!FIRST) { const float4 c = __ldg(P.in_t + idx); thr = mk(c.x, c.y, c.z); no_emit = NEE && c.w != 0.0f; }
+    if (!FIRST) { const float4 c = __ldg(P.in_t + idx); thr = mk(c.x, c.y, c.z); cos_b = NEE ? c.w : 0.0f; }
     const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene, true);
     Hit e1, e2, unused;
     const bool hit1 = exact_leaf(k1, P.bvh, P.g, o, d, e1);
@@ -711,7 +701,7 @@ __device__ __noinline__ void run_deferred(const BounceParams& P, const uint2* li
     atomicAdd(&P.ctrl->fallbacks, n_open);       // statistics: segments that needed the exact traversal ...
     atomicAdd(&P.ctrl->retries, n - n_open);     // ... and segments the retry pass settled
   }
-  shade_and_compact<LAST, false, NEE>(P, io, nullptr, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
+  shade_and_compact<LAST, false, NEE>(P, io, nullptr, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, cos_b);
 }
 
 template <bool FIRST, bool LAST, bool NEE = false>
@@ -814,7 +804,7 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
       const bool valid = j < n_pool;
       f3 o = mk(0, 0, 0), d = mk(0, 0, 1), thr = mk(1, 1, 1);
       uint32_t pixel = 0, sample = 0;
-      bool no_emit = false;
+      float cos_b = 0.0f;
       Hit h;
       h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
       bool defer = false;
@@ -824,7 +814,7 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
         const float2 res = S.res[j];
         o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
         d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
-        if (!FIRST) { const float4 c = __ldcs(P.in_t + base + j); thr = mk(c.x, c.y, c.z); no_emit = NEE && c.w != 0.0f; }
+        if (!FIRST) { const float4 c = __ldcs(P.in_t + base + j); thr = mk(c.x, c.y, c.z); cos_b = NEE ? c.w : 0.0f; }
         k1 = __float_as_int(res.y);
         if (k1 >= 0) defer = !confirm_candidate(k1, res.x, P.bvh, P.g, o, d, h);  // k1 < 0: every geom is a proven miss
       }
@@ -832,7 +822,7 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
       PT_CHECK(n_defer + __popc(dmask) <= (uint32_t)kDeferCap);
       if (defer) S.defer[n_defer + __popc(dmask & ((1u << lane) - 1u))] = make_uint2(base + j, (uint32_t)k1);
       n_defer += __popc(dmask);
-      shade_and_compact<LAST, false, NEE>(P, io, nullptr, lane, valid && !defer && h.id >= 0, h, o, d, thr, pixel, sample, no_emit);
+      shade_and_compact<LAST, false, NEE>(P, io, nullptr, lane, valid && !defer && h.id >= 0, h, o, d, thr, pixel, sample, cos_b);
       if (n_defer >= kUnit) {
         __syncwarp();
         n_defer -= kUnit;

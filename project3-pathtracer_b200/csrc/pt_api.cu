@@ -16,6 +16,8 @@
 #include <cstring>
 #include <string>
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <functional>
 #include <vector>
 
@@ -445,7 +447,7 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
     std::vector<double> suffix(n);
     struct BNode { Box b[2]; int c[2]; };  // the binary tree; collapsed into 4-wide nodes below
     std::vector<BNode> bnodes((size_t)(n > 1 ? n - 1 : 1));
-    int next_node = 0;
+    std::atomic<int> next_node{0};  // (subtrees are built by several host threads: node numbers are handed out atomically)
     // Returns the child reference (node index, or ~leaf) and the box of idx[first, last).  Split rule: the cheapest, by
     // the surface-area heuristic (area x count of each side), of
     //   * the largest geom on its own (a ground slab among pebbles: whatever group it stayed in would inherit its
@@ -510,7 +512,15 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
       }
       const int me = next_node++;
       Box b0, b1;
-      const int c0 = build(first, mid, depth + 1, b0), c1 = build(mid, last, depth + 1, b1);
+      int c0, c1;
+      if (depth < 3 && cnt >= 2048) {  // the two halves are independent (disjoint ranges of idx / suffix): up to 8 threads
+        std::thread left([&] { c0 = build(first, mid, depth + 1, b0); });
+        c1 = build(mid, last, depth + 1, b1);
+        left.join();
+      } else {
+        c0 = build(first, mid, depth + 1, b0);
+        c1 = build(mid, last, depth + 1, b1);
+      }
       bnodes[me].b[0] = b0; bnodes[me].b[1] = b1; bnodes[me].c[0] = c0; bnodes[me].c[1] = c1;
       box = merge(b0, b1);
       return me;
@@ -572,7 +582,7 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
       };
       if (root_ref >= 0) collapse(root_ref, stack_need);
       if (getenv("PT_B200_BVH_DEBUG"))
-        fprintf(stderr, "pt_b200 bvh: %d leaves, %d binary nodes, %zu wide nodes, stack need %d of %d%s\n", n, next_node,
+        fprintf(stderr, "pt_b200 bvh: %d leaves, %d binary nodes, %zu wide nodes, stack need %d of %d%s\n", n, next_node.load(),
                 F.nodes.size() / kBvhNodeRows, stack_need, kBvhStack, median_only ? " (median splits)" : "");
       if (stack_need + 2 <= kBvhStack || median_only) break;
       median_only = true;  // a degenerate tree: the balanced one needs 3 entries per two binary levels at most

@@ -110,6 +110,41 @@ def test_sample_stream_equals_one_render_per_sample(pt, sample_scene, group):
             b.stream_next()  # no stream open any more
 
 
+def test_sample_stream_with_direct_lighting_and_scene_change(pt, oracle, sample_scene):
+    """a stream under direct light sampling (several contributions per pixel and sample: float summation order differs,
+    the sums agree to 1e-5), then a scene update in the middle of a group: the samples traced ahead with the old scene are
+    dropped, the samples handed out so far stay in the sum, and a new stream continues with the new scene"""
+    cam = with_resolution(sample_scene["camera"], 64, 48)
+    g, m = sample_scene["geoms"], sample_scene["materials"]
+    depth, seed = 6, 21
+    with pt.Context(g, m, cam) as a, pt.Context(g, m, cam) as b:
+        for c in (a, b):
+            c.set_direct_lighting(True)
+        b.stream_begin(0, 0, depth, seed, 4)
+        for k in range(6):  # one and a half groups
+            a.render(k, 1, depth, seed)
+            mean, spp = b.stream_next()
+            want = a.download_mean(k + 1)
+            assert spp == k + 1 and np.allclose(mean, want, rtol=1e-5, atol=1e-5), k
+        g2 = g.copy()
+        g2[5]["materialid"] = 1  # the big sphere turns red
+        for c in (a, b):
+            c.update_scene(g2, m, cam)
+        assert np.allclose(b.download_sum(), a.download_sum(), rtol=1e-5, atol=1e-5)  # six samples of the old scene, no more
+        b.stream_begin(6, 6, depth, seed, 4)
+        for k in range(6, 9):
+            a.render(k, 1, depth, seed)
+            mean, spp = b.stream_next()
+            assert spp == k + 1 and np.allclose(mean, a.download_mean(k + 1), rtol=1e-5, atol=1e-5), k
+        b.stream_end()
+        assert np.allclose(b.download_sum(), a.download_sum(), rtol=1e-5, atol=1e-5)
+        # the oracle agrees with the mixed sequence: 6 samples of the first scene + 3 of the second
+        want = np.zeros((64 * 48, 3), np.float32)
+        oracle.render(oracle.make_scene(g, m, cam, direct_lighting=True), 0, 6, depth, seed, sum_rgb=want)
+        oracle.render(oracle.make_scene(g2, m, cam, direct_lighting=True), 6, 3, depth, seed, sum_rgb=want)
+        assert np.allclose(a.download_sum(), want, rtol=1e-5, atol=1e-5)
+
+
 def test_cudaRaytraceCore_frame_selects_per_frame_arrays_and_writes_pbo(pt, compat, oracle, sample_scene):
     import torch
     cam = with_resolution(sample_scene["camera"], 64, 64)

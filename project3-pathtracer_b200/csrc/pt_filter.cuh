@@ -247,15 +247,18 @@ __device__ __forceinline__ void filter_scan(const float4* v, int first, int last
 // ---- the exact test of ONE geom: the reference's arithmetic, unfused, in its order (see pt_device.cuh) ----
 // Returns false if the object-space test reports a miss; otherwise the world distance, the world point and the face
 // code (cube: axis | (negative ? 4 : 0); sphere: 8).  The caller applies `dist > 0` and the closest-hit rule.
+// M: Guarded (range guards inside sqrt / reciprocal, the rule) or DeferredGuard (fast paths unconditionally, the caller checks
+// m.bad and does not use the result if it is set)
+template <typename M>
 __device__ __forceinline__ bool exact_hit(int type, float4 i0, float4 i1, float4 i2, float4 f0, float4 f1, float4 f2,
-                                          f3 o, f3 d, float& dist, f3& P, int& ncode) {
+                                          f3 o, f3 d, float& dist, f3& P, int& ncode, M& m) {
   // intersections.h:85-86: object-space origin and re-normalised direction
   // (Scalar on purpose.  Doing both products side by side with the packed f32x2 instructions would halve these 42
   // operations, but ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad false -- also when
   // they are spelled fma(a, b, -0) and fma(a, 1, b) -- and the fused sums differ in the last bit: parity with the
   // reference's arithmetic was lost (tests/test_gpu_parity.py::test_closest_hit_primary_rays) for no gain.  DESIGN.md 3b.)
   const f3 ro = mulMV(i0, i1, i2, o.x, o.y, o.z, 1.0f);
-  const f3 rd = normalize(mulMV(i0, i1, i2, d.x, d.y, d.z, 0.0f));
+  const f3 rd = normalize(mulMV(i0, i1, i2, d.x, d.y, d.z, 0.0f), m);
   float t;
   if (type == 0) {
     // sphereIntersectionTest, intersections.h:90-108
@@ -263,7 +266,7 @@ __device__ __forceinline__ bool exact_hit(int type, float4 i0, float4 i1, float4
     // the reference's host build evaluates float*float - (float - pow(.5f,2)) in binary64 (pow -> double)
     const float radicand = (float)((double)(vDot * vDot) - ((double)dot(ro, ro) - 0.25));
     if (radicand < 0) return false;
-    const float sq = sqrt_ieee(radicand);
+    const float sq = m.sqrt(radicand);
     const float first_term = -vDot;
     const float t1 = first_term + sq;
     const float t2 = first_term - sq;
@@ -273,7 +276,7 @@ __device__ __forceinline__ bool exact_hit(int type, float4 i0, float4 i1, float4
     ncode = 8;
   } else {
     // boxIntersectionTest (stub in the reference), DESIGN.md "box test": slabs on [-0.5,0.5]^3, IEEE minNum/maxNum
-    const float ivx = rcp_ieee(rd.x), ivy = rcp_ieee(rd.y), ivz = rcp_ieee(rd.z);
+    const float ivx = m.rcp(rd.x), ivy = m.rcp(rd.y), ivz = m.rcp(rd.z);
     const float t1x = (-0.5f - ro.x) * ivx, t2x = (0.5f - ro.x) * ivx;
     const float t1y = (-0.5f - ro.y) * ivy, t2y = (0.5f - ro.y) * ivy;
     const float t1z = (-0.5f - ro.z) * ivz, t2z = (0.5f - ro.z) * ivz;
@@ -291,10 +294,16 @@ __device__ __forceinline__ bool exact_hit(int type, float4 i0, float4 i1, float4
     ncode = axis | (negative ? 4 : 0);
   }
   // intersections.h:110,116: world point of the pulled-back object-space point, world distance
-  const f3 po = point_on_ray(ro, rd, t);
+  const f3 po = point_on_ray(ro, rd, t, m);
   P = mulMV(f0, f1, f2, po.x, po.y, po.z, 1.0f);
-  dist = length(o - P);
+  dist = length(o - P, m);
   return true;
+}
+
+__device__ __forceinline__ bool exact_hit(int type, float4 i0, float4 i1, float4 i2, float4 f0, float4 f1, float4 f2,
+                                          f3 o, f3 d, float& dist, f3& P, int& ncode) {
+  Guarded m;
+  return exact_hit(type, i0, i1, i2, f0, f1, f2, o, d, dist, P, ncode, m);
 }
 
 // the exact scan: every geom through exact_hit, index order, strictly smaller positive distance wins
@@ -326,9 +335,10 @@ __device__ __forceinline__ bool resolve_scan(const ScanBest& best, const FiltSoA
   float dist;
   f3 P;
   int ncode;
+  DeferredGuard m;  // (an argument outside the fast paths' range sends the ray to the exact scan, which guards every call)
   const bool hit = exact_hit(type, __ldg(g.inv0 + gi), __ldg(g.inv1 + gi), __ldg(g.inv2 + gi), __ldg(g.fwd0 + gi),
-                             __ldg(g.fwd1 + gi), __ldg(g.fwd2 + gi), o, d, dist, P, ncode);
-  if (hit && dist > 0 && dist < best.lo2) {
+                             __ldg(g.fwd1 + gi), __ldg(g.fwd2 + gi), o, d, dist, P, ncode, m);
+  if (!m.bad && hit && dist > 0 && dist < best.lo2) {
     h.t = dist; h.id = gi; h.p = P; h.ncode = ncode;
     return false;
   }

@@ -526,10 +526,11 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
       const int gi = __float_as_int(e.y);
       const float lo2 = e.x;
       Hit h;
+      DeferredGuard m;  // (an argument outside the fast paths' range sends the lane to the exact scan, which guards every call)
       const bool hit = exact_hit(type, __ldg(P.g.inv0 + gi), __ldg(P.g.inv1 + gi), __ldg(P.g.inv2 + gi), __ldg(P.g.fwd0 + gi),
-                                 __ldg(P.g.fwd1 + gi), __ldg(P.g.fwd2 + gi), o, d, h.t, h.p, h.ncode);
+                                 __ldg(P.g.fwd1 + gi), __ldg(P.g.fwd2 + gi), o, d, h.t, h.p, h.ncode, m);
       h.id = gi;
-      if (!(hit && h.t > 0 && h.t < lo2)) {
+      if (m.bad || !(hit && h.t > 0 && h.t < lo2)) {
         // the candidate is not confirmed: the exact scan decides (0.008 % of the segments on the sample scene)
         h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
         if (valid) {

@@ -835,7 +835,7 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
   c->g.fwd0 = c->d_rows + 3 * (size_t)n_geoms; c->g.fwd1 = c->d_rows + 4 * (size_t)n_geoms;
   c->g.fwd2 = c->d_rows + 5 * (size_t)n_geoms;
   c->g.meta = c->d_meta;
-  k_normal_table<<<(n_geoms + 127) / 128, 128, 0, c->stream>>>(c->g, n_geoms, c->d_normals);
+  k_normal_table<<<(n_geoms + 127) / 128, 128, 0, c->stream>>>(c->g, n_geoms, reinterpret_cast<const float4*>(c->d_mats), c->d_normals);
   CU(cudaGetLastError());
   c->cam = make_raygen(*cam, lens);
   c->W = (uint32_t)Wi; c->H = (uint32_t)Hi; c->npix = c->W * c->H;

@@ -130,40 +130,18 @@ __device__ __forceinline__ void scan_take(ScanBest& b, float lo, int k) {
 // Scan pairs [first, last) (global pair indices); `v` points at the record of pair `first`; end[k] = first pair
 // index after class k.  Every "miss" needs a comparison to come out TRUE, so a NaN anywhere keeps the geom as a
 // candidate.
-#ifndef PT_FILT_BRANCHFREE
-#define PT_FILT_BRANCHFREE 1
-#endif
-#if PT_FILT_BRANCHFREE
-// Branch-free: a proven miss is handed to the sink as the bound +inf, which changes nothing there (scan_take).  Some
-// lane of a warp nearly always needs the body, so the branches bought nothing but BSSY / BRA / BSYNC.
-// (sqrt of a negative discriminant is NaN, and NaN < 0 is false: the decision is the first comparison's, as before.)
-#define PT_SPHERE_HALF(H, K)                                                                          \
-  {                                                                                                   \
-    const float sd = mufu_sqrt(disc.H), ia = mufu_rcp(a.H);                                           \
-    const bool miss = (disc.H < 0.0f) || ((sd - b.H) * ia < 0.0f); /* 2nd: the sphere lies behind */  \
-    sink(miss ? INFINITY : __fmaf_rn((-b.H - sd) * ia, r.dl, -ew.H), K);                              \
-  }
-#define PT_BOX_HALF(H, K)                                                                             \
-  {                                                                                                   \
-    const float tnear = fmaxf(fmaxf(nx.H, ny.H), nz.H), tfar = fminf(fminf(fx.H, fy.H), fz.H);        \
-    const bool miss = (tnear > tfar) || (tfar < 0.0f); /* misses the inflated box, or it lies behind */ \
-    sink(miss ? INFINITY : __fmaf_rn(tnear, r.dl, -ew.H), K);                                         \
-  }
-#else
-#define PT_SPHERE_HALF(H, K)                                                                          \
-  if (!(disc.H < 0.0f)) {                                                                             \
-    const float sd = mufu_sqrt(disc.H), ia = mufu_rcp(a.H);                                           \
-    if (!((sd - b.H) * ia < 0.0f)) /* else: the inflated sphere lies behind the origin */             \
-      sink(__fmaf_rn((-b.H - sd) * ia, r.dl, -ew.H), K);                                              \
-  }
-#define PT_BOX_HALF(H, K)                                                                             \
-  {                                                                                                   \
-    const float tnear = fmaxf(fmaxf(nx.H, ny.H), nz.H), tfar = fminf(fminf(fx.H, fy.H), fz.H);        \
-    if (!(tnear > tfar || tfar < 0.0f)) /* else: misses the inflated box, or the box lies behind */   \
-      sink(__fmaf_rn(tnear, r.dl, -ew.H), K);                                                         \
-  }
-#endif
-// `sink(lo, k)` receives every geom the filter cannot rule out: its lower bound and 2*pair + half
+// Branch-free halves: a proven miss is handed to the sink as such and changes nothing there.  Some lane of a warp nearly
+// always needs the body, so branches bought nothing but BSSY / BRA / BSYNC.
+// (sqrt of a negative discriminant is NaN, and NaN < 0 is false: the decision is the first comparison's.)
+#define PT_SPHERE_HALF(H)                                                                             \
+  const float sd_##H = mufu_sqrt(disc.H), ia_##H = mufu_rcp(a.H);                                     \
+  const bool miss_##H = (disc.H < 0.0f) || ((sd_##H - b.H) * ia_##H < 0.0f); /* 2nd: the sphere lies behind */ \
+  const float lo_##H = __fmaf_rn((-b.H - sd_##H) * ia_##H, r.dl, -ew.H);
+#define PT_BOX_HALF(H)                                                                                \
+  const float tnear_##H = fmaxf(fmaxf(nx.H, ny.H), nz.H), tfar_##H = fminf(fminf(fx.H, fy.H), fz.H);  \
+  const bool miss_##H = (tnear_##H > tfar_##H) || (tfar_##H < 0.0f); /* misses the inflated box, or it lies behind */ \
+  const float lo_##H = __fmaf_rn(tnear_##H, r.dl, -ew.H);
+// `sink(lo_A, miss_A, lo_B, miss_B, pair)` receives both halves of every pair: lower bound, and whether the geom is ruled out
 template <typename Sink>
 __device__ __forceinline__ void filter_scan_to(const float4* v, int first, int last, const int end[kFiltClasses],
                                                const ScanRay& r, Sink& sink) {
@@ -182,8 +160,9 @@ __device__ __forceinline__ void filter_scan_to(const float4* v, int first, int l
     if (disc.x < 0.0f && disc.y < 0.0f) continue;          // both lines miss their inflated spheres
     const f2 ew = fma2(hi2(C3), w2, lo2(C3));
     const f2 a = bc2(r.a);
-    PT_SPHERE_HALF(x, 2 * i)
-    PT_SPHERE_HALF(y, 2 * i + 1)
+    PT_SPHERE_HALF(x)
+    PT_SPHERE_HALF(y)
+    sink(lo_x, miss_x, lo_y, miss_y, i);
   }
   // ---- class 1: other spheres, object space ----
   for (const int e = min(last, end[1]); i < e; i++, v += kFiltRows) {
@@ -197,8 +176,9 @@ __device__ __forceinline__ void filter_scan_to(const float4* v, int first, int l
     const f2 disc = fma2(a, nc, mul2(b, b));      // (ro.rw)^2 - |rw|^2 (|ro|^2 - R^2)
     if (disc.x < 0.0f && disc.y < 0.0f) continue;  // both lines miss their inflated spheres
     const f2 ew = fma2(lo2(v[8]), w2, hi2(K1));
-    PT_SPHERE_HALF(x, 2 * i)
-    PT_SPHERE_HALF(y, 2 * i + 1)
+    PT_SPHERE_HALF(x)
+    PT_SPHERE_HALF(y)
+    sink(lo_x, miss_x, lo_y, miss_y, i);
   }
   // ---- class 2: world-axis-aligned cubes, world space ----
   for (const int e = min(last, end[2]); i < e; i++, v += kFiltRows) {
@@ -211,8 +191,9 @@ __device__ __forceinline__ void filter_scan_to(const float4* v, int first, int l
     const f2 nx = fma2(hx, neg2(aix), cx), ny = fma2(hy, neg2(aiy), cy), nz = fma2(hz, neg2(aiz), cz);
     const f2 fx = fma2(hx, aix, cx), fy = fma2(hy, aiy, cy), fz = fma2(hz, aiz, cz);
     const f2 ew = fma2(lo2(v[5]), w2, hi2(C4));
-    PT_BOX_HALF(x, 2 * i)
-    PT_BOX_HALF(y, 2 * i + 1)
+    PT_BOX_HALF(x)
+    PT_BOX_HALF(y)
+    sink(lo_x, miss_x, lo_y, miss_y, i);
   }
   // ---- class 3: other cubes, object space ----
   for (const int e = min(last, end[3]); i < e; i++, v += kFiltRows) {
@@ -227,21 +208,60 @@ __device__ __forceinline__ void filter_scan_to(const float4* v, int first, int l
     const f2 nx = fma2(hx, neg2(abs2(ix)), cx), ny = fma2(hy, neg2(abs2(iy)), cy), nz = fma2(hz, neg2(abs2(iz)), cz);
     const f2 fx = fma2(hx, abs2(ix), cx), fy = fma2(hy, abs2(iy), cy), fz = fma2(hz, abs2(iz), cz);
     const f2 ew = fma2(hi2(K3), w2, lo2(K3));
-    PT_BOX_HALF(x, 2 * i)
-    PT_BOX_HALF(y, 2 * i + 1)
+    PT_BOX_HALF(x)
+    PT_BOX_HALF(y)
+    sink(lo_x, miss_x, lo_y, miss_y, i);
   }
 }
 #undef PT_SPHERE_HALF
 #undef PT_BOX_HALF
 #undef PT_FILT_TRANSFORM
+#ifndef PT_FILT_KEYED
+#define PT_FILT_KEYED 1
+#endif
 struct TakeBest {
   ScanBest& b;
-  __device__ __forceinline__ void operator()(float lo, int k) { scan_take(b, lo, k); }
+  __device__ __forceinline__ void operator()(float lo_a, bool miss_a, float lo_b, bool miss_b, int pair) {
+    scan_take(b, miss_a ? INFINITY : lo_a, 2 * pair);
+    scan_take(b, miss_b ? INFINITY : lo_b, 2 * pair + 1);
+  }
 };
+// The same bookkeeping on KEYS: a candidate's index 2*pair + half replaces the low kKeyBits bits of its (non-negative)
+// bound, which rounds the bound DOWN by at most 2^-16 of itself -- still a lower bound -- and lets minimum / maximum
+// instructions carry the index along: 11 instructions per pair instead of 14.  Keys of non-negative floats order like the
+// floats; +inf (no index bits) = nothing.  A bound that is itself +inf or NaN can only lose the candidate or lower lo2:
+// +inf cannot be the bound of a hit the exact test accepts (finite distances only), NaN became 0 before.
+constexpr int kKeyBits = 7;  // 2 * kMaxSmemPairs = 128 halves
+constexpr uint32_t kKeyMask = (1u << kKeyBits) - 1u;
+struct TakeBestKeyed {
+  float k1 = INFINITY, k2 = INFINITY;
+  static __device__ __forceinline__ float key(float lo, bool miss, uint32_t k) {
+    const float v = __uint_as_float((__float_as_uint(fmaxf(lo, 0.0f)) & ~kKeyMask) | k);  // (NaN -> 0: "no information")
+    return miss ? INFINITY : v;
+  }
+  __device__ __forceinline__ void operator()(float lo_a, bool miss_a, float lo_b, bool miss_b, int pair) {
+    const float ka = key(lo_a, miss_a, 2u * pair), kb = key(lo_b, miss_b, 2u * pair + 1u);
+    const float mn = fminf(ka, kb), mx = fmaxf(ka, kb);
+    k2 = fminf(fminf(k2, fmaxf(k1, mn)), mx);
+    k1 = fminf(k1, mn);
+  }
+  __device__ __forceinline__ void finish(ScanBest& b) const {
+    b.k1 = k1 < INFINITY ? (int)(__float_as_uint(k1) & kKeyMask) : -1;
+    b.lo1 = __uint_as_float(__float_as_uint(k1) & ~kKeyMask);
+    b.lo2 = __uint_as_float(__float_as_uint(k2) & ~kKeyMask);
+  }
+};
+// (`best` is overwritten: a scan starts from nothing)
 __device__ __forceinline__ void filter_scan(const float4* v, int first, int last, const int end[kFiltClasses],
                                             const ScanRay& r, ScanBest& best) {
+#if PT_FILT_KEYED
+  TakeBestKeyed sink;
+  filter_scan_to(v, first, last, end, r, sink);
+  sink.finish(best);
+#else
   TakeBest sink{best};
   filter_scan_to(v, first, last, end, r, sink);
+#endif
 }
 
 // ---- the exact test of ONE geom: the reference's arithmetic, unfused, in its order (see pt_device.cuh) ----

@@ -252,6 +252,9 @@ __device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const DepthIO&
 // Deferred output (k_bounce_q): a batch's survivors wait in shared memory while the atomic that reserves their slots is
 // in flight, and are written one batch later -- the warp never waits for the atomic (it was 7 % of the stall samples:
 // one address per depth takes 0.6 atomics per nanosecond, and their latency under that load exceeds a whole shading pass).
+#ifndef PT_MD_FROM_TABLE
+#define PT_MD_FROM_TABLE 1
+#endif
 struct DeferredOut {
   float4* stage;      // [3][kUnit] in the warp's shared memory: the survivors' (origin | direction | throughput) rows, ranked
   uint32_t pend_raw;  // lane 0: slot base of the staged survivors (result of the atomic; read one batch later)
@@ -279,7 +282,8 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const D
   float4 md = make_float4(0, 0, 0, 0);  // (absorption.yz, reducedScatter, emittance)
   if (hit) {
     mat = __ldg(P.g.meta + h.id).y;
-    md = __ldg(P.mats + 4 * mat + 3);
+    // (the per-geom table holds a copy of its material's fourth row: one load instead of two dependent ones ahead of the ballot)
+    md = (TABLE && PT_MD_FROM_TABLE) ? __ldg(P.normals + (size_t)h.id * kNormalRows + kMatRow) : __ldg(P.mats + 4 * mat + 3);
   }
   const bool alive = hit && !(md.w > 0);
   uint32_t base_raw = 0, ballot = 0;
@@ -430,6 +434,9 @@ constexpr int kQCap = 96;
 #ifndef PT_Q_PREFETCH
 #define PT_Q_PREFETCH 1  // the next unit's path state travels HBM -> shared memory (cp.async) while this unit is traced
 #endif
+#ifndef PT_Q_PREFETCH_EARLY
+#define PT_Q_PREFETCH_EARLY 1
+#endif
 #ifndef PT_Q_DEFER_OUT
 #define PT_Q_DEFER_OUT 1
 #endif
@@ -559,6 +566,9 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
       cp_async_wait_all();  // every lane reads only the slots it requested itself
       const float4 a = Q.st[0][lane], b = Q.st[1][lane];
       float4 c = Q.st[2][lane];
+#if PT_Q_PREFETCH_EARLY
+      advance();  // this lane's staging slots are free again: the next unit's rows travel during this unit's scan as well
+#endif
 #else
       const uint32_t idc = valid ? idx : n_in - 1u;  // (n_in >= 1 here) lanes past the end scan a copy of the last path
       const float4 a = __ldcs(P.in_o + idc), b = __ldcs(P.in_d + idc);
@@ -582,7 +592,9 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
       }
       ns += __popc(bs);
       nc += __popc(bc);
+#if !(PT_Q_PREFETCH && PT_Q_PREFETCH_EARLY)
       advance();  // (the staged rows of this unit are in registers / in the queue by now)
+#endif
       __syncwarp();
     }
   }
@@ -856,7 +868,7 @@ __global__ void k_accum_counts(const WfCtrl* ctrl, unsigned long long* live_tota
 }
 
 // the ray-independent part of hit_normal, once per scene: identical instructions, so identical bits
-__global__ void k_normal_table(GeomSoA g, int n_geoms, float4* tab) {
+__global__ void k_normal_table(GeomSoA g, int n_geoms, const float4* mats, float4* tab) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_geoms) return;
   const float4 f0 = g.fwd0[i], f1 = g.fwd1[i], f2 = g.fwd2[i];
@@ -876,7 +888,9 @@ __global__ void k_normal_table(GeomSoA g, int n_geoms, float4* tab) {
   }
   const f3 c = mulMV(f0, f1, f2, 0.0f, 0.0f, 0.0f, 1.0f);  // intersections.h:111: transform * (0,0,0,1)
   tab[(size_t)i * kNormalRows + 6] = make_float4(c.x, c.y, c.z, 0.0f);
-  tab[(size_t)i * kNormalRows + 7] = make_float4(0, 0, 0, 0);
+  // the row of the geom's material that decides whether a path ends here (emittance) and how it scatters
+  const int2 me = g.meta[i];
+  tab[(size_t)i * kNormalRows + kMatRow] = me.x <= 1 ? mats[4 * me.y + 3] : make_float4(0, 0, 0, 0);
 }
 
 // ---- parity entry points ----

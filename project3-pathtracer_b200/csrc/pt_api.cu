@@ -162,6 +162,11 @@ static void sym3_eigen_range(double S[3][3], double* emin, double* emax) {
   *emin = fmin(S[0][0], fmin(S[1][1], S[2][2]));
   *emax = fmax(S[0][0], fmax(S[1][1], S[2][2]));
 }
+static float round_down(double x) {  // a float <= x
+  float f = (float)x;
+  if ((double)f > x) f = nextafterf(f, -INFINITY);
+  return nextafterf(f, -INFINITY);
+}
 static float round_up(double x) {  // smallest-ish float >= x (x >= 0)
   float f = (float)x;
   if ((double)f < x) f = nextafterf(f, INFINITY);
@@ -176,6 +181,7 @@ struct HostFilter {
   // hierarchy (pt_bvh.cuh); empty when the scene is small enough for the pair scan
   std::vector<float4> nodes, leaves;
   std::vector<int2> leaf_meta;
+  int root = 0;  // reference of the hierarchy's root: node 0, or the only leaf
   float ew_c_max = 0.0f, ew_w_max = 0.0f;
 };
 static const int kBvhMinGeoms = 33;  // scenes with fewer geoms use the linear pair scan (shared memory, packed)
@@ -202,6 +208,7 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
     float k[8];      // object-space constants (classes 1, 3)
     float c[3];      // world point that inverseTransform maps to the object origin (classes 0, 2)
     float wk[6];     // class 0: Wc, Ww, Wr;  class 2: Hc.xyz, Hw.xyz
+    float wd[3];     // the DEFLATED shape's constants at w = 0 (sure-hit bound, pt_bvh.cuh): class 0: Wc'; class 2: Hd.xyz
     float ew_c, ew_w;
     double bc[3], bh[3], p1, p2;  // world AABB (centre, half extents) of the inflated shape at w = 0; pad coefficients
   };
@@ -289,6 +296,7 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
     q.ew_c = round_up(ew_c); q.ew_w = round_up(ew_w);
     // ---- world-space classes: c = the world point that A maps to the object origin ----
     q.cls = g.type == 0 ? 1 : 3;
+    q.wd[0] = q.wd[1] = q.wd[2] = -INFINITY;  // (never a sure hit)
     if (inv3(A3, Ai)) {
       double cw[3], dc = 0.0;
       for (int r = 0; r < 3; r++) {
@@ -322,6 +330,8 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
         q.wk[0] = round_up(objk[0] / lmin + 4.0 * rad * dc);
         q.wk[1] = round_up(objk[1] / lmin);
         q.wk[2] = round_up(objk[2] * (lmax / lmin) + scale * 32.0 * u);
+        // deflated: a world point within r' of c maps to within sqrt(lmax) r' of the object origin
+        q.wd[0] = round_down((0.5 - objk[0]) / lmax * (1.0 - 1e-6) - 4.0 * rad * dc);
         q.cls = 0;
       } else if (g.type == 1 && finite) {
         // world AABB of the inflated cube { x : |A (x - c)|_j <= h_j }: half extents sum_j |Ai_ij| h_j
@@ -333,7 +343,24 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
           q.wk[r] = round_up(fabs(Ai[r][0]) * objk[0] + fabs(Ai[r][1]) * objk[1] + fabs(Ai[r][2]) * objk[2] + 2.0 * dc);
           q.wk[3 + r] = round_up(fabs(Ai[r][0]) * objk[3] + fabs(Ai[r][1]) * objk[4] + fabs(Ai[r][2]) * objk[5] + scale * 16.0 * u);
         }
-        if (tight) q.cls = 2;
+        if (tight) {
+          q.cls = 2;
+          // deflated: a world AABB {|x_r| <= H'_r} INSIDE the cube deflated to half extents 1 - objk[j]:
+          // sum_r |A_jr| H'_r <= 1 - objk[j] for every object axis j (checked, with a growing shrink factor)
+          for (double eps = 1e-3; eps < 0.6; eps *= 4.0) {
+            double Hd[3];
+            bool ok = true;
+            for (int r = 0; r < 3; r++) {
+              int jd = 0;  // the object axis this world axis runs along
+              for (int j = 1; j < 3; j++) if (fabs(Ai[r][j]) > fabs(Ai[r][jd])) jd = j;
+              Hd[r] = fabs(Ai[r][jd]) * (1.0 - objk[jd]) * (1.0 - eps) - 2.0 * dc;
+              if (!(Hd[r] > 0)) ok = false;
+            }
+            for (int j = 0; j < 3 && ok; j++)
+              if (!(fabs(A3[j][0]) * Hd[0] + fabs(A3[j][1]) * Hd[1] + fabs(A3[j][2]) * Hd[2] <= (1.0 - objk[j]) * (1.0 - 1e-6))) ok = false;
+            if (ok) { for (int r = 0; r < 3; r++) q.wd[r] = round_down(Hd[r]); break; }
+          }
+        }
       }
     }
     else {  // singular inverseTransform: cannot be bounded, always visited
@@ -407,10 +434,12 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
       if (x.cls == 0) {
         L[0] = make_float4(x.c[0], x.c[1], x.c[2], x.wk[0]);
         L[1] = make_float4(x.wk[1], x.wk[2], x.ew_c, x.ew_w);
+        L[2] = make_float4(x.wd[0], 0, 0, 0);
       } else if (x.cls == 2) {
         L[0] = make_float4(x.c[0], x.c[1], x.c[2], x.ew_c);
         L[1] = make_float4(x.wk[0], x.wk[1], x.wk[2], x.ew_w);
         L[2] = make_float4(x.wk[3], x.wk[4], x.wk[5], 0);
+        L[3] = make_float4(x.wd[0], x.wd[1], x.wd[2], 0);
       } else {
         for (int t = 0; t < 3; t++) L[t] = make_float4(A[4 * t], A[4 * t + 1], A[4 * t + 2], A[4 * t + 3]);
         if (x.cls == 1) { L[3] = make_float4(x.k[0], x.k[1], x.k[2], x.ew_c); L[4] = make_float4(x.ew_w, 0, 0, 0); }
@@ -556,7 +585,9 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
           child[i] = kBvhNoChild;
           if (i < cnt) {
             int sub = 0;
-            child[i] = ref[i] >= 0 ? collapse(ref[i], sub) : ref[i];
+            // (a leaf's reference carries its filter class, so that a traversal fetches the leaf's record without
+            // waiting for its meta word: one dependent fetch less per leaf)
+            child[i] = ref[i] >= 0 ? collapse(ref[i], sub) : bvh_leaf_ref(~ref[i], per[~ref[i]].cls);
             deepest = std::max(deepest, sub);
           }
         }
@@ -580,6 +611,7 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
         N[8] = make_float4(cf[0], cf[1], cf[2], cf[3]);
         return me;
       };
+      F.root = root_ref >= 0 ? 0 : bvh_leaf_ref(~root_ref, per[~root_ref].cls);
       if (root_ref >= 0) collapse(root_ref, stack_need);
       if (getenv("PT_B200_BVH_DEBUG"))
         fprintf(stderr, "pt_b200 bvh: %d leaves, %d binary nodes, %zu wide nodes, stack need %d of %d%s\n", n, next_node.load(),
@@ -629,10 +661,10 @@ static int setup_variant(pt_context* c, int slot) {
   int per_sm = 0, per_sm_nee = 0;
   constexpr bool N = NeeOf<F, L>::value;
   if (c->mode) {
-    CU(cudaFuncSetAttribute(k_bounce_bvh<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce_bvh<F, L>, kBvhThreads, c->smem_bytes));
-    CU(cudaFuncSetAttribute(k_bounce_bvh<F, L, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_nee, k_bounce_bvh<F, L, N>, kBvhThreads, c->smem_bytes));
+    CU(cudaFuncSetAttribute(k_bounce_bvh<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bvh_smem_bytes(F)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce_bvh<F, L>, kBvhThreads, bvh_smem_bytes(F)));
+    CU(cudaFuncSetAttribute(k_bounce_bvh<F, L, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bvh_smem_bytes(F)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_nee, k_bounce_bvh<F, L, N>, kBvhThreads, bvh_smem_bytes(F)));
   } else {
     CU(cudaFuncSetAttribute(k_bounce<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce<F, L>, kBounceThreads, c->smem_bytes));
@@ -755,6 +787,7 @@ static int upload_filter(pt_context* c) {
     CU(cudaMemcpy(c->d_bvh_meta, F.leaf_meta.data(), F.leaf_meta.size() * sizeof(int2), cudaMemcpyHostToDevice));
     c->bvh.nodes = c->d_bvh_nodes; c->bvh.leaves = c->d_bvh_leaves; c->bvh.leaf_meta = c->d_bvh_meta;
     c->bvh.n_leaves = (int)F.leaf_meta.size(); c->bvh.ew_c_max = F.ew_c_max; c->bvh.ew_w_max = F.ew_w_max;
+    c->bvh.root = F.root;
   }
   return PT_OK;
 }
@@ -845,7 +878,7 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
     c->filt_cap = cap;
     c->geom_smem = filt_smem_bytes(cap);
     c->mode = mode;
-    c->smem_bytes = mode == 0 ? c->geom_smem : kBvhSmemBytes;  // k_bounce: filter geometry; k_bounce_bvh: the warps' ray pools
+    c->smem_bytes = mode == 0 ? c->geom_smem : bvh_smem_bytes(false);  // k_bounce: filter geometry (k_bounce_bvh sizes its own: bvh_smem_bytes)
     int rc;
     if ((rc = setup_variant<true, false>(c, 0))) return rc;
     if ((rc = setup_variant<true, true>(c, 1))) return rc;
@@ -1055,10 +1088,10 @@ static cudaError_t launch_bounce(pt_context* c, int slot, const BounceParams& P,
     if (nee) k_bounce_q<L, N><<<gq, kQThreads, c->q_smem_total, st>>>(P);
     else k_bounce_q<L><<<gq, kQThreads, c->q_smem_total, st>>>(P);
   } else if (c->mode) {
-    const uint32_t ctas = (n_upper + kPool * (kBvhThreads / 32) - 1) / (kPool * (kBvhThreads / 32));  // one pool per warp at least
+    const uint32_t ctas = (n_upper + kPoolMin * (kBvhThreads / 32) - 1) / (kPoolMin * (kBvhThreads / 32));  // a (smallest) pool per warp at least
     if (ctas < grid) grid = ctas ? ctas : 1;
-    if (nee) k_bounce_bvh<F, L, N><<<grid, kBvhThreads, c->smem_bytes, st>>>(P);
-    else k_bounce_bvh<F, L><<<grid, kBvhThreads, c->smem_bytes, st>>>(P);
+    if (nee) k_bounce_bvh<F, L, N><<<grid, kBvhThreads, bvh_smem_bytes(F), st>>>(P);
+    else k_bounce_bvh<F, L><<<grid, kBvhThreads, bvh_smem_bytes(F), st>>>(P);
   } else {
     const uint32_t ctas = (n_upper + kBounceThreads - 1) / kBounceThreads;  // one unit per warp at least
     if (ctas < grid) grid = ctas ? ctas : 1;
@@ -1757,3 +1790,9 @@ extern "C" int pt_reduce_to_first(pt_context* const* ctxs, int n) {
   }
   return PT_OK;
 }
+
+#ifdef PT_BVH_STACK_HIST
+extern "C" int pt_debug_sp_hist(unsigned long long* out64) {
+  return cudaMemcpyFromSymbol(out64, ptd::g_sp_hist, 64 * sizeof(unsigned long long)) == cudaSuccess ? 0 : 1;
+}
+#endif

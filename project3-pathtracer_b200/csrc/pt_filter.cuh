@@ -106,8 +106,9 @@ __device__ __forceinline__ ScanRay make_scan_ray(f3 o, f3 d, float r_scene, bool
 struct ScanBest {
   float lo1, lo2;  // smallest and second-smallest lower bound
   int k1;          // 2*pair + half of the smallest, -1 = every geom so far is a proven miss
+  float hi;        // hierarchy only (pt_bvh.cuh): smallest UPPER bound on the exact distance of a geom that is surely hit
 };
-__device__ __forceinline__ void scan_init(ScanBest& b) { b.lo1 = INFINITY; b.lo2 = INFINITY; b.k1 = -1; }
+__device__ __forceinline__ void scan_init(ScanBest& b) { b.lo1 = INFINITY; b.lo2 = INFINITY; b.k1 = -1; b.hi = INFINITY; }
 __device__ __forceinline__ void scan_take(ScanBest& b, float lo, int k) {
   lo = fmaxf(lo, 0.0f);  // also turns a NaN bound into 0 (fmaxf ignores NaN): "no information"
   const bool better = lo < b.lo1;

@@ -607,30 +607,38 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
 // traversal takes anything from a handful to hundreds of steps, and neighbouring paths stop being neighbours in space
 // after the first bounce, so a warp that walked 32 rays in lock step kept 9 of its 32 lanes busy on average
 // (profiles/r01_bvh_v1_metrics.txt).  Work decomposition here, per warp:
-//   phase 0  a ticket = a POOL of kPoolUnits x 32 consecutive paths; their rays are generated / loaded (coalesced) into
-//            the warp's slice of shared memory;
+//   a POOL of up to kPool consecutive paths is taken from the wavefront's counter (fewer towards the end of the
+//   wavefront, so that the warps finish together);
 //   phase 1  filter traversal of the pool: every lane walks one ray at a time and, when it is done, takes the next ray
-//            of the pool (lanes are refilled once kRefillMin of them are idle, so the refill code runs rarely);
-//            the result (k1, lo2) of a ray goes to shared memory;
-//   phase 2  unit by unit, all 32 lanes together: exact test of each path's candidate k1, shading, compaction --
-//            as in k_bounce.  A path whose candidate is not confirmed (the fallback, ~3 % of the paths) is NOT
-//            re-traversed on the spot -- that would occupy the warp with one or two live lanes for a whole traversal
-//            -- but DEFERRED: its index goes to a per-warp list, and whenever 32 have gathered they are run as a unit
-//            of their own through the exact traversal, shading and compaction.
+//            of the pool -- generated (depth 0) or read from the wavefront's buffers right there; lanes are refilled
+//            once kRefillMin of them are idle, so the refill code runs rarely.  The result (k1, lo2) of a ray goes to
+//            shared memory: 8 bytes per ray is all a pool costs, so it can be long -- a pool ends with a tail in which
+//            the last long traversals run alone, and that tail is paid once per pool (pools of 128 rays held in
+//            shared memory: 13.7 of 32 lanes busy; profiles/r02_bvh_notes.txt);
+//   phase 2  unit by unit, all 32 lanes together: the rays once more (generated / read, coalesced this time), exact test
+//            of each path's candidate k1, shading, compaction -- as in k_bounce.  A path whose candidate is not confirmed
+//            (~3 % of the paths) is NOT re-traversed on the spot -- that would occupy the warp with one or two live
+//            lanes for a whole traversal -- but DEFERRED: its index goes to a per-warp list, and whenever 32 have
+//            gathered they are run as a unit of their own through the retry pass (run_deferred).
 #ifndef PT_BVH_POOL_UNITS
 #define PT_BVH_POOL_UNITS 4
+#endif
+#ifndef PT_BVH_POOL_MIN_UNITS
+#define PT_BVH_POOL_MIN_UNITS 2
 #endif
 #ifndef PT_BVH_REFILL_MIN
 #define PT_BVH_REFILL_MIN 8
 #endif
-#ifndef PT_BVH_WHILE_WHILE
-#define PT_BVH_WHILE_WHILE 0
+#ifndef PT_BVH_SMEM_STACK
+#define PT_BVH_SMEM_STACK 8  // levels of a lane's traversal stack held in shared memory (pt_bvh.cuh: TravStack)
 #endif
-#ifndef PT_BVH_NODE_MIN
-#define PT_BVH_NODE_MIN 16  // the node loop goes on while at least this many lanes stand at an inner node (or no lane holds a leaf)
+#ifndef PT_BVH_SMEM_STACK_FIRST
+#define PT_BVH_SMEM_STACK_FIRST 0  // ... at depth 0, where the pool's rays live in shared memory too
 #endif
-constexpr int kBvhNodeMin = PT_BVH_NODE_MIN;
-constexpr int kPoolUnits = PT_BVH_POOL_UNITS, kPool = kPoolUnits * kUnit, kRefillMin = PT_BVH_REFILL_MIN, kDeferCap = 2 * kUnit;
+constexpr int kPoolUnits = PT_BVH_POOL_UNITS, kPool = kPoolUnits * kUnit, kPoolMin = PT_BVH_POOL_MIN_UNITS * kUnit;
+constexpr int kRefillMin = PT_BVH_REFILL_MIN, kDeferCap = 2 * kUnit;
+template <bool FIRST>
+struct BvhCfg { static constexpr int kSmemStack = FIRST ? PT_BVH_SMEM_STACK_FIRST : PT_BVH_SMEM_STACK; };
 #ifndef PT_BVH_THREADS
 #define PT_BVH_THREADS 256
 #endif
@@ -638,13 +646,20 @@ constexpr int kPoolUnits = PT_BVH_POOL_UNITS, kPool = kPoolUnits * kUnit, kRefil
 #define PT_BVH_MIN_BLOCKS 4  // 64 registers, 32 resident warps per SM: +3 % over 3 x 80 registers (the kernel waits on node fetches)
 #endif
 constexpr int kBvhThreads = PT_BVH_THREADS;
+// Depth 0 GENERATES its rays: densely, once per pool, into shared memory (generating them inside the traversal loop's
+// refill branch put the ray generator into the loop's instruction footprint: 40 % of the warps' time went to instruction
+// fetch, profiles/r02_bvh_notes.txt).  Depths >= 1 read them from the wavefront's buffers where they are needed.
+template <bool FIRST>
 struct BvhWarpSmem {
-  float4 ro[kPool];           // (origin.xyz, pixel)
-  float4 rd[kPool];           // (direction.xyz, sample)
-  float2 res[kPool];          // (lo2, bits of k1)
-  uint2 defer[kDeferCap];     // (index into the wavefront's input, unconfirmed candidate leaf) of paths waiting for the retry pass
+  float4 ro[FIRST ? kPool : 1];  // (origin.xyz, pixel)
+  float4 rd[FIRST ? kPool : 1];  // (direction.xyz, sample)
+  float2 res[kPool];             // (lo2, bits of k1) of the pool's rays
+  uint2 defer[kDeferCap];        // (index into the wavefront's input, unconfirmed candidate leaf) of paths waiting for the retry pass
+  StackEnt stk[BvhCfg<FIRST>::kSmemStack > 0 ? BvhCfg<FIRST>::kSmemStack * kUnit : 1];  // the lanes' traversal stacks, lowest levels
 };
-constexpr size_t kBvhSmemBytes = sizeof(BvhWarpSmem) * (kBvhThreads / 32);
+__host__ __device__ inline size_t bvh_smem_bytes(bool first) {
+  return (first ? sizeof(BvhWarpSmem<true>) : sizeof(BvhWarpSmem<false>)) * (kBvhThreads / 32);
+}
 
 template <bool FIRST>
 __device__ __forceinline__ void load_path(const BounceParams& P, uint32_t idx, f3& o, f3& d, uint32_t& pixel, uint32_t& sample) {
@@ -658,6 +673,14 @@ __device__ __forceinline__ void load_path(const BounceParams& P, uint32_t idx, f
     o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
     d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
   }
+}
+
+// shading + compaction of one unit of k_bounce_bvh: ONE copy of the code for the pool's units and the retry pass's units
+// (the kernel's instruction footprint is what its warps wait for at depth 0: profiles/r02_bvh_notes.txt)
+template <bool LAST, bool NEE>
+__device__ __noinline__ void shade_unit_bvh(const BounceParams& P, const DepthIO& io, uint32_t lane, bool hit, const Hit& h, f3 o, f3 d,
+                                            f3 thr, uint32_t pixel, uint32_t sample, float cos_b) {
+  shade_and_compact<LAST, false, NEE>(P, io, nullptr, lane, hit, h, o, d, thr, pixel, sample, cos_b);
 }
 
 // `n` (<= 32, warp-uniform) deferred paths, taken from the top of the warp's list (path index, unconfirmed candidate leaf).
@@ -714,41 +737,52 @@ __device__ __noinline__ void run_deferred(const BounceParams& P, const uint2* li
     atomicAdd(&P.ctrl->fallbacks, n_open);       // statistics: segments that needed the exact traversal ...
     atomicAdd(&P.ctrl->retries, n - n_open);     // ... and segments the retry pass settled
   }
-  shade_and_compact<LAST, false, NEE>(P, io, nullptr, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, cos_b);
+  shade_unit_bvh<LAST, NEE>(P, io, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, cos_b);
 }
 
 template <bool FIRST, bool LAST, bool NEE = false>
 __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(const __grid_constant__ BounceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31u;
-  BvhWarpSmem& S = reinterpret_cast<BvhWarpSmem*>(smem_raw)[threadIdx.x >> 5];
+  BvhWarpSmem<FIRST>& S = reinterpret_cast<BvhWarpSmem<FIRST>*>(smem_raw)[threadIdx.x >> 5];
+  constexpr int kSmemStack = BvhCfg<FIRST>::kSmemStack;
   const DepthIO io = depth_io(P);
 
   const uint32_t n_in = FIRST ? P.n_first : P.ctrl->count[P.depth];
   if (FIRST && blockIdx.x == 0 && threadIdx.x == 0) P.ctrl->count[0] = n_in;
-  uint32_t* const ticket = &P.ctrl->tile_ctr[P.depth];
+  uint32_t* const ticket = &P.ctrl->tile_ctr[P.depth];  // (counts PATHS here: first path nobody has taken yet)
+  const uint32_t n_warps = gridDim.x * (kBvhThreads / 32);
   uint32_t n_defer = 0;  // warp-uniform
 
-  uint32_t next_raw = 0;  // lane 0: the ticket taken ahead of time
-  if (lane == 0) next_raw = atom_add_u32(ticket, 1u);
-
   for (;;) {
-    const uint64_t base64 = (uint64_t)__shfl_sync(0xffffffffu, next_raw, 0) * kPool;
-    if (base64 >= n_in) break;
-    const uint32_t base = (uint32_t)base64;
-    if (lane == 0) next_raw = atom_add_u32(ticket, 1u);
-    const uint32_t n_pool = min((uint32_t)kPool, n_in - base);
-
-    // ---- phase 0: the pool's rays ----
-#pragma unroll 1
-    for (uint32_t j = lane; j < n_pool; j += kUnit) {
-      f3 o, d;
-      uint32_t pixel, sample;
-      load_path<FIRST>(P, base + j, o, d, pixel, sample);
-      S.ro[j] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
-      S.rd[j] = make_float4(d.x, d.y, d.z, __uint_as_float(sample));
+    // ---- the next pool: kPool paths while plenty are left, fewer (down to kPoolMin) when the wavefront runs out ----
+    uint32_t base = 0, chunk = 0;
+    if (lane == 0) {
+      const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(ticket);  // (a little stale: only sizes the chunk)
+      chunk = kPool;
+      if (seen < n_in) {
+        const uint32_t fair = ((n_in - seen) / (2u * n_warps)) & ~(kUnit - 1u);
+        chunk = min((uint32_t)kPool, max((uint32_t)kPoolMin, fair));
+      }
+      base = atom_add_u32(ticket, chunk);
     }
-    __syncwarp();
+    base = __shfl_sync(0xffffffffu, base, 0);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if (base >= n_in) break;
+    const uint32_t n_pool = min(chunk, n_in - base);
+
+    // ---- phase 0 (depth 0): the pool's rays ----
+    if (FIRST) {
+#pragma unroll 1
+      for (uint32_t j = lane; j < n_pool; j += kUnit) {
+        f3 o, d;
+        uint32_t pixel, sample;
+        load_path<true>(P, base + j, o, d, pixel, sample);
+        S.ro[j] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
+        S.rd[j] = make_float4(d.x, d.y, d.z, __uint_as_float(sample));
+      }
+      __syncwarp();
+    }
 
     // ---- phase 1: filter traversal; idle lanes take the next rays of the pool ----
     {
@@ -757,9 +791,10 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
       ScanRay r;
       TravRay tr;
       ScanBest best;
-      Hit unused;
-      int stack[kBvhStack];
-      int sp = 0, cur = 0;
+      StackEnt ov[kBvhStack - kSmemStack];
+      TravStack<kSmemStack> st;
+      st.sm = S.stk + lane; st.ov = ov;
+      int cur = 0;
       r = make_scan_ray(mk(0, 0, 0), mk(0, 0, 1), 0.0f, true);
       tr = make_trav_ray(P.bvh, r);
       scan_init(best);
@@ -770,42 +805,34 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
             const uint32_t j = next + __popc(idle & ((1u << lane) - 1u));
             if (ray < 0 && j < n_pool) {
               ray = (int)j;
-              const float4 a = S.ro[j], b = S.rd[j];
-              r = make_scan_ray(mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), P.filt.r_scene, true);
+              f3 o, d;
+              if (FIRST) {
+                const float4 a = S.ro[j], b = S.rd[j];
+                o = mk(a.x, a.y, a.z); d = mk(b.x, b.y, b.z);
+              } else {
+                uint32_t pixel, sample;
+                load_path<false>(P, base + j, o, d, pixel, sample);
+              }
+              r = make_scan_ray(o, d, P.filt.r_scene, true);
               tr = make_trav_ray(P.bvh, r);
               scan_init(best);
-              sp = 0;
+              st.sp = 0;
               cur = bvh_root(P.bvh);
             }
             next += __popc(idle);
+            // the rays the next refill will take: on their way into L1 meanwhile (4 lines each of origins and directions)
+            if (!FIRST && lane < 8u) {
+              const uint32_t q = base + next + (lane & 3u) * 8u;
+              if (q < n_in) asm volatile("prefetch.global.L1 [%0];" ::"l"((lane < 4u ? P.in_o : P.in_d) + q));
+            }
           } else if (idle == 0xffffffffu) {
             break;
           }
         }
-#if PT_BVH_WHILE_WHILE
-        // "while-while" (measured, not adopted): the lanes that stand at an inner node keep descending together until
-        // fewer than kBvhNodeMin of them are left, then the leaves are tested by all the lanes that hold one.  The kernel
-        // waits on node fetches, not on issue slots: lanes parked at a leaf cost more than the divergence saved
-        // (10k-object config: 1.66 / 2.01 / 2.06 Gseg/s at kBvhNodeMin 1 / 8 / 16 against 2.16 with mixed steps).
-        while (__popc(__ballot_sync(0xffffffffu, ray >= 0 && cur >= 0)) >= kBvhNodeMin) {
-          if (ray >= 0 && cur >= 0 && !node_visit<false>(P.bvh, r, tr, best, unused, cur, sp, stack)) cur = sp ? stack[--sp] : kBvhDone;
-        }
-        if (kBvhNodeMin > 1 && ray >= 0 && cur >= 0) {
-          if (!node_visit<false>(P.bvh, r, tr, best, unused, cur, sp, stack)) cur = sp ? stack[--sp] : kBvhDone;
-        } else if (ray >= 0 && cur < 0 && cur != kBvhDone) {
-          leaf_visit<false>(P.bvh, P.g, r, best, unused, cur);
-          cur = sp ? stack[--sp] : kBvhDone;
-        }
-        if (ray >= 0 && cur == kBvhDone) {
+        if (ray >= 0 && !filter_step(P.bvh, r, tr, best, cur, st)) {
           S.res[ray] = make_float2(best.lo2, __int_as_float(best.k1));
           ray = -1;
         }
-#else
-        if (ray >= 0 && !trav_step<false>(P.bvh, P.g, r, tr, best, unused, cur, sp, stack)) {
-          S.res[ray] = make_float2(best.lo2, __int_as_float(best.k1));
-          ray = -1;
-        }
-#endif
       }
     }
     __syncwarp();
@@ -823,10 +850,14 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
       bool defer = false;
       int k1 = -1;
       if (valid) {
-        const float4 a = S.ro[j], b = S.rd[j];
+        if (FIRST) {
+          const float4 a = S.ro[j], b = S.rd[j];
+          o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
+          d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
+        } else {
+          load_path<false>(P, base + j, o, d, pixel, sample);
+        }
         const float2 res = S.res[j];
-        o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
-        d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
         if (!FIRST) { const float4 c = __ldcs(P.in_t + base + j); thr = mk(c.x, c.y, c.z); cos_b = NEE ? c.w : 0.0f; }
         k1 = __float_as_int(res.y);
         if (k1 >= 0) defer = !confirm_candidate(k1, res.x, P.bvh, P.g, o, d, h);  // k1 < 0: every geom is a proven miss
@@ -835,7 +866,7 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
       PT_CHECK(n_defer + __popc(dmask) <= (uint32_t)kDeferCap);
       if (defer) S.defer[n_defer + __popc(dmask & ((1u << lane) - 1u))] = make_uint2(base + j, (uint32_t)k1);
       n_defer += __popc(dmask);
-      shade_and_compact<LAST, false, NEE>(P, io, nullptr, lane, valid && !defer && h.id >= 0, h, o, d, thr, pixel, sample, cos_b);
+      shade_unit_bvh<LAST, NEE>(P, io, lane, valid && !defer && h.id >= 0, h, o, d, thr, pixel, sample, cos_b);
       if (n_defer >= kUnit) {
         __syncwarp();
         n_defer -= kUnit;
@@ -843,6 +874,7 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
         __syncwarp();
       }
     }
+    __syncwarp();  // (the pool's results are consumed: the next pool may overwrite them)
   }
   if (n_defer) {
     __syncwarp();

@@ -94,7 +94,7 @@ struct pt_context {
   // Two wavefronts are in flight at a time, each on its own internal stream with its own path-state buffers and control
   // block: the tail of one wavefront's launch (its last units) overlaps the head of the other's instead of idling SMs.
   static const int kSlots = 2;
-  float4* d_state = nullptr; // per slot: 6 arrays of wf_capacity float4: o0 d0 t0 o1 d1 t1
+  float4* d_state = nullptr; // per slot (state_bytes): 6 arrays of wf_capacity float4: o0 d0 t0 o1 d1 t1, then wf_capacity float2 (hierarchy results)
   WfCtrl* d_ctrl = nullptr;  // per slot
   int n_slots = kSlots;      // slots in use (1 for frames whose accumulation image alone fills the L2)
   cudaStream_t wf_stream[kSlots] = {nullptr, nullptr};
@@ -660,11 +660,11 @@ template <bool F, bool L>
 static int setup_variant(pt_context* c, int slot) {
   int per_sm = 0, per_sm_nee = 0;
   constexpr bool N = NeeOf<F, L>::value;
-  if (c->mode) {
-    CU(cudaFuncSetAttribute(k_bounce_bvh<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bvh_smem_bytes(F)));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce_bvh<F, L>, kBvhThreads, bvh_smem_bytes(F)));
-    CU(cudaFuncSetAttribute(k_bounce_bvh<F, L, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bvh_smem_bytes(F)));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_nee, k_bounce_bvh<F, L, N>, kBvhThreads, bvh_smem_bytes(F)));
+  if (c->mode) {  // (many geoms: one kernel for every depth, primary rays come from k_raygen_wf)
+    CU(cudaFuncSetAttribute(k_bounce_bvh<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBvhSmemBytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce_bvh<L>, kBvhThreads, kBvhSmemBytes));
+    CU(cudaFuncSetAttribute(k_bounce_bvh<L, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBvhSmemBytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_nee, k_bounce_bvh<L, N>, kBvhThreads, kBvhSmemBytes));
   } else {
     CU(cudaFuncSetAttribute(k_bounce<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce<F, L>, kBounceThreads, c->smem_bytes));
@@ -878,7 +878,7 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
     c->filt_cap = cap;
     c->geom_smem = filt_smem_bytes(cap);
     c->mode = mode;
-    c->smem_bytes = mode == 0 ? c->geom_smem : bvh_smem_bytes(false);  // k_bounce: filter geometry (k_bounce_bvh sizes its own: bvh_smem_bytes)
+    c->smem_bytes = mode == 0 ? c->geom_smem : kBvhSmemBytes;  // k_bounce: filter geometry; k_bounce_bvh: pool results, retry list, stacks
     int rc;
     if ((rc = setup_variant<true, false>(c, 0))) return rc;
     if ((rc = setup_variant<true, true>(c, 1))) return rc;
@@ -894,6 +894,9 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
   return PT_OK;
 }
 
+// bytes of one wavefront slot: two ping-pong buffers of three float4 arrays, and the hierarchy kernel's per-path results
+// (lo2, candidate leaf: k_bounce_bvh keeps them in HBM so that a warp's pool of rays can be as long as it likes)
+static size_t state_bytes(uint64_t cap) { return (((size_t)cap * (6 * sizeof(float4) + sizeof(float2))) + 255) & ~(size_t)255; }
 static int alloc_wavefront(pt_context* c, uint64_t max_paths) {
   uint64_t spp = max_paths / c->npix;
   if (spp < 1) spp = 1;
@@ -918,10 +921,10 @@ static int alloc_wavefront(pt_context* c, uint64_t max_paths) {
   const int old_slots = c->n_slots;
   if (c->d_state) CU(cudaFree(c->d_state));
   c->d_state = nullptr; c->wf_capacity = 0;
-  if (cudaMalloc(&c->d_state, (size_t)n_slots * 6 * cap * sizeof(float4)) != cudaSuccess) {
+  if (cudaMalloc(&c->d_state, (size_t)n_slots * state_bytes(cap)) != cudaSuccess) {
     const cudaError_t e = cudaGetLastError();
     c->d_state = nullptr;
-    if (old_cap && cudaMalloc(&c->d_state, (size_t)old_slots * 6 * old_cap * sizeof(float4)) == cudaSuccess) {
+    if (old_cap && cudaMalloc(&c->d_state, (size_t)old_slots * state_bytes(old_cap)) == cudaSuccess) {
       c->wf_capacity = old_cap; c->n_slots = old_slots;
     } else {
       cudaGetLastError();
@@ -1088,10 +1091,14 @@ static cudaError_t launch_bounce(pt_context* c, int slot, const BounceParams& P,
     if (nee) k_bounce_q<L, N><<<gq, kQThreads, c->q_smem_total, st>>>(P);
     else k_bounce_q<L><<<gq, kQThreads, c->q_smem_total, st>>>(P);
   } else if (c->mode) {
+    if (F) {  // primary rays into the wavefront's input buffers
+      const uint32_t blocks = (n_upper + 255u) / 256u, most = (uint32_t)c->sm_count * 8u;
+      k_raygen_wf<<<blocks < most ? (blocks ? blocks : 1u) : most, 256, 0, st>>>(P);
+    }
     const uint32_t ctas = (n_upper + kPoolMin * (kBvhThreads / 32) - 1) / (kPoolMin * (kBvhThreads / 32));  // a (smallest) pool per warp at least
     if (ctas < grid) grid = ctas ? ctas : 1;
-    if (nee) k_bounce_bvh<F, L, N><<<grid, kBvhThreads, bvh_smem_bytes(F), st>>>(P);
-    else k_bounce_bvh<F, L><<<grid, kBvhThreads, bvh_smem_bytes(F), st>>>(P);
+    if (nee) k_bounce_bvh<L, N><<<grid, kBvhThreads, kBvhSmemBytes, st>>>(P);
+    else k_bounce_bvh<L><<<grid, kBvhThreads, kBvhSmemBytes, st>>>(P);
   } else {
     const uint32_t ctas = (n_upper + kBounceThreads - 1) / kBounceThreads;  // one unit per warp at least
     if (ctas < grid) grid = ctas ? ctas : 1;
@@ -1142,7 +1149,7 @@ static int render_into(pt_context* c, uint32_t first_sample, uint32_t n_samples,
     NvtxRange nvtx_wf("wavefront");
     const int sl = (int)(wf % (uint64_t)slots_used);
     cudaStream_t st = forked ? c->wf_stream[sl] : stream0;
-    float4* S = c->d_state + (size_t)sl * 6 * cap;
+    float4* S = reinterpret_cast<float4*>(reinterpret_cast<char*>(c->d_state) + (size_t)sl * state_bytes(cap));
     WfCtrl* ctrl = c->d_ctrl + sl;
     const uint32_t ns = (n_samples - s0 < spp_wf) ? (n_samples - s0) : spp_wf;
     const uint32_t n_first = ns * band;
@@ -1157,6 +1164,7 @@ static int render_into(pt_context* c, uint32_t first_sample, uint32_t n_samples,
       P.normals = c->d_normals;
       P.filt = c->filt; P.filt_cap = c->filt_cap;
       P.bvh = c->bvh;
+      P.bvh_res = reinterpret_cast<float2*>(S + 6 * cap);
       P.mats = c->d_mats;
       P.lights = c->d_lights; P.n_lights = c->n_lights; P.light_k = c->d_light_k;
       P.cam = c->cam;

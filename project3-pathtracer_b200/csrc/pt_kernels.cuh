@@ -102,6 +102,7 @@ struct BounceParams {
   FiltSoA filt;                      // filter geometry (pt_filter.cuh): pairs of geoms, four classes
   int filt_cap;                      // pairs that fit in shared memory
   BvhSoA bvh;                        // hierarchy over the same filter tests for scenes with many geoms (pt_bvh.cuh)
+  float2* bvh_res;                   // k_bounce_bvh: per path of the wavefront (lo2, bits of the candidate leaf k1), between its two phases
   const float4* mats;                // 4 float4 per material
   const float4* lights;              // direct light sampling: 3 float4 per light (E.xyz | geom) (th0..th3) (th4, type, K, -)
   const float* light_k;              // per geom: K = area * n_lights / pi of a light, 0 otherwise (balance heuristic at emissive hits)
@@ -621,24 +622,19 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
 //            lanes for a whole traversal -- but DEFERRED: its index goes to a per-warp list, and whenever 32 have
 //            gathered they are run as a unit of their own through the retry pass (run_deferred).
 #ifndef PT_BVH_POOL_UNITS
-#define PT_BVH_POOL_UNITS 4
+#define PT_BVH_POOL_UNITS 32
 #endif
 #ifndef PT_BVH_POOL_MIN_UNITS
-#define PT_BVH_POOL_MIN_UNITS 2
+#define PT_BVH_POOL_MIN_UNITS 4
 #endif
 #ifndef PT_BVH_REFILL_MIN
 #define PT_BVH_REFILL_MIN 8
 #endif
 #ifndef PT_BVH_SMEM_STACK
-#define PT_BVH_SMEM_STACK 8  // levels of a lane's traversal stack held in shared memory (pt_bvh.cuh: TravStack)
-#endif
-#ifndef PT_BVH_SMEM_STACK_FIRST
-#define PT_BVH_SMEM_STACK_FIRST 0  // ... at depth 0, where the pool's rays live in shared memory too
+#define PT_BVH_SMEM_STACK 0  // levels of a lane's traversal stack held in shared memory (pt_bvh.cuh: TravStack)
 #endif
 constexpr int kPoolUnits = PT_BVH_POOL_UNITS, kPool = kPoolUnits * kUnit, kPoolMin = PT_BVH_POOL_MIN_UNITS * kUnit;
-constexpr int kRefillMin = PT_BVH_REFILL_MIN, kDeferCap = 2 * kUnit;
-template <bool FIRST>
-struct BvhCfg { static constexpr int kSmemStack = FIRST ? PT_BVH_SMEM_STACK_FIRST : PT_BVH_SMEM_STACK; };
+constexpr int kRefillMin = PT_BVH_REFILL_MIN, kDeferCap = 2 * kUnit, kSmemStack = PT_BVH_SMEM_STACK;
 #ifndef PT_BVH_THREADS
 #define PT_BVH_THREADS 256
 #endif
@@ -646,33 +642,38 @@ struct BvhCfg { static constexpr int kSmemStack = FIRST ? PT_BVH_SMEM_STACK_FIRS
 #define PT_BVH_MIN_BLOCKS 4  // 64 registers, 32 resident warps per SM: +3 % over 3 x 80 registers (the kernel waits on node fetches)
 #endif
 constexpr int kBvhThreads = PT_BVH_THREADS;
-// Depth 0 GENERATES its rays: densely, once per pool, into shared memory (generating them inside the traversal loop's
-// refill branch put the ray generator into the loop's instruction footprint: 40 % of the warps' time went to instruction
-// fetch, profiles/r02_bvh_notes.txt).  Depths >= 1 read them from the wavefront's buffers where they are needed.
-template <bool FIRST>
 struct BvhWarpSmem {
-  float4 ro[FIRST ? kPool : 1];  // (origin.xyz, pixel)
-  float4 rd[FIRST ? kPool : 1];  // (direction.xyz, sample)
-  float2 res[kPool];             // (lo2, bits of k1) of the pool's rays
   uint2 defer[kDeferCap];        // (index into the wavefront's input, unconfirmed candidate leaf) of paths waiting for the retry pass
-  StackEnt stk[BvhCfg<FIRST>::kSmemStack > 0 ? BvhCfg<FIRST>::kSmemStack * kUnit : 1];  // the lanes' traversal stacks, lowest levels
+  StackEnt stk[kSmemStack > 0 ? kSmemStack * kUnit : 1];  // the lanes' traversal stacks, lowest levels
 };
-__host__ __device__ inline size_t bvh_smem_bytes(bool first) {
-  return (first ? sizeof(BvhWarpSmem<true>) : sizeof(BvhWarpSmem<false>)) * (kBvhThreads / 32);
+constexpr size_t kBvhSmemBytes = sizeof(BvhWarpSmem) * (kBvhThreads / 32);
+
+// Depth 0 of a many-geom scene: the primary rays are GENERATED by a kernel of their own into the wavefront's input
+// buffers (free at depth 0) and k_bounce_bvh then traces every depth alike.  96 bytes of HBM traffic per path -- 1.5 % of
+// what the wavefront takes -- buy a traversal loop without the ray generator in its instruction footprint (generated in
+// the loop's refill branch: 40 % of the stall samples were instruction fetches) and long pools at depth 0 as well.
+__global__ void __launch_bounds__(256) k_raygen_wf(const __grid_constant__ BounceParams P) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) P.ctrl->count[0] = P.n_first;
+  float4* const wo = const_cast<float4*>(P.in_o);
+  float4* const wd = const_cast<float4*>(P.in_d);
+  float4* const wt = const_cast<float4*>(P.in_t);
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P.n_first; idx += gridDim.x * blockDim.x) {
+    PT_CHECK(idx < P.cap);
+    const uint32_t si = fastdiv(idx, P.div_band);
+    const uint32_t pixel = P.pix0 + (idx - si * P.band), sample = P.first_sample + si;
+    f3 o, d;
+    raygen(P.cam, P.keys, pixel, sample, o, d);
+    wo[idx] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
+    wd[idx] = make_float4(d.x, d.y, d.z, __uint_as_float(sample));
+    wt[idx] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);  // throughput 1, no diffuse bounce behind the path
+  }
 }
 
-template <bool FIRST>
+// a path of the wavefront's input: ray, pixel, sample
 __device__ __forceinline__ void load_path(const BounceParams& P, uint32_t idx, f3& o, f3& d, uint32_t& pixel, uint32_t& sample) {
-  if (FIRST) {
-    const uint32_t si = fastdiv(idx, P.div_band);
-    pixel = P.pix0 + (idx - si * P.band);
-    sample = P.first_sample + si;
-    raygen(P.cam, P.keys, pixel, sample, o, d);
-  } else {
-    const float4 a = __ldg(P.in_o + idx), b = __ldg(P.in_d + idx);
-    o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
-    d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
-  }
+  const float4 a = __ldg(P.in_o + idx), b = __ldg(P.in_d + idx);
+  o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
+  d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
 }
 
 // shading + compaction of one unit of k_bounce_bvh: ONE copy of the code for the pool's units and the retry pass's units
@@ -693,7 +694,7 @@ __device__ __noinline__ void shade_unit_bvh(const BounceParams& P, const DepthIO
 // the way) goes through the exact traversal.  The retry costs one ordinary traversal and two exact tests at full warp width
 // where the exact traversal tests every candidate leaf along the ray exactly: 15 % of the 10 000-geom config's time went
 // there for 2.6 % of its segments.
-template <bool FIRST, bool LAST, bool NEE>
+template <bool LAST, bool NEE>
 __device__ __noinline__ void run_deferred(const BounceParams& P, const uint2* list, uint32_t n) {
   const uint32_t lane = threadIdx.x & 31u;
   const DepthIO io = depth_io(P);
@@ -708,8 +709,8 @@ __device__ __noinline__ void run_deferred(const BounceParams& P, const uint2* li
     const uint2 ent = list[lane];
     const uint32_t idx = ent.x;
     const int k1 = (int)ent.y;
-    load_path<FIRST>(P, idx, o, d, pixel, sample);
-    if (!FIRST) { const float4 c = __ldg(P.in_t + idx); thr = mk(c.x, c.y, c.z); cos_b = NEE ? c.w : 0.0f; }
+    load_path(P, idx, o, d, pixel, sample);
+    { const float4 c = __ldg(P.in_t + idx); thr = mk(c.x, c.y, c.z); cos_b = NEE ? c.w : 0.0f; }
     const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene, true);
     Hit e1, e2, unused;
     const bool hit1 = exact_leaf(k1, P.bvh, P.g, o, d, e1);
@@ -740,16 +741,14 @@ __device__ __noinline__ void run_deferred(const BounceParams& P, const uint2* li
   shade_unit_bvh<LAST, NEE>(P, io, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, cos_b);
 }
 
-template <bool FIRST, bool LAST, bool NEE = false>
+template <bool LAST, bool NEE = false>
 __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(const __grid_constant__ BounceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31u;
-  BvhWarpSmem<FIRST>& S = reinterpret_cast<BvhWarpSmem<FIRST>*>(smem_raw)[threadIdx.x >> 5];
-  constexpr int kSmemStack = BvhCfg<FIRST>::kSmemStack;
+  BvhWarpSmem& S = reinterpret_cast<BvhWarpSmem*>(smem_raw)[threadIdx.x >> 5];
   const DepthIO io = depth_io(P);
 
-  const uint32_t n_in = FIRST ? P.n_first : P.ctrl->count[P.depth];
-  if (FIRST && blockIdx.x == 0 && threadIdx.x == 0) P.ctrl->count[0] = n_in;
+  const uint32_t n_in = P.ctrl->count[P.depth];  // (depth 0: set by k_raygen_wf)
   uint32_t* const ticket = &P.ctrl->tile_ctr[P.depth];  // (counts PATHS here: first path nobody has taken yet)
   const uint32_t n_warps = gridDim.x * (kBvhThreads / 32);
   uint32_t n_defer = 0;  // warp-uniform
@@ -770,19 +769,6 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
     chunk = __shfl_sync(0xffffffffu, chunk, 0);
     if (base >= n_in) break;
     const uint32_t n_pool = min(chunk, n_in - base);
-
-    // ---- phase 0 (depth 0): the pool's rays ----
-    if (FIRST) {
-#pragma unroll 1
-      for (uint32_t j = lane; j < n_pool; j += kUnit) {
-        f3 o, d;
-        uint32_t pixel, sample;
-        load_path<true>(P, base + j, o, d, pixel, sample);
-        S.ro[j] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
-        S.rd[j] = make_float4(d.x, d.y, d.z, __uint_as_float(sample));
-      }
-      __syncwarp();
-    }
 
     // ---- phase 1: filter traversal; idle lanes take the next rays of the pool ----
     {
@@ -806,13 +792,8 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
             if (ray < 0 && j < n_pool) {
               ray = (int)j;
               f3 o, d;
-              if (FIRST) {
-                const float4 a = S.ro[j], b = S.rd[j];
-                o = mk(a.x, a.y, a.z); d = mk(b.x, b.y, b.z);
-              } else {
-                uint32_t pixel, sample;
-                load_path<false>(P, base + j, o, d, pixel, sample);
-              }
+              uint32_t pixel, sample;
+              load_path(P, base + j, o, d, pixel, sample);
               r = make_scan_ray(o, d, P.filt.r_scene, true);
               tr = make_trav_ray(P.bvh, r);
               scan_init(best);
@@ -821,7 +802,7 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
             }
             next += __popc(idle);
             // the rays the next refill will take: on their way into L1 meanwhile (4 lines each of origins and directions)
-            if (!FIRST && lane < 8u) {
+            if (lane < 8u) {
               const uint32_t q = base + next + (lane & 3u) * 8u;
               if (q < n_in) asm volatile("prefetch.global.L1 [%0];" ::"l"((lane < 4u ? P.in_o : P.in_d) + q));
             }
@@ -829,8 +810,19 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
             break;
           }
         }
+#ifdef PT_BVH_STACK_HIST
+        {
+          const uint32_t act = __ballot_sync(0xffffffffu, ray >= 0), atn = __ballot_sync(0xffffffffu, ray >= 0 && cur >= 0);
+          if (lane == 0) {
+            atomicAdd(&g_sp_hist[45], (unsigned long long)__popc(act));
+            atomicAdd(&g_sp_hist[46], 1ull);
+            if (next >= n_pool) { atomicAdd(&g_sp_hist[47], 1ull); atomicAdd(&g_sp_hist[48], (unsigned long long)__popc(act)); }
+            atomicAdd(&g_sp_hist[49], (unsigned long long)__popc(atn));
+          }
+        }
+#endif
         if (ray >= 0 && !filter_step(P.bvh, r, tr, best, cur, st)) {
-          S.res[ray] = make_float2(best.lo2, __int_as_float(best.k1));
+          P.bvh_res[base + (uint32_t)ray] = make_float2(best.lo2, __int_as_float(best.k1));
           ray = -1;
         }
       }
@@ -850,15 +842,9 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
       bool defer = false;
       int k1 = -1;
       if (valid) {
-        if (FIRST) {
-          const float4 a = S.ro[j], b = S.rd[j];
-          o = mk(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
-          d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
-        } else {
-          load_path<false>(P, base + j, o, d, pixel, sample);
-        }
-        const float2 res = S.res[j];
-        if (!FIRST) { const float4 c = __ldcs(P.in_t + base + j); thr = mk(c.x, c.y, c.z); cos_b = NEE ? c.w : 0.0f; }
+        load_path(P, base + j, o, d, pixel, sample);
+        const float2 res = P.bvh_res[base + j];  // (written by this warp: ordered by the __syncwarp above)
+        { const float4 c = __ldcs(P.in_t + base + j); thr = mk(c.x, c.y, c.z); cos_b = NEE ? c.w : 0.0f; }
         k1 = __float_as_int(res.y);
         if (k1 >= 0) defer = !confirm_candidate(k1, res.x, P.bvh, P.g, o, d, h);  // k1 < 0: every geom is a proven miss
       }
@@ -870,7 +856,7 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
       if (n_defer >= kUnit) {
         __syncwarp();
         n_defer -= kUnit;
-        run_deferred<FIRST, LAST, NEE>(P, S.defer + n_defer, kUnit);
+        run_deferred<LAST, NEE>(P, S.defer + n_defer, kUnit);
         __syncwarp();
       }
     }
@@ -878,7 +864,7 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
   }
   if (n_defer) {
     __syncwarp();
-    run_deferred<FIRST, LAST, NEE>(P, S.defer, n_defer);
+    run_deferred<LAST, NEE>(P, S.defer, n_defer);
   }
 }
 

@@ -92,7 +92,7 @@ int pt_context_destroy(pt_context* ctx);
 int pt_update_scene(pt_context* ctx, const pt_static_geom* geoms, int n_geoms, const pt_material* materials,
                     int n_materials, const pt_camera_data* cam, const pt_lens* lens);
 /* upper bound on paths in flight per wavefront (rounded down to whole samples of the frame, at least one).
- * Default: 16 Mi paths. Path state costs 208 bytes of HBM per path of capacity: two wavefronts are in flight at a time
+ * Default: 16 Mi paths. Path state costs 224 bytes of HBM per path of capacity: two wavefronts are in flight at a time
  * (on two internal streams, so that the tail of one overlaps the head of the other), each with two ping-pong buffers
  * of 3 float4. */
 int pt_set_wavefront_paths(pt_context* ctx, uint64_t max_paths);

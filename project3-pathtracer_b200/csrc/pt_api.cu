@@ -94,7 +94,7 @@ struct pt_context {
   // Two wavefronts are in flight at a time, each on its own internal stream with its own path-state buffers and control
   // block: the tail of one wavefront's launch (its last units) overlaps the head of the other's instead of idling SMs.
   static const int kSlots = 2;
-  float4* d_state = nullptr; // per slot (state_bytes): 6 arrays of wf_capacity float4: o0 d0 t0 o1 d1 t1, then wf_capacity float2 (hierarchy results)
+  float4* d_state = nullptr; // per slot (state_bytes): 6 arrays of wf_capacity float4: o0 d0 t0 o1 d1 t1, then wf_capacity float4 (hierarchy results)
   WfCtrl* d_ctrl = nullptr;  // per slot
   int n_slots = kSlots;      // slots in use (1 for frames whose accumulation image alone fills the L2)
   cudaStream_t wf_stream[kSlots] = {nullptr, nullptr};
@@ -895,8 +895,8 @@ static int upload_scene(pt_context* c, const pt_static_geom* geoms, int n_geoms,
 }
 
 // bytes of one wavefront slot: two ping-pong buffers of three float4 arrays, and the hierarchy kernel's per-path results
-// (lo2, candidate leaf: k_bounce_bvh keeps them in HBM so that a warp's pool of rays can be as long as it likes)
-static size_t state_bytes(uint64_t cap) { return (((size_t)cap * (6 * sizeof(float4) + sizeof(float2))) + 255) & ~(size_t)255; }
+// (two candidate leaves and two bounds: k_bounce_bvh keeps them in HBM so that a warp's pool of rays can be as long as it likes)
+static size_t state_bytes(uint64_t cap) { return (((size_t)cap * (7 * sizeof(float4))) + 255) & ~(size_t)255; }
 static int alloc_wavefront(pt_context* c, uint64_t max_paths) {
   uint64_t spp = max_paths / c->npix;
   if (spp < 1) spp = 1;
@@ -1164,7 +1164,7 @@ static int render_into(pt_context* c, uint32_t first_sample, uint32_t n_samples,
       P.normals = c->d_normals;
       P.filt = c->filt; P.filt_cap = c->filt_cap;
       P.bvh = c->bvh;
-      P.bvh_res = reinterpret_cast<float2*>(S + 6 * cap);
+      P.bvh_res = S + 6 * cap;
       P.mats = c->d_mats;
       P.lights = c->d_lights; P.n_lights = c->n_lights; P.light_k = c->d_light_k;
       P.cam = c->cam;

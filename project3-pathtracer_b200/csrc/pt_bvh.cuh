@@ -10,10 +10,16 @@
 //     it at w = 0; the w- and distance-dependent part of the inflation is added per ray as a pad
 //     P1*w + P2*D^2 (P1, P2 = maxima over the subtree, D = largest distance from the origin to the box), so "the ray
 //     misses the padded box" implies "the filter proves a miss for every geom below".
-//   * Pass 1 (bvh_scan) computes the same (lo1, k1, lo2) as the linear scan would over the geoms it visits; a child is
-//     skipped if its box's entry distance minus the largest world slack is >= lo2 -- nothing below it can change k1
-//     or lower lo2.  The exact test of k1 then decides as usual (resolve in pt_kernels.cuh).
-//   * Pass 2 (the fallback, a few per cent of the rays) is the exact scan restricted to the filter's candidates: every
+//   * Pass 1 (the filter traversal) keeps the THREE smallest lower bounds and the two geoms k1, k2 they belong to; a
+//     child is skipped if its box's entry distance minus the largest world slack is >= lo3 (nothing below it can change
+//     any of them) or > hi, the smallest upper bound of a geom that is SURELY hit (leaf_filter_rows).  The exact test of
+//     k1 decides as usual if it reports a hit closer than lo2; otherwise the exact test of k2 joins in, and the closer
+//     of the two exact results is the closest hit if it is closer than lo3 -- every other geom is a proven miss or no
+//     closer than its bound >= lo3 (bvh_phase2 in pt_kernels.cuh; the parity entry points below use k1 and lo2 only).
+//     Why two candidates: the conservative bound of a small distant sphere is several times its radius (the
+//     reference's own cancellation error), so the nearest candidate is often a near miss; settling those with a second
+//     traversal that leaves k1 out cost 18 % of the 10 000-geom config's time for 2.5 % of its segments.
+//   * Pass 2 (the fallback, ~0.1 % of the rays) is the exact scan restricted to the filter's candidates: every
 //     candidate leaf whose bound does not exceed the best exact distance so far goes through exact_hit; smaller
 //     distance wins, ties go to the lower geom index (the index-order rule of the specification, applied explicitly
 //     because the traversal order is not the index order).  k_bounce_bvh collects the rays that need it and runs them
@@ -209,13 +215,13 @@ __device__ __forceinline__ TravRay make_trav_ray(const BvhSoA& B, const ScanRay&
 __device__ __forceinline__ int bvh_root(const BvhSoA& B) { return B.root; }
 
 // can anything below a box entered at parameter `e` still matter?
-//   filter pass: no if its best possible bound is >= lo2 (it changes neither k1 nor lo2) or > hi (a geom that is surely
-//                hit lies closer than everything in the box: pt_kernels.cuh resolves among the geoms with bound <= hi);
+//   filter pass: no if its best possible bound is >= lo3 (it changes none of k1, k2, lo2, lo3) or > hi (a geom that is
+//                surely hit lies closer than everything in the box: pt_kernels.cuh resolves among the geoms with bound <= hi);
 //   exact pass:  no if the bound exceeds the best exact distance (ties may still win).
 template <bool EXACT>
 __device__ __forceinline__ bool can_matter(float e, const TravRay& tr, const ScanBest& best, const Hit& h) {
   const float bd = __fmaf_rn(e, tr.dls, -tr.ewmax);
-  return EXACT ? !(bd > h.t) : (bd < best.lo2 && !(bd > best.hi));
+  return EXACT ? !(bd > h.t) : (bd < best.lo3 && !(bd > best.hi));
 }
 
 // the leaf `cur` (< 0): filter test (EXACT: exact test of the candidate if it can still matter)
@@ -230,7 +236,7 @@ __device__ __forceinline__ void leaf_visit(const BvhSoA& B, const GeomSoA& g, co
     lo = fmaxf(lo, 0.0f);
     if (hi < INFINITY) PT_HIST(42);
     if (!EXACT) {
-      scan_take(best, lo, leaf);
+      scan_take3(best, lo, leaf);
       best.hi = fminf(best.hi, hi);  // (NaN is ignored)
     } else if (!(lo > h.t)) {
       const int gi = __ldg(B.leaf_meta + leaf).y;
@@ -368,7 +374,7 @@ __device__ __forceinline__ bool filter_step(const BvhSoA& B, const ScanRay& r, c
     float lo, hi;
     PT_HIST(41);
     if (leaf != skip_leaf && leaf_filter_rows(cls, q0, q1, q2, q3, q4, r, tr.dlu, lo, hi)) {  // (skip_leaf: the retry pass)
-      scan_take(best, fmaxf(lo, 0.0f), leaf);
+      scan_take3(best, lo, leaf);
       best.hi = fminf(best.hi, hi);  // (NaN is ignored)
     }
   }
@@ -416,6 +422,9 @@ __device__ __noinline__ void bvh_exact(const BvhSoA B, const GeomSoA g, f3 o, f3
   scan_init(unused);
   bvh_traverse<true>(B, g, r, unused, h);
 }
+
+// the exact test of leaf k on its own, kept out of line (k_bounce_bvh tests two candidates per path: one copy of the code)
+__device__ __noinline__ bool exact_leaf_call(int k, const BvhSoA B, const GeomSoA g, f3 o, f3 d, Hit& e) { return exact_leaf(k, B, g, o, d, e); }
 
 // The exact test of the filter pass's best candidate leaf k1: confirmed (h filled in) if it is a hit closer than every
 // other geom's lower bound lo2.

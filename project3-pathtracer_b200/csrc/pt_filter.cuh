@@ -106,9 +106,24 @@ __device__ __forceinline__ ScanRay make_scan_ray(f3 o, f3 d, float r_scene, bool
 struct ScanBest {
   float lo1, lo2;  // smallest and second-smallest lower bound
   int k1;          // 2*pair + half of the smallest, -1 = every geom so far is a proven miss
-  float hi;        // hierarchy only (pt_bvh.cuh): smallest UPPER bound on the exact distance of a geom that is surely hit
+  // hierarchy only (pt_bvh.cuh):
+  float hi;        // smallest UPPER bound on the exact distance of a geom that is surely hit
+  float lo3;       // third-smallest lower bound
+  int k2;          // the geom with the second-smallest bound (-1: none)
 };
-__device__ __forceinline__ void scan_init(ScanBest& b) { b.lo1 = INFINITY; b.lo2 = INFINITY; b.k1 = -1; b.hi = INFINITY; }
+__device__ __forceinline__ void scan_init(ScanBest& b) {
+  b.lo1 = INFINITY; b.lo2 = INFINITY; b.k1 = -1; b.hi = INFINITY; b.lo3 = INFINITY; b.k2 = -1;
+}
+// the best THREE bounds and the two geoms of the smaller ones (hierarchy, pt_bvh.cuh)
+__device__ __forceinline__ void scan_take3(ScanBest& b, float lo, int k) {
+  lo = fmaxf(lo, 0.0f);  // (NaN -> 0: "no information")
+  const bool first = lo < b.lo1, second = !first && lo < b.lo2;
+  b.lo3 = first || second ? b.lo2 : fminf(b.lo3, lo);
+  b.lo2 = first ? b.lo1 : (second ? lo : b.lo2);
+  b.k2 = first ? b.k1 : (second ? k : b.k2);
+  b.lo1 = first ? lo : b.lo1;
+  b.k1 = first ? k : b.k1;
+}
 __device__ __forceinline__ void scan_take(ScanBest& b, float lo, int k) {
   lo = fmaxf(lo, 0.0f);  // also turns a NaN bound into 0 (fmaxf ignores NaN): "no information"
   const bool better = lo < b.lo1;

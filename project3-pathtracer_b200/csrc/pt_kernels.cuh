@@ -38,7 +38,7 @@ struct WfCtrl {
   uint32_t count[kMaxDepth + 1];     // count[d] = live paths entering depth d
   uint32_t tile_ctr[kMaxDepth + 1];  // ticket counter of the depth-d launch
   uint32_t fallbacks;                // rays whose filtered closest hit fell back to the exact scan (statistics)
-  uint32_t retries;                  // hierarchy: rays whose unconfirmed candidate was settled by the retry pass (statistics)
+  uint32_t retries;                  // hierarchy: rays whose nearest candidate was not confirmed and whose second candidate settled them (statistics)
   unsigned long long shadow;         // shadow rays traced by direct light sampling
 };
 
@@ -102,7 +102,7 @@ struct BounceParams {
   FiltSoA filt;                      // filter geometry (pt_filter.cuh): pairs of geoms, four classes
   int filt_cap;                      // pairs that fit in shared memory
   BvhSoA bvh;                        // hierarchy over the same filter tests for scenes with many geoms (pt_bvh.cuh)
-  float2* bvh_res;                   // k_bounce_bvh: per path of the wavefront (lo2, bits of the candidate leaf k1), between its two phases
+  float4* bvh_res;                   // k_bounce_bvh: per path of the wavefront (lo2, lo3, bits of the candidate leaves k1, k2), between its two phases
   const float4* mats;                // 4 float4 per material
   const float4* lights;              // direct light sampling: 3 float4 per light (E.xyz | geom) (th0..th3) (th4, type, K, -)
   const float* light_k;              // per geom: K = area * n_lights / pi of a light, 0 otherwise (balance heuristic at emissive hits)
@@ -200,7 +200,7 @@ __device__ __forceinline__ void closest_hit_one(const BounceParams& P, const flo
 #ifndef PT_NEE_INLINE
 #define PT_NEE_INLINE __forceinline__  // measured: 19.75 G rays/s inlined, 19.25 out of line (sample scene, direct light on)
 #endif
-template <bool TABLE>
+template <bool TABLE, bool LINEAR>
 __device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const DepthIO& io, const float4* fs, uint32_t lane, bool active, f3 ns, f3 o, f3 thr,
                                           uint32_t pixel, uint32_t sample) {
   bool traced = false;
@@ -230,7 +230,7 @@ __device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const DepthIO&
   if (!traced) return;
   Hit h;
   h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
-  closest_hit_one<TABLE>(P, fs, o, wd, h);
+  closest_hit_one<LINEAR>(P, fs, o, wd, h);
   // y is visible iff the ray arrives ON the light AT y (its far side is hidden by the light itself)
   if (h.id != gl || !((dy - h.t) < 1e-3f * dy + 1e-3f)) return;
   const f3 n2 = TABLE ? hit_normal_table(P.normals, h)
@@ -246,8 +246,8 @@ __device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const DepthIO&
 
 // The second half of a segment, by a whole warp: material lookup, reservation of the unit's output slots, BSDF
 // sampling, radiance of finished paths, survivors written to base + rank.  `hit` lanes carry a closest hit in h.
-// TABLE: normals from the per-geom table (few geoms, L1-resident; `fs` = the filter pairs in shared memory) or from the
-// winner's own rows (many geoms, hierarchy).  NEE: direct light sampling at diffuse bounces; `cos_b` > 0 = the path's
+// TABLE: normals from the per-geom table or from the winner's own rows.  LINEAR: shadow rays scan the filter pairs in
+// shared memory (`fs`; few geoms) or walk the hierarchy (many geoms).  NEE: direct light sampling at diffuse bounces; `cos_b` > 0 = the path's
 // previous event was one (the cosine of the direction it sampled travels in throughput.w): a light it reaches by itself is
 // weighted by the balance heuristic against that event's light sample.
 // Deferred output (k_bounce_q): a batch's survivors wait in shared memory while the atomic that reserves their slots is
@@ -274,7 +274,7 @@ __device__ __forceinline__ void deferred_flush(DeferredOut& W, const BounceParam
   __syncwarp();  // the staging rows may be overwritten now
 }
 
-template <bool LAST, bool TABLE, bool NEE, bool DEFER = false>
+template <bool LAST, bool TABLE, bool NEE, bool DEFER = false, bool LINEAR = TABLE>
 __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const DepthIO& io, const float4* fs, uint32_t lane, bool hit, const Hit& h, f3 o, f3 d, f3 thr,
                                                   uint32_t pixel, uint32_t sample, float cos_b, DeferredOut* W = nullptr) {
   // a path survives this segment unless it left the scene or reached a light; the slot of the unit's survivors
@@ -347,7 +347,7 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const D
         __stcs(io.out_t + slot, make_float4(thr.x, thr.y, thr.z, sampled ? cos_s : 0.0f));
       }
     }
-    if (NEE && __any_sync(0xffffffffu, sampled)) direct_light<TABLE>(P, io, fs, lane, sampled, ns, o, thr, pixel, sample);
+    if (NEE && __any_sync(0xffffffffu, sampled)) direct_light<TABLE, LINEAR>(P, io, fs, lane, sampled, ns, o, thr, pixel, sample);
   }
 }
 
@@ -643,7 +643,7 @@ constexpr int kRefillMin = PT_BVH_REFILL_MIN, kDeferCap = 2 * kUnit, kSmemStack 
 #endif
 constexpr int kBvhThreads = PT_BVH_THREADS;
 struct BvhWarpSmem {
-  uint2 defer[kDeferCap];        // (index into the wavefront's input, unconfirmed candidate leaf) of paths waiting for the retry pass
+  uint32_t defer[kDeferCap];     // paths (index into the wavefront's input) waiting for the exact traversal
   StackEnt stk[kSmemStack > 0 ? kSmemStack * kUnit : 1];  // the lanes' traversal stacks, lowest levels
 };
 constexpr size_t kBvhSmemBytes = sizeof(BvhWarpSmem) * (kBvhThreads / 32);
@@ -678,24 +678,21 @@ __device__ __forceinline__ void load_path(const BounceParams& P, uint32_t idx, f
 
 // shading + compaction of one unit of k_bounce_bvh: ONE copy of the code for the pool's units and the retry pass's units
 // (the kernel's instruction footprint is what its warps wait for at depth 0: profiles/r02_bvh_notes.txt)
+#ifndef PT_BVH_TABLE
+#define PT_BVH_TABLE 0  // normals, tangent frames and the material row from the per-geom table, as in the few-geom kernels
+#endif
 template <bool LAST, bool NEE>
 __device__ __noinline__ void shade_unit_bvh(const BounceParams& P, const DepthIO& io, uint32_t lane, bool hit, const Hit& h, f3 o, f3 d,
                                             f3 thr, uint32_t pixel, uint32_t sample, float cos_b) {
-  shade_and_compact<LAST, false, NEE>(P, io, nullptr, lane, hit, h, o, d, thr, pixel, sample, cos_b);
+  shade_and_compact<LAST, PT_BVH_TABLE != 0, NEE, false, false>(P, io, nullptr, lane, hit, h, o, d, thr, pixel, sample, cos_b);
 }
 
-// `n` (<= 32, warp-uniform) deferred paths, taken from the top of the warp's list (path index, unconfirmed candidate leaf).
-// A path is deferred when the exact test of its best candidate k1 did not settle the closest hit: it missed (the
-// inflated bound of a small distant sphere is several times its radius: the reference's own cancellation error), or it hit
-// no closer than the second-smallest bound.  RETRY PASS, all lanes together: the filter traversal once more WITHOUT k1
-// gives the best other candidate k2 and the second-smallest other bound lo2'; the closer of the two exact results
-// (ties: lower geom index, the index-order rule) is the closest hit if it is closer than lo2' -- every geom other than
-// k1 and k2 is a proven miss or no closer than its bound >= lo2'.  Only what is still open after that (a third geom in
-// the way) goes through the exact traversal.  The retry costs one ordinary traversal and two exact tests at full warp width
-// where the exact traversal tests every candidate leaf along the ray exactly: 15 % of the 10 000-geom config's time went
-// there for 2.6 % of its segments.
+// `n` (<= 32, warp-uniform) deferred paths, taken from the top of the warp's list: paths whose two nearest candidates
+// did not settle the closest hit (a third geom is in the way: ~0.1 % of the segments) go through the EXACT traversal --
+// every candidate leaf along the ray that can still matter is tested exactly -- all lanes together, then shading and
+// compaction as a unit of their own.
 template <bool LAST, bool NEE>
-__device__ __noinline__ void run_deferred(const BounceParams& P, const uint2* list, uint32_t n) {
+__device__ __noinline__ void run_deferred(const BounceParams& P, const uint32_t* list, uint32_t n) {
   const uint32_t lane = threadIdx.x & 31u;
   const DepthIO io = depth_io(P);
   const bool valid = lane < n;
@@ -704,163 +701,174 @@ __device__ __noinline__ void run_deferred(const BounceParams& P, const uint2* li
   float cos_b = 0.0f;
   Hit h;
   h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
-  bool open = false;  // the retry pass did not settle it either
   if (valid) {
-    const uint2 ent = list[lane];
-    const uint32_t idx = ent.x;
-    const int k1 = (int)ent.y;
+    const uint32_t idx = list[lane];
     load_path(P, idx, o, d, pixel, sample);
     { const float4 c = __ldg(P.in_t + idx); thr = mk(c.x, c.y, c.z); cos_b = NEE ? c.w : 0.0f; }
-    const ScanRay ray = make_scan_ray(o, d, P.filt.r_scene, true);
-    Hit e1, e2, unused;
-    const bool hit1 = exact_leaf(k1, P.bvh, P.g, o, d, e1);
-    ScanBest best;
-    scan_init(best);
-    bvh_traverse<false>(P.bvh, P.g, ray, best, unused, k1);
-    bool hit2 = false;
-    if (best.k1 >= 0) hit2 = exact_leaf(best.k1, P.bvh, P.g, o, d, e2);
-    const bool second = hit2 && (!hit1 || e2.t < e1.t || (e2.t == e1.t && e2.id < e1.id));
-    const Hit& b = second ? e2 : e1;
-    if (hit1 || hit2) {
-      if (b.t < best.lo2) h = b; else open = true;
-    } else {
-      open = best.k1 >= 0 && best.lo2 < INFINITY;  // two misses: settled unless a third geom is a candidate
-    }
-    if (open) {
-      h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
-      ScanBest unused2;
-      scan_init(unused2);
-      bvh_traverse<true>(P.bvh, P.g, ray, unused2, h);
-    }
+    bvh_exact(P.bvh, P.g, o, d, P.filt.r_scene, h);
   }
-  const uint32_t n_open = __popc(__ballot_sync(0xffffffffu, open));
-  if (lane == 0) {
-    atomicAdd(&P.ctrl->fallbacks, n_open);       // statistics: segments that needed the exact traversal ...
-    atomicAdd(&P.ctrl->retries, n - n_open);     // ... and segments the retry pass settled
-  }
+  if (lane == 0) atomicAdd(&P.ctrl->fallbacks, n);  // statistics: segments that needed the exact traversal
   shade_unit_bvh<LAST, NEE>(P, io, lane, valid && h.id >= 0, h, o, d, thr, pixel, sample, cos_b);
 }
 
+// the next pool of a warp: kPool paths while plenty are left, fewer (down to kPoolMin) when the wavefront runs out, so
+// that the warps finish together.  Returns false when the wavefront is exhausted.  (`ticket` counts PATHS.)
+__device__ __forceinline__ bool bvh_take_pool(uint32_t* ticket, uint32_t n_in, uint32_t n_warps, uint32_t lane, uint32_t& base, uint32_t& n_pool) {
+  uint32_t chunk = 0;
+  base = 0;
+  if (lane == 0) {
+    const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(ticket);  // (a little stale: only sizes the chunk)
+    chunk = kPool;
+    if (seen < n_in) {
+      const uint32_t fair = ((n_in - seen) / (2u * n_warps)) & ~(kUnit - 1u);
+      chunk = min((uint32_t)kPool, max((uint32_t)kPoolMin, fair));
+    }
+    base = atom_add_u32(ticket, chunk);
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  chunk = __shfl_sync(0xffffffffu, chunk, 0);
+  if (base >= n_in) return false;
+  n_pool = min(chunk, n_in - base);
+  return true;
+}
+
+// phase 1 of a pool: filter traversal of paths [base, base + n_pool); (lo2, k1) of every path to P.bvh_res
+__device__ __forceinline__ void bvh_phase1(const BounceParams& P, BvhWarpSmem& S, uint32_t lane, uint32_t n_in, uint32_t base, uint32_t n_pool) {
+  {
+    uint32_t next = 0;  // warp-uniform: first ray of the pool nobody has taken yet
+    int ray = -1;       // this lane's ray, -1 = idle
+    ScanRay r;
+    TravRay tr;
+    ScanBest best;
+    StackEnt ov[kBvhStack - kSmemStack];
+    TravStack<kSmemStack> st;
+    st.sm = S.stk + lane; st.ov = ov;
+    int cur = 0;
+    r = make_scan_ray(mk(0, 0, 0), mk(0, 0, 1), 0.0f, true);
+    tr = make_trav_ray(P.bvh, r);
+    scan_init(best);
+    for (;;) {
+      const uint32_t idle = __ballot_sync(0xffffffffu, ray < 0);
+      if (idle) {
+        if (next < n_pool && (__popc(idle) >= kRefillMin || idle == 0xffffffffu)) {
+          const uint32_t j = next + __popc(idle & ((1u << lane) - 1u));
+          if (ray < 0 && j < n_pool) {
+            ray = (int)j;
+            f3 o, d;
+            uint32_t pixel, sample;
+            load_path(P, base + j, o, d, pixel, sample);
+            r = make_scan_ray(o, d, P.filt.r_scene, true);
+            tr = make_trav_ray(P.bvh, r);
+            scan_init(best);
+            st.sp = 0;
+            cur = bvh_root(P.bvh);
+          }
+          next += __popc(idle);
+          // the rays the next refill will take: on their way into L1 meanwhile (4 lines each of origins and directions)
+          if (lane < 8u) {
+            const uint32_t q = base + next + (lane & 3u) * 8u;
+            if (q < n_in) asm volatile("prefetch.global.L1 [%0];" ::"l"((lane < 4u ? P.in_o : P.in_d) + q));
+          }
+        } else if (idle == 0xffffffffu) {
+          break;
+        }
+      }
+#ifdef PT_BVH_STACK_HIST
+      {
+        const uint32_t act = __ballot_sync(0xffffffffu, ray >= 0), atn = __ballot_sync(0xffffffffu, ray >= 0 && cur >= 0);
+        if (lane == 0) {
+          atomicAdd(&g_sp_hist[45], (unsigned long long)__popc(act));
+          atomicAdd(&g_sp_hist[46], 1ull);
+          if (next >= n_pool) { atomicAdd(&g_sp_hist[47], 1ull); atomicAdd(&g_sp_hist[48], (unsigned long long)__popc(act)); }
+          atomicAdd(&g_sp_hist[49], (unsigned long long)__popc(atn));
+        }
+      }
+#endif
+      if (ray >= 0 && !filter_step(P.bvh, r, tr, best, cur, st)) {
+        P.bvh_res[base + (uint32_t)ray] = make_float4(best.lo2, best.lo3, __int_as_float(best.k1), __int_as_float(best.k2));
+        ray = -1;
+      }
+    }
+  }
+}
+
+// phase 2 of a pool: exact test of the candidates, shading, compaction, unit by unit; paths that two candidates do not
+// settle go to the warp's list for the exact traversal, which is run whenever the list holds a unit's worth
+template <bool LAST, bool NEE>
+__device__ __forceinline__ void bvh_phase2(const BounceParams& P, const DepthIO& io, BvhWarpSmem& S, uint32_t lane, uint32_t base, uint32_t n_pool,
+                                           uint32_t& n_defer) {
+#pragma unroll 1
+  for (uint32_t j0 = 0; j0 < n_pool; j0 += kUnit) {
+    const uint32_t j = j0 + lane;
+    const bool valid = j < n_pool;
+    f3 o = mk(0, 0, 0), d = mk(0, 0, 1), thr = mk(1, 1, 1);
+    uint32_t pixel = 0, sample = 0;
+    float cos_b = 0.0f;
+    Hit h;
+    h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
+    bool defer = false;  // neither candidate settles it: the exact traversal decides (run_deferred)
+    int k1 = -1, k2 = -1;
+    float lo2 = INFINITY, lo3 = INFINITY;
+    Hit e1;
+    e1.t = INFINITY; e1.id = -1; e1.p = mk(0, 0, 0); e1.ncode = 0;
+    bool hit1 = false;
+    if (valid) {
+      load_path(P, base + j, o, d, pixel, sample);
+      const float4 res = P.bvh_res[base + j];  // (written by this warp: ordered by the __syncwarp after phase 1)
+      { const float4 c = __ldcs(P.in_t + base + j); thr = mk(c.x, c.y, c.z); cos_b = NEE ? c.w : 0.0f; }
+      lo2 = res.x; lo3 = res.y; k1 = __float_as_int(res.z); k2 = __float_as_int(res.w);
+    }
+    // the nearest candidate (k1 < 0: every geom is a proven miss)
+    if (k1 >= 0) hit1 = exact_leaf_call(k1, P.bvh, P.g, o, d, e1);
+    const bool settled1 = k1 < 0 || (hit1 && e1.t < lo2) || (!hit1 && k2 < 0);
+    if (hit1 && e1.t < lo2) h = e1;
+    // ... and, where that did not settle it, the second one: the closer exact result wins if it is closer than lo3
+    if (__any_sync(0xffffffffu, !settled1)) {
+      if (!settled1) {
+        Hit e2;
+        const bool hit2 = exact_leaf_call(k2, P.bvh, P.g, o, d, e2);
+        const bool second = hit2 && (!hit1 || e2.t < e1.t || (e2.t == e1.t && e2.id < e1.id));
+        if (hit1 || hit2) {
+          if (second) e1 = e2;
+          if (e1.t < lo3) h = e1; else defer = true;
+        } else {
+          defer = lo3 < INFINITY;  // two misses: settled unless a third geom is a candidate
+        }
+      }
+      const uint32_t n2 = __popc(__ballot_sync(0xffffffffu, !settled1 && !defer));
+      if (lane == 0 && n2) atomicAdd(&P.ctrl->retries, n2);  // statistics: segments the second candidate settled
+    }
+    const uint32_t dmask = __ballot_sync(0xffffffffu, defer);
+    PT_CHECK(n_defer + __popc(dmask) <= (uint32_t)kDeferCap);
+    if (defer) S.defer[n_defer + __popc(dmask & ((1u << lane) - 1u))] = base + j;
+    n_defer += __popc(dmask);
+    shade_unit_bvh<LAST, NEE>(P, io, lane, valid && !defer && h.id >= 0, h, o, d, thr, pixel, sample, cos_b);
+    if (n_defer >= kUnit) {
+      __syncwarp();
+      n_defer -= kUnit;
+      run_deferred<LAST, NEE>(P, S.defer + n_defer, kUnit);
+      __syncwarp();
+    }
+  }
+}
+
+// (Traversal and exact test + shading as two kernels were measured: the traversal loop alone fits 48 registers only with
+// spills, and at 64 it takes as long as this kernel takes for both phases -- in one kernel the arithmetic of the warps in
+// phase 2 fills the issue slots that the warps in phase 1 leave while they wait for nodes: 2.51 vs 3.00 Gseg/s.)
 template <bool LAST, bool NEE = false>
 __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(const __grid_constant__ BounceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31u;
   BvhWarpSmem& S = reinterpret_cast<BvhWarpSmem*>(smem_raw)[threadIdx.x >> 5];
   const DepthIO io = depth_io(P);
-
   const uint32_t n_in = P.ctrl->count[P.depth];  // (depth 0: set by k_raygen_wf)
-  uint32_t* const ticket = &P.ctrl->tile_ctr[P.depth];  // (counts PATHS here: first path nobody has taken yet)
   const uint32_t n_warps = gridDim.x * (kBvhThreads / 32);
   uint32_t n_defer = 0;  // warp-uniform
-
-  for (;;) {
-    // ---- the next pool: kPool paths while plenty are left, fewer (down to kPoolMin) when the wavefront runs out ----
-    uint32_t base = 0, chunk = 0;
-    if (lane == 0) {
-      const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(ticket);  // (a little stale: only sizes the chunk)
-      chunk = kPool;
-      if (seen < n_in) {
-        const uint32_t fair = ((n_in - seen) / (2u * n_warps)) & ~(kUnit - 1u);
-        chunk = min((uint32_t)kPool, max((uint32_t)kPoolMin, fair));
-      }
-      base = atom_add_u32(ticket, chunk);
-    }
-    base = __shfl_sync(0xffffffffu, base, 0);
-    chunk = __shfl_sync(0xffffffffu, chunk, 0);
-    if (base >= n_in) break;
-    const uint32_t n_pool = min(chunk, n_in - base);
-
-    // ---- phase 1: filter traversal; idle lanes take the next rays of the pool ----
-    {
-      uint32_t next = 0;  // warp-uniform: first ray of the pool nobody has taken yet
-      int ray = -1;       // this lane's ray, -1 = idle
-      ScanRay r;
-      TravRay tr;
-      ScanBest best;
-      StackEnt ov[kBvhStack - kSmemStack];
-      TravStack<kSmemStack> st;
-      st.sm = S.stk + lane; st.ov = ov;
-      int cur = 0;
-      r = make_scan_ray(mk(0, 0, 0), mk(0, 0, 1), 0.0f, true);
-      tr = make_trav_ray(P.bvh, r);
-      scan_init(best);
-      for (;;) {
-        const uint32_t idle = __ballot_sync(0xffffffffu, ray < 0);
-        if (idle) {
-          if (next < n_pool && (__popc(idle) >= kRefillMin || idle == 0xffffffffu)) {
-            const uint32_t j = next + __popc(idle & ((1u << lane) - 1u));
-            if (ray < 0 && j < n_pool) {
-              ray = (int)j;
-              f3 o, d;
-              uint32_t pixel, sample;
-              load_path(P, base + j, o, d, pixel, sample);
-              r = make_scan_ray(o, d, P.filt.r_scene, true);
-              tr = make_trav_ray(P.bvh, r);
-              scan_init(best);
-              st.sp = 0;
-              cur = bvh_root(P.bvh);
-            }
-            next += __popc(idle);
-            // the rays the next refill will take: on their way into L1 meanwhile (4 lines each of origins and directions)
-            if (lane < 8u) {
-              const uint32_t q = base + next + (lane & 3u) * 8u;
-              if (q < n_in) asm volatile("prefetch.global.L1 [%0];" ::"l"((lane < 4u ? P.in_o : P.in_d) + q));
-            }
-          } else if (idle == 0xffffffffu) {
-            break;
-          }
-        }
-#ifdef PT_BVH_STACK_HIST
-        {
-          const uint32_t act = __ballot_sync(0xffffffffu, ray >= 0), atn = __ballot_sync(0xffffffffu, ray >= 0 && cur >= 0);
-          if (lane == 0) {
-            atomicAdd(&g_sp_hist[45], (unsigned long long)__popc(act));
-            atomicAdd(&g_sp_hist[46], 1ull);
-            if (next >= n_pool) { atomicAdd(&g_sp_hist[47], 1ull); atomicAdd(&g_sp_hist[48], (unsigned long long)__popc(act)); }
-            atomicAdd(&g_sp_hist[49], (unsigned long long)__popc(atn));
-          }
-        }
-#endif
-        if (ray >= 0 && !filter_step(P.bvh, r, tr, best, cur, st)) {
-          P.bvh_res[base + (uint32_t)ray] = make_float2(best.lo2, __int_as_float(best.k1));
-          ray = -1;
-        }
-      }
-    }
-    __syncwarp();
-
-    // ---- phase 2: exact test of the candidates, shading, compaction; unit by unit ----
-#pragma unroll 1
-    for (uint32_t j0 = 0; j0 < n_pool; j0 += kUnit) {
-      const uint32_t j = j0 + lane;
-      const bool valid = j < n_pool;
-      f3 o = mk(0, 0, 0), d = mk(0, 0, 1), thr = mk(1, 1, 1);
-      uint32_t pixel = 0, sample = 0;
-      float cos_b = 0.0f;
-      Hit h;
-      h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
-      bool defer = false;
-      int k1 = -1;
-      if (valid) {
-        load_path(P, base + j, o, d, pixel, sample);
-        const float2 res = P.bvh_res[base + j];  // (written by this warp: ordered by the __syncwarp above)
-        { const float4 c = __ldcs(P.in_t + base + j); thr = mk(c.x, c.y, c.z); cos_b = NEE ? c.w : 0.0f; }
-        k1 = __float_as_int(res.y);
-        if (k1 >= 0) defer = !confirm_candidate(k1, res.x, P.bvh, P.g, o, d, h);  // k1 < 0: every geom is a proven miss
-      }
-      const uint32_t dmask = __ballot_sync(0xffffffffu, defer);
-      PT_CHECK(n_defer + __popc(dmask) <= (uint32_t)kDeferCap);
-      if (defer) S.defer[n_defer + __popc(dmask & ((1u << lane) - 1u))] = make_uint2(base + j, (uint32_t)k1);
-      n_defer += __popc(dmask);
-      shade_unit_bvh<LAST, NEE>(P, io, lane, valid && !defer && h.id >= 0, h, o, d, thr, pixel, sample, cos_b);
-      if (n_defer >= kUnit) {
-        __syncwarp();
-        n_defer -= kUnit;
-        run_deferred<LAST, NEE>(P, S.defer + n_defer, kUnit);
-        __syncwarp();
-      }
-    }
-    __syncwarp();  // (the pool's results are consumed: the next pool may overwrite them)
+  uint32_t base, n_pool;
+  while (bvh_take_pool(&P.ctrl->tile_ctr[P.depth], n_in, n_warps, lane, base, n_pool)) {
+    bvh_phase1(P, S, lane, n_in, base, n_pool);
+    __syncwarp();  // (the pool's results were written by this warp: ordered for its other lanes)
+    bvh_phase2<LAST, NEE>(P, io, S, lane, base, n_pool, n_defer);
   }
   if (n_defer) {
     __syncwarp();

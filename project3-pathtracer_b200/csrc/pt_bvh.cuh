@@ -40,6 +40,7 @@ __device__ unsigned long long g_sp_hist[64];  // [0..39] depth at push; 40 node 
 #define PT_BVH_SURE 1
 #endif
 
+
 // node = 9 float4: two blocks of four rows, each holding two children side by side (child a in the low half of each
 // float2, child b in the high half), children (0, 1) in rows 0-3 and (2, 3) in rows 4-7:
 //   r0 = (min_a.x, min_b.x | min_a.y, min_b.y)  r1 = (min_a.z, min_b.z | max_a.x, max_b.x)  r2 = (max_a.y, max_b.y | max_a.z, max_b.z)
@@ -265,6 +266,8 @@ struct TravStack {
   StackEnt* ov;  // kBvhStack - S entries of local memory (an array of the caller's: a member array would drag `sp` into
                  // local memory with it)
   int sp = 0;
+  // (Measured and dropped: the top entry in registers, a pop handing it out at once and requesting the entry below for the
+  // NEXT pop -- 2.0 instead of 3.0 Gseg/s: the outstanding load's scoreboard stalls the step it was meant to overlap.)
   __device__ __forceinline__ void push(StackEnt e) {
     PT_CHECK(sp < kBvhStack);
     if (S > 0 && sp < S) sm[sp * 32] = e; else ov[sp - S] = e;

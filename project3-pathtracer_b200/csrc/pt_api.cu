@@ -94,6 +94,12 @@ struct pt_context {
   // Two wavefronts are in flight at a time, each on its own internal stream with its own path-state buffers and control
   // block: the tail of one wavefront's launch (its last units) overlaps the head of the other's instead of idling SMs.
   static const int kSlots = 2;
+  float4* d_shadow = nullptr;   // direct light sampling: per slot 4 arrays of shadow_cap float4 (the depth's queue of shadow rays)
+  uint64_t shadow_cap = 0;      // ... allocated when the first render with direct lighting needs it (ensure_shadow)
+  int shadow_slots = 0;
+  int grid_blocks_shadow = 0;   // resident CTAs of k_shadow_lin / k_shadow_bvh ...
+  int shadow_cfg_mode = -1;     // ... worked out for this scene mode and this much filter geometry
+  size_t shadow_cfg_smem = 0;
   float4* d_state = nullptr; // per slot (state_bytes): 6 arrays of wf_capacity float4: o0 d0 t0 o1 d1 t1, then wf_capacity float4 (hierarchy results)
   WfCtrl* d_ctrl = nullptr;  // per slot
   int n_slots = kSlots;      // slots in use (1 for frames whose accumulation image alone fills the L2)
@@ -953,7 +959,7 @@ extern "C" int pt_context_destroy(pt_context* c) {
   PT_FREE(c->d_rows); PT_FREE(c->d_meta); PT_FREE(c->d_normals); PT_FREE(c->d_mats); PT_FREE(c->d_lights); PT_FREE(c->d_state);
   PT_FREE(c->d_filt); PT_FREE(c->d_filt_ids); PT_FREE(c->d_bvh_nodes); PT_FREE(c->d_bvh_leaves); PT_FREE(c->d_bvh_meta);
   PT_FREE(c->d_ctrl); PT_FREE(c->d_live); PT_FREE(c->d_accum); PT_FREE(c->d_rgb); PT_FREE(c->d_rgba8);
-  PT_FREE(c->d_scratch); PT_FREE(c->d_light_k);
+  PT_FREE(c->d_scratch); PT_FREE(c->d_light_k); PT_FREE(c->d_shadow);
   PT_FREE(c->d_slab); PT_FREE(c->d_means); PT_FREE(c->d_base[0]); PT_FREE(c->d_base[1]);
 #undef PT_FREE
   for (int i = 0; i < pt_context::kSlots; i++) {
@@ -1109,6 +1115,50 @@ static cudaError_t launch_bounce(pt_context* c, int slot, const BounceParams& P,
   return cudaGetLastError();
 }
 
+// the shadow-ray queues of direct light sampling: one per wavefront slot, as long as a wavefront (a path queues at most
+// one shadow ray per depth, and a depth's queue is traced before the next depth fills it again)
+static int ensure_shadow(pt_context* c) {
+  if (!(c->d_shadow && c->shadow_cap == c->wf_capacity && c->shadow_slots == c->n_slots)) {
+    if (c->d_shadow) CU(cudaFree(c->d_shadow));
+    c->d_shadow = nullptr; c->shadow_cap = 0;
+    if (cudaMalloc(&c->d_shadow, (size_t)c->n_slots * 4 * c->wf_capacity * sizeof(float4)) != cudaSuccess) {
+      const cudaError_t e = cudaGetLastError();
+      c->d_shadow = nullptr;
+      pt_set_error_("cudaMalloc of the shadow-ray queues (%llu paths) failed: %s", (unsigned long long)c->wf_capacity, cudaGetErrorString(e));
+      return PT_ERR_CUDA;
+    }
+    c->shadow_cap = c->wf_capacity; c->shadow_slots = c->n_slots;
+  }
+  if (c->shadow_cfg_mode == c->mode && c->shadow_cfg_smem == c->geom_smem) return PT_OK;
+  int per_sm = 0;
+  if (c->mode) {
+    CU(cudaFuncSetAttribute(k_shadow_bvh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBvhSmemBytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shadow_bvh, kBvhThreads, kBvhSmemBytes));
+  } else {
+    CU(cudaFuncSetAttribute(k_shadow_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->geom_smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shadow_lin, kBounceThreads, c->geom_smem));
+  }
+  if (per_sm < 1) { pt_set_error_("k_shadow does not fit on an SM"); return PT_ERR_CUDA; }
+  c->grid_blocks_shadow = per_sm * c->sm_count;
+  c->shadow_cfg_mode = c->mode; c->shadow_cfg_smem = c->geom_smem;
+  return PT_OK;
+}
+// trace the shadow rays the depth-P.depth launch queued (n_upper: how many there can be at most)
+static cudaError_t launch_shadow(pt_context* c, BounceParams P, uint32_t n_upper, cudaStream_t st) {
+  P.in_o = P.sq_o; P.in_d = P.sq_d;  // the traversal reads its rays from the queue
+  uint32_t grid = (uint32_t)c->grid_blocks_shadow;
+  if (c->mode) {
+    const uint32_t ctas = (n_upper + kPoolMin * (kBvhThreads / 32) - 1) / (kPoolMin * (kBvhThreads / 32));
+    if (ctas < grid) grid = ctas ? ctas : 1;
+    k_shadow_bvh<<<grid, kBvhThreads, kBvhSmemBytes, st>>>(P);
+  } else {
+    const uint32_t ctas = (n_upper + kBounceThreads - 1) / kBounceThreads;
+    if (ctas < grid) grid = ctas ? ctas : 1;
+    k_shadow_lin<<<grid, kBounceThreads, c->geom_smem, st>>>(P);
+  }
+  return cudaGetLastError();
+}
+
 // Trace samples [first_sample, first_sample + n_samples) of every pixel, enqueued behind `stream0`.  Radiance goes to
 // accum[(s - acc_s0) * acc_stride + pixel] (stride 0: one image).
 static int render_into(pt_context* c, uint32_t first_sample, uint32_t n_samples, int max_depth, uint64_t seed, cudaStream_t stream0,
@@ -1119,6 +1169,8 @@ static int render_into(pt_context* c, uint32_t first_sample, uint32_t n_samples,
     pt_set_error_("no wavefront buffers (a previous pt_set_wavefront_paths failed): call it again with a size that fits");
     return PT_ERR_STATE;
   }
+  const bool nee_on = c->nee && c->n_lights > 0 && max_depth > 1;
+  if (nee_on) { if (int rc = ensure_shadow(c)) return rc; }
   NvtxRange nvtx_render("pt_render");
   if (timed) CU(cudaEventRecord(c->ev0, stream0));
   const uint64_t cap = c->wf_capacity;
@@ -1165,6 +1217,8 @@ static int render_into(pt_context* c, uint32_t first_sample, uint32_t n_samples,
       P.filt = c->filt; P.filt_cap = c->filt_cap;
       P.bvh = c->bvh;
       P.bvh_res = S + 6 * cap;
+      float4* const SQ = nee_on ? c->d_shadow + (size_t)sl * 4 * cap : nullptr;
+      P.sq_o = SQ; P.sq_d = SQ ? SQ + cap : nullptr; P.sq_t = SQ ? SQ + 2 * cap : nullptr; P.sq_x = SQ ? SQ + 3 * cap : nullptr;
       P.mats = c->d_mats;
       P.lights = c->d_lights; P.n_lights = c->n_lights; P.light_k = c->d_light_k;
       P.cam = c->cam;
@@ -1184,6 +1238,11 @@ static int render_into(pt_context* c, uint32_t first_sample, uint32_t n_samples,
       else if (last) e = launch_bounce<false, true>(c, 3, P, n_first, st);
       else e = launch_bounce<false, false>(c, 2, P, n_first, st);
       if (e != cudaSuccess) { pt_set_error_("k_bounce launch failed: %s", cudaGetErrorString(e)); return PT_ERR_CUDA; }
+      // direct light sampling: the shadow rays this depth queued, before the next depth queues its own
+      if (nee_on && !last && (e = launch_shadow(c, P, n_first, st)) != cudaSuccess) {
+        pt_set_error_("k_shadow launch failed: %s", cudaGetErrorString(e));
+        return PT_ERR_CUDA;
+      }
     }
     k_accum_counts<<<1, kMaxDepth, 0, st>>>(ctrl, c->d_live, max_depth, c->q_mode == 0 && !c->mode ? c->d_policy : nullptr);
     c->launches++;

@@ -40,6 +40,7 @@ struct WfCtrl {
   uint32_t fallbacks;                // rays whose filtered closest hit fell back to the exact scan (statistics)
   uint32_t retries;                  // hierarchy: rays whose nearest candidate was not confirmed and whose second candidate settled them (statistics)
   unsigned long long shadow;         // shadow rays traced by direct light sampling
+  uint32_t shadow_ctr[kMaxDepth + 1];  // ticket counter of the depth-d shadow launch (k_shadow_*)
 };
 
 // ---- decoupled look-back (Merrill & Garland 2016) on 64-bit status words ----
@@ -114,6 +115,8 @@ struct BounceParams {
   uint32_t first_sample, n_first;    // FIRST only: paths to generate = band * samples in this wavefront
   uint32_t pix0, band;               // FIRST only: the wavefront covers pixels [pix0, pix0 + band) (the whole frame unless banded)
   FastDiv div_band;                  // FIRST only: path index -> (sample, pixel of the band)
+  float4 *sq_o, *sq_d, *sq_t, *sq_x; // direct light sampling: the wavefront's queue of shadow rays (origin | pixel) (direction | sample)
+                                     // (throughput * emittance | cosine at the surface) (distance to the light point, K, light geom, -)
   uint32_t q_offset;                 // k_bounce_q: byte offset of the warps' candidate queues in dynamic shared memory
   uint32_t cap;                      // paths the in / out buffers hold (debug checks)
   uint32_t acc_s0, acc_stride;       // radiance of sample s goes to accum[(s - acc_s0) * acc_stride + pixel]: stride 0 = one image for
@@ -195,14 +198,36 @@ __device__ __forceinline__ void closest_hit_one(const BounceParams& P, const flo
 
 // Direct light sampling (DESIGN.md "direct light sampling"; oracle: or_render_ex), by a whole warp; `active` lanes
 // have just sampled a diffuse bounce: o = new path origin, ns = shading normal, thr = throughput after the bounce.
+#ifndef PT_NEE_QUEUE
+#define PT_NEE_QUEUE 1
+#endif
+// The light sample's contribution once the closest hit `h` of its shadow ray (direction wd, unit length) is known.
+// TE = throughput * emittance, cs = cosine at the surface, dy = distance to the sampled point y, gl = the light's geom.
+template <bool TABLE>
+__device__ __forceinline__ void shadow_resolve(const BounceParams& P, const Hit& h, f3 wd, f3 TE, float cs, float dy, float K, int gl,
+                                               uint32_t pixel, uint32_t sample) {
+  // y is visible iff the ray arrives ON the light AT y (its far side is hidden by the light itself)
+  if (h.id != gl || !((dy - h.t) < 1e-3f * dy + 1e-3f)) return;
+  const f3 n2 = TABLE ? hit_normal_table(P.normals, h)
+                      : hit_normal(__ldg(P.g.fwd0 + gl), __ldg(P.g.fwd1 + gl), __ldg(P.g.fwd2 + gl), h);
+  const float cl = -dot(n2, wd);
+  if (!(cl > 0)) return;
+  const float G = (cs * cl) / (h.t * h.t);
+  const float wl = 1.0f / (1.0f + G * K);  // balance heuristic: p_bsdf / p_light = G * K, K = area * n_lights / pi
+  const f3 Ld = (TE * G) * wl;
+  PT_CHECK(pixel < P.cam.npix);
+  accum_add(accum_at(P, pixel, sample), Ld);
+}
+
 // One light, one point on it (getRandomPointOnCube's area-weighted faces / the sphere sampler, Philox block 65 + depth),
 // one shadow ray through the ordinary closest hit.
 #ifndef PT_NEE_INLINE
 #define PT_NEE_INLINE __forceinline__  // measured: 19.75 G rays/s inlined, 19.25 out of line (sample scene, direct light on)
 #endif
+// `alive` lanes continue as path `slot` of the next depth's wavefront; `active` ones among them bounced diffusely.
 template <bool TABLE, bool LINEAR>
-__device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const DepthIO& io, const float4* fs, uint32_t lane, bool active, f3 ns, f3 o, f3 thr,
-                                          uint32_t pixel, uint32_t sample) {
+__device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const DepthIO& io, const float4* fs, uint32_t lane, bool active, bool alive,
+                                          uint32_t slot, f3 ns, f3 o, f3 thr, uint32_t pixel, uint32_t sample) {
   bool traced = false;
   f3 wd = mk(0, 0, 1), E = mk(0, 0, 0);
   float cs = 0.0f, dy = 0.0f, K = 0.0f;
@@ -226,22 +251,34 @@ __device__ PT_NEE_INLINE void direct_light(const BounceParams& P, const DepthIO&
     traced = cs > 0;
   }
   const uint32_t tmask = __ballot_sync(0xffffffffu, traced);
+#if PT_NEE_QUEUE
+  // The shadow rays are not traced here -- a few lanes of a warp in the middle of the shading code -- but QUEUED: a launch
+  // of its own traces the depth's shadow rays as dense units (k_shadow_lin) or through the pooled traversal (k_shadow_bvh).
+  // Everything the contribution needs travels with the ray; the operations are the ones below, in the same order.
+  // The queue is indexed like the next depth's wavefront -- the shadow ray of the path that continues in slot i is entry
+  // i -- so it needs no slot reservation of its own (a second atomic per unit next to the compaction's, on the same L2
+  // slice, halved the bounce kernels' speed); a path that continues without a shadow ray marks its entry empty.
+  if (lane == 0 && tmask) atomicAdd(&P.ctrl->shadow, (unsigned long long)__popc(tmask));
+  if (alive) {
+    PT_CHECK(slot < P.cap);
+    if (traced) {
+      const f3 TE = thr * E;
+      __stcs(P.sq_o + slot, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
+      __stcs(P.sq_d + slot, make_float4(wd.x, wd.y, wd.z, __uint_as_float(sample)));
+      __stcs(P.sq_t + slot, make_float4(TE.x, TE.y, TE.z, cs));
+      __stcs(P.sq_x + slot, make_float4(dy, K, __int_as_float(gl), 0.0f));
+    } else {
+      __stcs(P.sq_x + slot, make_float4(0.0f, 0.0f, __int_as_float(-1), 0.0f));  // no shadow ray
+    }
+  }
+#else
   if (lane == 0 && tmask) atomicAdd(&P.ctrl->shadow, (unsigned long long)__popc(tmask));
   if (!traced) return;
   Hit h;
   h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
   closest_hit_one<LINEAR>(P, fs, o, wd, h);
-  // y is visible iff the ray arrives ON the light AT y (its far side is hidden by the light itself)
-  if (h.id != gl || !((dy - h.t) < 1e-3f * dy + 1e-3f)) return;
-  const f3 n2 = TABLE ? hit_normal_table(P.normals, h)
-                      : hit_normal(__ldg(P.g.fwd0 + gl), __ldg(P.g.fwd1 + gl), __ldg(P.g.fwd2 + gl), h);
-  const float cl = -dot(n2, wd);
-  if (!(cl > 0)) return;
-  const float G = (cs * cl) / (h.t * h.t);
-  const float wl = 1.0f / (1.0f + G * K);  // balance heuristic: p_bsdf / p_light = G * K, K = area * n_lights / pi
-  const f3 Ld = ((thr * E) * G) * wl;
-  PT_CHECK(pixel < P.cam.npix);
-  accum_add(accum_at(P, pixel, sample), Ld);
+  shadow_resolve<TABLE>(P, h, wd, thr * E, cs, dy, K, gl, pixel, sample);
+#endif
 }
 
 // The second half of a segment, by a whole warp: material lookup, reservation of the unit's output slots, BSDF
@@ -330,16 +367,18 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const D
     if (sampled) cos_s = dot(ns, d);  // of the direction the bounce just sampled
   }
   if (!LAST) {
+    const uint32_t rank = __popc(ballot & ((1u << lane) - 1u));
+    uint32_t slot = 0;  // where an alive lane's path continues in the next depth's wavefront
     if (DEFER) {
-      const uint32_t rank = __popc(ballot & ((1u << lane) - 1u));
       if (alive) {
         W->stage[rank] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
         W->stage[kUnit + rank] = make_float4(d.x, d.y, d.z, __uint_as_float(sample));
         W->stage[2 * kUnit + rank] = make_float4(thr.x, thr.y, thr.z, sampled ? cos_s : 0.0f);
       }
       __syncwarp();
+      if (NEE && PT_NEE_QUEUE) slot = __shfl_sync(0xffffffffu, W->pend_raw, 0) + rank;  // (the atomic was issued before the shading)
     } else {
-      const uint32_t slot = __shfl_sync(0xffffffffu, base_raw, 0) + __popc(ballot & ((1u << lane) - 1u));
+      slot = __shfl_sync(0xffffffffu, base_raw, 0) + rank;
       if (alive) {
         PT_CHECK(slot < P.cap);
         __stcs(io.out_o + slot, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
@@ -347,7 +386,8 @@ __device__ __forceinline__ void shade_and_compact(const BounceParams& P, const D
         __stcs(io.out_t + slot, make_float4(thr.x, thr.y, thr.z, sampled ? cos_s : 0.0f));
       }
     }
-    if (NEE && __any_sync(0xffffffffu, sampled)) direct_light<TABLE, LINEAR>(P, io, fs, lane, sampled, ns, o, thr, pixel, sample);
+    if (NEE && (PT_NEE_QUEUE ? ballot != 0u : __any_sync(0xffffffffu, sampled)))
+      direct_light<TABLE, LINEAR>(P, io, fs, lane, sampled, alive, slot, ns, o, thr, pixel, sample);
   }
 }
 
@@ -732,7 +772,9 @@ __device__ __forceinline__ bool bvh_take_pool(uint32_t* ticket, uint32_t n_in, u
   return true;
 }
 
-// phase 1 of a pool: filter traversal of paths [base, base + n_pool); (lo2, k1) of every path to P.bvh_res
+// phase 1 of a pool: filter traversal of paths [base, base + n_pool); the result of every path to P.bvh_res
+// (SHADOW: the rays are the entries of the shadow queue, some of which are empty)
+template <bool SHADOW = false>
 __device__ __forceinline__ void bvh_phase1(const BounceParams& P, BvhWarpSmem& S, uint32_t lane, uint32_t n_in, uint32_t base, uint32_t n_pool) {
   {
     uint32_t next = 0;  // warp-uniform: first ray of the pool nobody has taken yet
@@ -756,12 +798,15 @@ __device__ __forceinline__ void bvh_phase1(const BounceParams& P, BvhWarpSmem& S
             ray = (int)j;
             f3 o, d;
             uint32_t pixel, sample;
+            if (SHADOW && __float_as_int(__ldg(&P.sq_x[base + j].z)) < 0) ray = -1;  // an empty entry: nothing to trace
+            if (ray >= 0) {
             load_path(P, base + j, o, d, pixel, sample);
             r = make_scan_ray(o, d, P.filt.r_scene, true);
             tr = make_trav_ray(P.bvh, r);
             scan_init(best);
             st.sp = 0;
             cur = bvh_root(P.bvh);
+            }
           }
           next += __popc(idle);
           // the rays the next refill will take: on their way into L1 meanwhile (4 lines each of origins and directions)
@@ -792,6 +837,38 @@ __device__ __forceinline__ void bvh_phase1(const BounceParams& P, BvhWarpSmem& S
   }
 }
 
+// The closest hit of a path from the filter traversal's result res = (lo2, lo3, k1, k2), all lanes of a warp together:
+// the nearest candidate k1 is tested exactly (k1 < 0: every geom is a proven miss) and decides if it reports a hit closer
+// than lo2; where it does not, the second candidate joins in and the closer exact result wins if it is closer than lo3
+// (every other geom is a proven miss or no closer than its bound >= lo3).  Returns true if that does not settle it
+// either (a third geom is in the way): the caller runs the exact traversal.  `h` is filled in when a hit is settled.
+__device__ __forceinline__ bool bvh_resolve2(const BounceParams& P, uint32_t lane, float4 res, f3 o, f3 d, Hit& h) {
+  const float lo2 = res.x, lo3 = res.y;
+  const int k1 = __float_as_int(res.z), k2 = __float_as_int(res.w);
+  Hit e1;
+  e1.t = INFINITY; e1.id = -1; e1.p = mk(0, 0, 0); e1.ncode = 0;
+  bool hit1 = false, defer = false;
+  if (k1 >= 0) hit1 = exact_leaf_call(k1, P.bvh, P.g, o, d, e1);
+  const bool settled1 = k1 < 0 || (hit1 && e1.t < lo2) || (!hit1 && k2 < 0);
+  if (hit1 && e1.t < lo2) h = e1;
+  if (__any_sync(0xffffffffu, !settled1)) {
+    if (!settled1) {
+      Hit e2;
+      const bool hit2 = exact_leaf_call(k2, P.bvh, P.g, o, d, e2);
+      const bool second = hit2 && (!hit1 || e2.t < e1.t || (e2.t == e1.t && e2.id < e1.id));
+      if (hit1 || hit2) {
+        if (second) e1 = e2;
+        if (e1.t < lo3) h = e1; else defer = true;
+      } else {
+        defer = lo3 < INFINITY;  // two misses: settled unless a third geom is a candidate
+      }
+    }
+    const uint32_t n2 = __popc(__ballot_sync(0xffffffffu, !settled1 && !defer));
+    if (lane == 0 && n2) atomicAdd(&P.ctrl->retries, n2);  // statistics: segments the second candidate settled
+  }
+  return defer;
+}
+
 // phase 2 of a pool: exact test of the candidates, shading, compaction, unit by unit; paths that two candidates do not
 // settle go to the warp's list for the exact traversal, which is run whenever the list holds a unit's worth
 template <bool LAST, bool NEE>
@@ -806,38 +883,13 @@ __device__ __forceinline__ void bvh_phase2(const BounceParams& P, const DepthIO&
     float cos_b = 0.0f;
     Hit h;
     h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
-    bool defer = false;  // neither candidate settles it: the exact traversal decides (run_deferred)
-    int k1 = -1, k2 = -1;
-    float lo2 = INFINITY, lo3 = INFINITY;
-    Hit e1;
-    e1.t = INFINITY; e1.id = -1; e1.p = mk(0, 0, 0); e1.ncode = 0;
-    bool hit1 = false;
+    float4 res = make_float4(INFINITY, INFINITY, __int_as_float(-1), __int_as_float(-1));
     if (valid) {
       load_path(P, base + j, o, d, pixel, sample);
-      const float4 res = P.bvh_res[base + j];  // (written by this warp: ordered by the __syncwarp after phase 1)
+      res = P.bvh_res[base + j];  // (written by this warp: ordered by the __syncwarp after phase 1)
       { const float4 c = __ldcs(P.in_t + base + j); thr = mk(c.x, c.y, c.z); cos_b = NEE ? c.w : 0.0f; }
-      lo2 = res.x; lo3 = res.y; k1 = __float_as_int(res.z); k2 = __float_as_int(res.w);
     }
-    // the nearest candidate (k1 < 0: every geom is a proven miss)
-    if (k1 >= 0) hit1 = exact_leaf_call(k1, P.bvh, P.g, o, d, e1);
-    const bool settled1 = k1 < 0 || (hit1 && e1.t < lo2) || (!hit1 && k2 < 0);
-    if (hit1 && e1.t < lo2) h = e1;
-    // ... and, where that did not settle it, the second one: the closer exact result wins if it is closer than lo3
-    if (__any_sync(0xffffffffu, !settled1)) {
-      if (!settled1) {
-        Hit e2;
-        const bool hit2 = exact_leaf_call(k2, P.bvh, P.g, o, d, e2);
-        const bool second = hit2 && (!hit1 || e2.t < e1.t || (e2.t == e1.t && e2.id < e1.id));
-        if (hit1 || hit2) {
-          if (second) e1 = e2;
-          if (e1.t < lo3) h = e1; else defer = true;
-        } else {
-          defer = lo3 < INFINITY;  // two misses: settled unless a third geom is a candidate
-        }
-      }
-      const uint32_t n2 = __popc(__ballot_sync(0xffffffffu, !settled1 && !defer));
-      if (lane == 0 && n2) atomicAdd(&P.ctrl->retries, n2);  // statistics: segments the second candidate settled
-    }
+    const bool defer = bvh_resolve2(P, lane, res, o, d, h);  // neither candidate settles it: the exact traversal decides (run_deferred)
     const uint32_t dmask = __ballot_sync(0xffffffffu, defer);
     PT_CHECK(n_defer + __popc(dmask) <= (uint32_t)kDeferCap);
     if (defer) S.defer[n_defer + __popc(dmask & ((1u << lane) - 1u))] = base + j;
@@ -873,6 +925,81 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
   if (n_defer) {
     __syncwarp();
     run_deferred<LAST, NEE>(P, S.defer, n_defer);
+  }
+}
+
+// ---- the shadow rays of direct light sampling, one launch per depth behind the depth's bounce launch ----
+// P.in_o / P.in_d point at the queue's (origin | pixel) / (direction | sample) rows, P.depth names the queue.
+// Few geoms: a unit of 32 queued rays per warp -- filter scan, exact test of the winner, visibility, contribution: the
+// closest hit of direct_light's former inline trace, bit for bit, with all lanes busy.
+__global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_shadow_lin(const __grid_constant__ BounceParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const float4* const fs = reinterpret_cast<const float4*>(smem_raw);
+  stage_filt(P.filt, 0, P.filt.end[3], reinterpret_cast<float4*>(smem_raw));
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t n = P.ctrl->count[P.depth + 1];  // entry i of the queue belongs to path i of the next depth's wavefront
+  const uint32_t n_units = (n + kUnit - 1) / kUnit;
+  uint32_t* const ticket = &P.ctrl->shadow_ctr[P.depth];
+  for (;;) {
+    uint32_t t = 0;
+    if (lane == 0) t = atom_add_u32(ticket, 1u);
+    const uint32_t unit0 = __shfl_sync(0xffffffffu, t, 0) * kTicketUnits;
+    if (unit0 >= n_units) break;
+    const uint32_t unit_end = min(unit0 + kTicketUnits, n_units);
+    for (uint32_t u = unit0; u < unit_end; u++) {
+      const uint32_t idx = u * kUnit + lane;
+      if (idx >= n) continue;
+      const float4 x = __ldcs(P.sq_x + idx);
+      if (__float_as_int(x.z) < 0) continue;  // that path continues without a shadow ray
+      const float4 a = __ldcs(P.in_o + idx), b = __ldcs(P.in_d + idx), c = __ldcs(P.sq_t + idx);
+      const f3 o = mk(a.x, a.y, a.z), wd = mk(b.x, b.y, b.z);
+      Hit h;
+      h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
+      closest_hit_one<true>(P, fs, o, wd, h);
+      shadow_resolve<true>(P, h, wd, mk(c.x, c.y, c.z), c.w, x.x, x.y, __float_as_int(x.z), __float_as_uint(a.w), __float_as_uint(b.w));
+    }
+  }
+}
+// Many geoms: the queue goes through the pooled filter traversal like a wavefront of paths (bvh_phase1), then unit by
+// unit through the two-candidate resolution; the few rays that leaves open take the exact traversal on the spot.
+__global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_shadow_bvh(const __grid_constant__ BounceParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t lane = threadIdx.x & 31u;
+  BvhWarpSmem& S = reinterpret_cast<BvhWarpSmem*>(smem_raw)[threadIdx.x >> 5];
+  const uint32_t n = P.ctrl->count[P.depth + 1];  // entry i of the queue belongs to path i of the next depth's wavefront
+  const uint32_t n_warps = gridDim.x * (kBvhThreads / 32);
+  uint32_t base, n_pool;
+  while (bvh_take_pool(&P.ctrl->shadow_ctr[P.depth], n, n_warps, lane, base, n_pool)) {
+    bvh_phase1<true>(P, S, lane, n, base, n_pool);
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t j0 = 0; j0 < n_pool; j0 += kUnit) {
+      const uint32_t j = j0 + lane;
+      const bool valid = j < n_pool;
+      f3 o = mk(0, 0, 0), wd = mk(0, 0, 1);
+      uint32_t pixel = 0, sample = 0;
+      float4 res = make_float4(INFINITY, INFINITY, __int_as_float(-1), __int_as_float(-1));
+      Hit h;
+      h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
+      float4 x = make_float4(0.0f, 0.0f, __int_as_float(-1), 0.0f);
+      if (valid) x = __ldcs(P.sq_x + base + j);
+      const bool queued = __float_as_int(x.z) >= 0;  // (an empty entry has no ray and no traversal result)
+      if (queued) {
+        load_path(P, base + j, o, wd, pixel, sample);
+        res = P.bvh_res[base + j];
+      }
+      if (bvh_resolve2(P, lane, res, o, wd, h)) {
+        h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
+        bvh_exact(P.bvh, P.g, o, wd, P.filt.r_scene, h);
+        atomicAdd(&P.ctrl->fallbacks, 1u);
+      }
+      if (queued) {
+        const float4 c = __ldcs(P.sq_t + base + j);
+        shadow_resolve<false>(P, h, wd, mk(c.x, c.y, c.z), c.w, x.x, x.y, __float_as_int(x.z), pixel, sample);
+      }
+    }
+    __syncwarp();
   }
 }
 

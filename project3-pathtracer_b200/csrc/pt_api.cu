@@ -1135,8 +1135,8 @@ static int ensure_shadow(pt_context* c) {
     CU(cudaFuncSetAttribute(k_shadow_bvh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBvhSmemBytes));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shadow_bvh, kBvhThreads, kBvhSmemBytes));
   } else {
-    CU(cudaFuncSetAttribute(k_shadow_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->geom_smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shadow_lin, kBounceThreads, c->geom_smem));
+    CU(cudaFuncSetAttribute(k_shadow_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shadow_lin_smem(c->geom_smem)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shadow_lin, kBounceThreads, shadow_lin_smem(c->geom_smem)));
   }
   if (per_sm < 1) { pt_set_error_("k_shadow does not fit on an SM"); return PT_ERR_CUDA; }
   c->grid_blocks_shadow = per_sm * c->sm_count;
@@ -1154,7 +1154,7 @@ static cudaError_t launch_shadow(pt_context* c, BounceParams P, uint32_t n_upper
   } else {
     const uint32_t ctas = (n_upper + kBounceThreads - 1) / kBounceThreads;
     if (ctas < grid) grid = ctas ? ctas : 1;
-    k_shadow_lin<<<grid, kBounceThreads, c->geom_smem, st>>>(P);
+    k_shadow_lin<<<grid, kBounceThreads, shadow_lin_smem(c->geom_smem), st>>>(P);
   }
   return cudaGetLastError();
 }

@@ -932,15 +932,27 @@ __global__ void __launch_bounds__(kBvhThreads, PT_BVH_MIN_BLOCKS) k_bounce_bvh(c
 // P.in_o / P.in_d point at the queue's (origin | pixel) / (direction | sample) rows, P.depth names the queue.
 // Few geoms: a unit of 32 queued rays per warp -- filter scan, exact test of the winner, visibility, contribution: the
 // closest hit of direct_light's former inline trace, bit for bit, with all lanes busy.
+constexpr int kShadowQ = 2 * kUnit;  // per warp: indices of queued shadow rays waiting for a full unit
+__host__ __device__ inline size_t shadow_lin_smem(size_t geom_smem) { return geom_smem + (size_t)(kBounceThreads / 32) * kShadowQ * sizeof(uint32_t); }
+__device__ __forceinline__ void shadow_trace_lin(const BounceParams& P, const float4* fs, uint32_t idx) {
+  const float4 a = __ldcs(P.in_o + idx), b = __ldcs(P.in_d + idx), c = __ldcs(P.sq_t + idx), x = __ldcs(P.sq_x + idx);
+  const f3 o = mk(a.x, a.y, a.z), wd = mk(b.x, b.y, b.z);
+  Hit h;
+  h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
+  closest_hit_one<true>(P, fs, o, wd, h);
+  shadow_resolve<true>(P, h, wd, mk(c.x, c.y, c.z), c.w, x.x, x.y, __float_as_int(x.z), __float_as_uint(a.w), __float_as_uint(b.w));
+}
 __global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_shadow_lin(const __grid_constant__ BounceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const float4* const fs = reinterpret_cast<const float4*>(smem_raw);
   stage_filt(P.filt, 0, P.filt.end[3], reinterpret_cast<float4*>(smem_raw));
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u;
+  uint32_t* const q = reinterpret_cast<uint32_t*>(smem_raw + P.q_offset) + (threadIdx.x >> 5) * kShadowQ;
   const uint32_t n = P.ctrl->count[P.depth + 1];  // entry i of the queue belongs to path i of the next depth's wavefront
   const uint32_t n_units = (n + kUnit - 1) / kUnit;
   uint32_t* const ticket = &P.ctrl->shadow_ctr[P.depth];
+  uint32_t nq = 0;  // warp-uniform: indices waiting in q (< 32 between units)
   for (;;) {
     uint32_t t = 0;
     if (lane == 0) t = atom_add_u32(ticket, 1u);
@@ -948,18 +960,23 @@ __global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_shadow_lin(co
     if (unit0 >= n_units) break;
     const uint32_t unit_end = min(unit0 + kTicketUnits, n_units);
     for (uint32_t u = unit0; u < unit_end; u++) {
+      // the entries of the queue that hold a ray (a path that continued without one left its entry empty) are gathered
+      // until 32 are there: the trace below always runs with a full warp
       const uint32_t idx = u * kUnit + lane;
-      if (idx >= n) continue;
-      const float4 x = __ldcs(P.sq_x + idx);
-      if (__float_as_int(x.z) < 0) continue;  // that path continues without a shadow ray
-      const float4 a = __ldcs(P.in_o + idx), b = __ldcs(P.in_d + idx), c = __ldcs(P.sq_t + idx);
-      const f3 o = mk(a.x, a.y, a.z), wd = mk(b.x, b.y, b.z);
-      Hit h;
-      h.t = INFINITY; h.id = -1; h.p = mk(0, 0, 0); h.ncode = 0;
-      closest_hit_one<true>(P, fs, o, wd, h);
-      shadow_resolve<true>(P, h, wd, mk(c.x, c.y, c.z), c.w, x.x, x.y, __float_as_int(x.z), __float_as_uint(a.w), __float_as_uint(b.w));
+      const bool has = idx < n && __float_as_int(__ldcs(&P.sq_x[idx].z)) >= 0;
+      const uint32_t m = __ballot_sync(0xffffffffu, has);
+      if (has) q[nq + __popc(m & ((1u << lane) - 1u))] = idx;
+      nq += __popc(m);
+      __syncwarp();
+      if (nq >= kUnit) {
+        nq -= kUnit;
+        const uint32_t i2 = q[nq + lane];
+        __syncwarp();
+        shadow_trace_lin(P, fs, i2);
+      }
     }
   }
+  if (lane < nq) shadow_trace_lin(P, fs, q[lane]);
 }
 // Many geoms: the queue goes through the pooled filter traversal like a wavefront of paths (bvh_phase1), then unit by
 // unit through the two-candidate resolution; the few rays that leaves open take the exact traversal on the spot.

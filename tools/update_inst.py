@@ -13,6 +13,8 @@ for r in rows:
     by.setdefault(r[0], {"k": r[4]})[r[-3]] = float(r[-1].replace(",", ""))
 inst, launches, lanes_w = 0.0, 0, 0.0
 for d in by.values():
+    if "k_accum_counts" in d["k"] and launches:
+        break  # one wavefront only: its segment count is what the log line states
     if "k_bounce" in d["k"]:
         inst += d["smsp__inst_executed.sum"]
         lanes_w += d["smsp__inst_executed.sum"] * d["smsp__thread_inst_executed_per_inst_executed.ratio"]

@@ -830,6 +830,7 @@ __device__ __forceinline__ void bvh_phase1(const BounceParams& P, BvhWarpSmem& S
       }
 #endif
       if (ray >= 0 && !filter_step(P.bvh, r, tr, best, cur, st)) {
+        PT_CHECK(base + (uint32_t)ray < P.cap && best.k1 < P.bvh.n_leaves && best.k2 < P.bvh.n_leaves);
         P.bvh_res[base + (uint32_t)ray] = make_float4(best.lo2, best.lo3, __int_as_float(best.k1), __int_as_float(best.k2));
         ray = -1;
       }
@@ -965,6 +966,7 @@ __global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_shadow_lin(co
       const uint32_t idx = u * kUnit + lane;
       const bool has = idx < n && __float_as_int(__ldcs(&P.sq_x[idx].z)) >= 0;
       const uint32_t m = __ballot_sync(0xffffffffu, has);
+      PT_CHECK(nq + __popc(m) <= (uint32_t)kShadowQ);
       if (has) q[nq + __popc(m & ((1u << lane) - 1u))] = idx;
       nq += __popc(m);
       __syncwarp();

@@ -93,7 +93,10 @@ struct pt_context {
   uint32_t band_pixels = 0;  // pixels per wavefront band; 0 = automatic (pt_set_band_pixels)
   // Two wavefronts are in flight at a time, each on its own internal stream with its own path-state buffers and control
   // block: the tail of one wavefront's launch (its last units) overlaps the head of the other's instead of idling SMs.
-  static const int kSlots = 2;
+#ifndef PT_WF_SLOTS
+#define PT_WF_SLOTS 2
+#endif
+  static const int kSlots = PT_WF_SLOTS;
   float4* d_shadow = nullptr;   // direct light sampling: per slot 4 arrays of shadow_cap float4 (the depth's queue of shadow rays)
   uint64_t shadow_cap = 0;      // ... allocated when the first render with direct lighting needs it (ensure_shadow)
   int shadow_slots = 0;
@@ -103,8 +106,8 @@ struct pt_context {
   float4* d_state = nullptr; // per slot (state_bytes): 6 arrays of wf_capacity float4: o0 d0 t0 o1 d1 t1, then wf_capacity float4 (hierarchy results)
   WfCtrl* d_ctrl = nullptr;  // per slot
   int n_slots = kSlots;      // slots in use (1 for frames whose accumulation image alone fills the L2)
-  cudaStream_t wf_stream[kSlots] = {nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {nullptr, nullptr};
+  cudaStream_t wf_stream[kSlots] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {};
   unsigned long long* d_live = nullptr;  // kMaxDepth totals, then fallbacks, then shadow rays
   uint64_t paths_total = 0;
   uint64_t launches = 0;     // kernels of this library launched on behalf of this context
@@ -600,21 +603,28 @@ static HostFilter build_filter(const pt_static_geom* geoms, int n_geoms, double 
         need = (cnt - 1) + deepest;  // the children not taken wait on the stack while the deepest one is walked
         float4* N = &F.nodes[(size_t)me * kBvhNodeRows];
         const float pinf = INFINITY, ninf = -INFINITY;
+        float cf[4];
+        memcpy(cf, child, sizeof(cf));
+        float p1n = 0.0f, p2n = 0.0f;  // (128-byte nodes: the pads of the node = the largest of its children's)
+        for (int i = 0; i < cnt; i++) { p1n = fmaxf(p1n, up(bx[i].p1)); p2n = fmaxf(p2n, up(bx[i].p2 * 1.000002)); }
         for (int h = 0; h < 2; h++) {  // two blocks in the layout child_entries reads: children (0, 1) and (2, 3)
           const int i0 = 2 * h, i1 = 2 * h + 1;
           auto lo = [&](int i, int r) { return i < cnt ? down(bx[i].lo[r]) : pinf; };  // an empty slot: a box nothing enters
           auto hi = [&](int i, int r) { return i < cnt ? up(bx[i].hi[r]) : ninf; };
           auto p1 = [&](int i) { return i < cnt ? up(bx[i].p1) : 0.0f; };
           auto p2 = [&](int i) { return i < cnt ? up(bx[i].p2 * 1.000002) : 0.0f; };  // x 1.000002: rounding of D^2 in child_entries
-          float4* Nh = N + 4 * h;
+          float4* Nh = N + (PT_BVH_NODE128 ? 3 : 4) * h;
           Nh[0] = make_float4(lo(i0, 0), lo(i1, 0), lo(i0, 1), lo(i1, 1));
           Nh[1] = make_float4(lo(i0, 2), lo(i1, 2), hi(i0, 0), hi(i1, 0));
           Nh[2] = make_float4(hi(i0, 1), hi(i1, 1), hi(i0, 2), hi(i1, 2));
-          Nh[3] = make_float4(p1(i0), p1(i1), p2(i0), p2(i1));
+          if (!PT_BVH_NODE128) Nh[3] = make_float4(p1(i0), p1(i1), p2(i0), p2(i1));
         }
-        float cf[4];
-        memcpy(cf, child, sizeof(cf));
-        N[8] = make_float4(cf[0], cf[1], cf[2], cf[3]);
+        if (PT_BVH_NODE128) {
+          N[6] = make_float4(cf[0], cf[1], cf[2], cf[3]);
+          N[7] = make_float4(p1n, p2n, 0.0f, 0.0f);
+        } else {
+          N[8] = make_float4(cf[0], cf[1], cf[2], cf[3]);
+        }
         return me;
       };
       F.root = root_ref >= 0 ? 0 : bvh_leaf_ref(~root_ref, per[~root_ref].cls);

@@ -51,7 +51,12 @@ __device__ unsigned long long g_sp_hist[64];  // [0..39] depth at push; 40 node 
 //   class 2: l0 = (c.xyz, Ew_c)  l1 = (Hc.xyz, Ew_w)  l2 = (Hw.xyz, -)
 //   class 1: l0..l2 = rows x,y,z of inverseTransform  l3 = (R2c, R2w, R2r, Ew_c)  l4 = (Ew_w, -, -, -)
 //   class 3: l0..l2 = rows x,y,z of inverseTransform  l3 = (hc.xyz, Ew_c)  l4 = (hw.xyz, Ew_w)
-constexpr int kBvhNodeRows = 9, kBvhLeafRows = 5;
+#ifndef PT_BVH_NODE128
+#define PT_BVH_NODE128 0  // 1: 8 rows = one 128-byte line per node, the pads P1, P2 kept per NODE.  Measured: 2.60 instead of 2.98 Gseg/s --
+                          // with a 128-byte stride row k of every lane's node falls into the same L1 banks (data pipe 84 % busy instead
+                          // of 70 %); the 144-byte stride staggers them
+#endif
+constexpr int kBvhNodeRows = PT_BVH_NODE128 ? 8 : 9, kBvhLeafRows = 5;
 constexpr int kBvhStack = 128;       // entries of a traversal's stack: the builder checks the collapsed tree's worst case
 constexpr int kBvhBinaryDepth = 40;  // depth limit of the binary tree before the collapse
 // reference of a leaf: ~(leaf index | filter class << kBvhLeafBits)  (< 0; distinct from the two markers below)
@@ -291,9 +296,16 @@ template <bool EXACT, typename Stack>
 __device__ __forceinline__ bool node_visit(const BvhSoA& B, const ScanRay& r, const TravRay& tr, const ScanBest& best, const Hit& h,
                                            int& cur, Stack& st) {
   const float4* N = B.nodes + (size_t)cur * kBvhNodeRows;
+#if PT_BVH_NODE128
+  const float4 a0 = __ldg(N), a1 = __ldg(N + 1), a2 = __ldg(N + 2), b0 = __ldg(N + 3), b1 = __ldg(N + 4), b2 = __ldg(N + 5);
+  const int4 ch = __ldg(reinterpret_cast<const int4*>(N + 6));
+  const float4 pd = __ldg(N + 7);
+  const float4 a3 = make_float4(pd.x, pd.x, pd.y, pd.y), b3 = a3;
+#else
   const float4 a0 = __ldg(N), a1 = __ldg(N + 1), a2 = __ldg(N + 2), a3 = __ldg(N + 3);
   const float4 b0 = __ldg(N + 4), b1 = __ldg(N + 5), b2 = __ldg(N + 6), b3 = __ldg(N + 7);
   const int4 ch = __ldg(reinterpret_cast<const int4*>(N + 8));
+#endif
   return node_rows<EXACT>(a0, a1, a2, a3, b0, b1, b2, b3, ch, r, tr, best, h, cur, st);
 }
 // ... the same with the node's nine rows already fetched
@@ -367,12 +379,20 @@ __device__ __forceinline__ bool filter_step(const BvhSoA& B, const ScanRay& r, c
   const float4* p = at_node ? B.nodes + (size_t)cur * kBvhNodeRows : B.leaves + (size_t)leaf * kBvhLeafRows;
   const float4 z = make_float4(0, 0, 0, 0);
   const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3), q4 = __ldg(p + 4);
-  const float4 q5 = at_node ? __ldg(p + 5) : z, q6 = at_node ? __ldg(p + 6) : z, q7 = at_node ? __ldg(p + 7) : z,
-               q8 = at_node ? __ldg(p + 8) : z;
+  const float4 q5 = at_node ? __ldg(p + 5) : z, q6 = at_node ? __ldg(p + 6) : z, q7 = at_node ? __ldg(p + 7) : z;
+#if !PT_BVH_NODE128
+  const float4 q8 = at_node ? __ldg(p + 8) : z;
+#endif
   const Hit unused{};
   if (at_node) {
+#if PT_BVH_NODE128
+    const int4 ch = make_int4(__float_as_int(q6.x), __float_as_int(q6.y), __float_as_int(q6.z), __float_as_int(q6.w));
+    const float4 pd = make_float4(q7.x, q7.x, q7.y, q7.y);
+    if (node_rows<false>(q0, q1, q2, pd, q3, q4, q5, pd, ch, r, tr, best, unused, cur, st)) return true;
+#else
     const int4 ch = make_int4(__float_as_int(q8.x), __float_as_int(q8.y), __float_as_int(q8.z), __float_as_int(q8.w));
     if (node_rows<false>(q0, q1, q2, q3, q4, q5, q6, q7, ch, r, tr, best, unused, cur, st)) return true;
+#endif
   } else {
     float lo, hi;
     PT_HIST(41);

@@ -122,3 +122,28 @@ def test_same_expected_image_less_noise(pt, sample_scene):
     assert abs(float(out[True][0].mean()) - lum) < 0.02 * lum
     assert out[True][1] < 0.35 * out[False][1], (out[True][1:], out[False][1:])
     assert out[True][2] < out[False][2]  # and the firefly-dominated RMS is at least not worse
+
+
+def test_shadow_queue_follows_scene_and_capacity_changes(pt, oracle, sample_scene):
+    """The shadow-ray queues are sized like the wavefront and served by a different launch in few-geom and hierarchy
+    scenes: one context that switches between the two kinds of scene and changes its wavefront capacity in between must
+    keep producing what fresh contexts produce (two-segment paths: bit-identical to the oracle)."""
+    cam = with_resolution(sample_scene["camera"], 96, 96)
+    g_few, m = lit_scene(pt, sample_scene)
+    light = int(sample_scene["geoms"][8]["materialid"])
+    g_many = random_scene(pt, 66, 7, extent=6.0, smin=0.2, smax=1.5)
+    g_many["materialid"] = np.arange(66) % 5
+    g_many[64] = build_geom(pt, 1, light, (0, 9, 0), (0, 0, 0), (4, 0.3, 4))
+    g_many[65] = build_geom(pt, 0, light, (5, 4, 5), (0, 0, 0), (2, 2, 2))
+    want = {}
+    for name, g in (("few", g_few), ("many", g_many)):
+        want[name], _, _ = oracle.render(oracle.make_scene(g, m, cam, direct_lighting=True), 0, 1, 2, 11)
+    with pt.Context(g_few, m, cam) as c:
+        c.set_direct_lighting(True)
+        for name, g, paths in (("few", g_few, 96 * 96), ("many", g_many, 96 * 96), ("many", g_many, 4 * 96 * 96),
+                               ("few", g_few, 4 * 96 * 96), ("many", g_many, 96 * 96)):
+            c.update_scene(g, m, cam)
+            c.set_wavefront_paths(paths)
+            c.clear()
+            c.render(0, 1, 2, 11)
+            assert same_bits(c.download_sum(), want[name]), (name, paths)

@@ -193,9 +193,9 @@ int pt_intersect_ex(pt_context* ctx, int mode, int n, const float* origin, const
 int pt_set_filter_scale(pt_context* ctx, float scale);
 /* segments of pt_render calls since the last pt_clear whose closest hit took the exact-scan fallback */
 int pt_filter_stats(pt_context* ctx, uint64_t* fallbacks);
-/* scenes with a hierarchy: segments since pt_clear whose best candidate was not confirmed by its exact test but whose
- * closest hit the retry pass settled (a second filter traversal without that candidate + one more exact test) -- they are
- * not counted by pt_filter_stats, which counts the exact traversals */
+/* scenes with a hierarchy: segments (and shadow rays) since pt_clear whose nearest candidate was not confirmed by its exact
+ * test but whose closest hit the exact test of the SECOND candidate settled (the traversal keeps two) -- they are not
+ * counted by pt_filter_stats, which counts the exact traversals */
 int pt_filter_retries(pt_context* ctx, uint64_t* retries);
 
 /* exhaustive check (all 2^32 inputs) of the kernels' single-guard IEEE sqrt, reciprocal and 1/sqrt against the generic

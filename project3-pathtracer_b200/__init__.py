@@ -228,7 +228,7 @@ class Context:
         _check(lib().pt_set_filter_scale(self._h, C.c_float(scale)))
 
     def filter_retries(self):
-        """hierarchy scenes: segments since the last clear() that the retry pass settled (pt_filter_retries)"""
+        """hierarchy scenes: segments since the last clear() that the second candidate's exact test settled (pt_filter_retries)"""
         n = C.c_uint64()
         _check(lib().pt_filter_retries(self._h, C.byref(n)))
         return n.value

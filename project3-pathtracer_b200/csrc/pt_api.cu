@@ -1110,6 +1110,7 @@ static cudaError_t launch_bounce(pt_context* c, int slot, const BounceParams& P,
     if (F) {  // primary rays into the wavefront's input buffers
       const uint32_t blocks = (n_upper + 255u) / 256u, most = (uint32_t)c->sm_count * 8u;
       k_raygen_wf<<<blocks < most ? (blocks ? blocks : 1u) : most, 256, 0, st>>>(P);
+      c->launches++;
     }
     const uint32_t ctas = (n_upper + kPoolMin * (kBvhThreads / 32) - 1) / (kPoolMin * (kBvhThreads / 32));  // a (smallest) pool per warp at least
     if (ctas < grid) grid = ctas ? ctas : 1;
@@ -1166,6 +1167,7 @@ static cudaError_t launch_shadow(pt_context* c, BounceParams P, uint32_t n_upper
     if (ctas < grid) grid = ctas ? ctas : 1;
     k_shadow_lin<<<grid, kBounceThreads, shadow_lin_smem(c->geom_smem), st>>>(P);
   }
+  c->launches++;
   return cudaGetLastError();
 }
 

@@ -163,7 +163,9 @@ def test_every_kernel_path_matches_oracle(pt, oracle, sample_scene, path, scene)
         assert np.allclose(got, want_sum, rtol=2e-6, atol=2e-6)
     else:
         assert same_bits(got, want_sum)
-    assert launches == depth + 2, launches  # one launch per depth, the count fold, the resolve of download_sum
+    # one launch per depth, the count fold, the resolve of download_sum; with direct lighting a shadow launch behind every
+    # depth but the last
+    assert launches == depth + 2 + (depth - 1 if nee else 0), launches
 
 
 def test_small_wavefronts_give_same_image(pt, sample_scene):

@@ -798,12 +798,22 @@ __device__ __forceinline__ void bvh_phase1(const BounceParams& P, BvhWarpSmem& S
             ray = (int)j;
             f3 o, d;
             uint32_t pixel, sample;
-            if (SHADOW && __float_as_int(__ldg(&P.sq_x[base + j].z)) < 0) ray = -1;  // an empty entry: nothing to trace
+            float reach = INFINITY;  // SHADOW: nothing beyond the sampled point of the light can change what the ray decides
+            if (SHADOW) {
+              const float4 x = __ldg(P.sq_x + base + j);
+              if (__float_as_int(x.z) < 0) ray = -1;  // an empty entry: nothing to trace
+              reach = __fmaf_rn(x.x, 1.002f, 2e-3f);
+            }
             if (ray >= 0) {
             load_path(P, base + j, o, d, pixel, sample);
             r = make_scan_ray(o, d, P.filt.r_scene, true);
             tr = make_trav_ray(P.bvh, r);
             scan_init(best);
+            // A shadow ray asks one thing: is its closest hit the light, at the sampled point's distance dy (within
+            // 1e-3 dy + 1e-3)?  A light that is hit is hit no farther than the point sampled on its surface, so geoms whose
+            // bound exceeds dy (1 + 2e-3) + 2e-3 cannot be that hit nor hide it: the traversal treats them like geoms
+            // behind a sure hit.
+            if (SHADOW) best.hi = reach;
             st.sp = 0;
             cur = bvh_root(P.bvh);
             }

@@ -49,7 +49,9 @@ WF_SPP = 50  # samples of the frame per wavefront: 32 M paths, 3.07 GB of path s
 STRONG_SCENE, STRONG_SPP, STRONG_WF_SPP = os.path.join("scenes", "sample_4k.txt"), 16384, 4
 # BASELINE configs[2], [3]: (name, scene file or procedural:n, spp of the config, depth, samples per wavefront)
 EXTRA_CONFIGS = [("cornell_glass_dof_1080p", os.path.join("scenes", "cornell_glass_dof.txt"), 4096, 12, 8),
-                 ("procedural_10k_1080p", "procedural:10000", 1024, 8, 8)]
+                 ("procedural_10k_1080p", "procedural:10000", 1024, 8, 8),
+                 # the headline scene once more, for its direct-light-sampling figure (`direct_light_sampling`)
+                 ("sample_800", os.path.join("scenes", "sample.txt"), 5000, 8, 50)]
 EXTRA_FRACTION = 0.1
 
 
@@ -246,7 +248,8 @@ def strong_leg(pt, sh, torch, dist, rank, world, local, stream, spp_total):
 
 
 def extra_configs(pt, peak):
-    """BASELINE configs[2], [3] at EXTRA_FRACTION of their sample counts (one GPU, device-timed)."""
+    """BASELINE configs[2], [3] (and the headline scene) at EXTRA_FRACTION of their sample counts (one GPU, device-timed),
+    each without and with direct light sampling."""
     out = []
     for name, path, spp_full, depth, wf_spp in EXTRA_CONFIGS:
         try:
@@ -273,11 +276,30 @@ def extra_configs(pt, peak):
                 paths, segs, _ = ctx.counters()
                 fb = ctx.filter_stats()
                 retries = ctx.filter_retries()
+                # the same frame with direct light sampling: shadow rays are traced from a queue by
+                # launches of their own and counted apart from path segments
+                direct = None
+                try:
+                    ctx.set_direct_lighting(True)
+                    ctx.clear()
+                    ctx.render(0, min(spp, wf_spp), depth, SEED)  # warm-up (allocates the shadow queues)
+                    ctx.sync()
+                    ctx.clear()
+                    ctx.render(0, spp, depth, SEED)
+                    ms_d = ctx.last_render_ms()
+                    _, segs_d, _ = ctx.counters()
+                    shadow, n_lights = ctx.shadow_rays()
+                    direct = {"Mseg_per_s": segs_d / ms_d / 1e3, "Mrays_per_s": (segs_d + shadow) / ms_d / 1e3,
+                              "shadow_rays": int(shadow), "lights": int(n_lights), "ms": ms_d,
+                              "cost_vs_paths_only": (ms_d / max(1, segs_d)) / (ms / max(1, segs))}
+                except Exception as e:
+                    direct = {"error": str(e)}
             alg = 96.0 * (segs - paths) + 32.0 * paths
             line = {"name": name, "geoms": int(sc.n_geoms), "resolution": [sc.width, sc.height], "spp": spp,
                     "spp_of_config": spp_full, "depth": depth, "ms": ms, "Mseg_per_s": segs / ms / 1e3,
                     "spp_per_s": spp / (ms * 1e-3), "segments": int(segs), "fallback_fraction": fb / max(1, segs),
                     "retry_fraction": retries / max(1, segs), "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "context_create_s": t_ctx}
+            line["direct_light_sampling"] = direct
             if sc.n_geoms > 32:
                 line["bound"] = "latency / FP32 (hierarchy traversal): the HBM fraction is reported for completeness only"
             out.append(line)

@@ -49,7 +49,7 @@ WF_SPP = 50  # samples of the frame per wavefront: 32 M paths, 3.07 GB of path s
 STRONG_SCENE, STRONG_SPP, STRONG_WF_SPP = os.path.join("scenes", "sample_4k.txt"), 16384, 4
 # BASELINE configs[2], [3]: (name, scene file or procedural:n, spp of the config, depth, samples per wavefront)
 EXTRA_CONFIGS = [("cornell_glass_dof_1080p", os.path.join("scenes", "cornell_glass_dof.txt"), 4096, 12, 8),
-                 ("procedural_10k_1080p", "procedural:10000", 1024, 8, 8),
+                 ("procedural_10k_1080p", "procedural:10000", 1024, 8, 32),
                  # the headline scene once more, for its direct-light-sampling figure (`direct_light_sampling`)
                  ("sample_800", os.path.join("scenes", "sample.txt"), 5000, 8, 50)]
 EXTRA_FRACTION = 0.1

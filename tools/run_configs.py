@@ -24,7 +24,7 @@ CONFIGS = [
     # name, scene file (generated if missing), spp, depth, wavefront spp
     ("config1_sample_800", "scenes/sample.txt", 5000, 8, 50),
     ("config2_cornell_glass_dof_1080p", "scenes/cornell_glass_dof.txt", 4096, 12, 8),
-    ("config3_procedural_10k_1080p", "procedural:10000", 1024, 8, 8),
+    ("config3_procedural_10k_1080p", "procedural:10000", 1024, 8, 32),
     ("config4_sample_4k", "scenes/sample_4k.txt", 16384, 8, 4),
 ]
 
@@ -35,12 +35,14 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_configs.jsonl"))
     ap.add_argument("--png-dir", default=os.path.join(ROOT, "gpurun_out"))
     ap.add_argument("--only", default="")
+    ap.add_argument("--wf-spp", type=int, default=0, help="samples per wavefront (0: the config's own)")
     ap.add_argument("--band", type=int, default=0, help="pixels per wavefront band (pt_set_band_pixels; 0 = automatic)")
     ap.add_argument("--direct", action="store_true", help="direct light sampling on (pt_set_direct_lighting)")
     ap.add_argument("--filter-scale", type=float, default=1.0, help="experiment: scale of the filter's rounding-error bounds")
     args = ap.parse_args()
     lines = []
     for name, path, spp_full, depth, wf_spp in CONFIGS:
+        wf_spp = args.wf_spp or wf_spp
         if args.only and args.only not in name:
             continue
         if path.startswith("procedural:"):

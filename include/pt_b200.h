@@ -207,8 +207,11 @@ int pt_selftest_math(int device, uint64_t bad[3]);
  * allowed segment, one emissive sphere / cube is picked uniformly, one point on it is drawn with
  * getRandomPointOnCube's area-weighted face rule (src/intersections.h:140-172) or the sphere sampler (:179-182),
  * a shadow ray is traced through the same closest hit, and a visible point adds
- * thr * Le * cos cos' / (pi t^2) * area * lights; the continuing path does not add emission if it then reaches a light
- * by itself.  Same expected image, less noise; shadow rays are counted apart from the path segments. */
+ * thr * Le * cos cos' / (pi t^2) * area * lights * w, w = 1 / (1 + G K) (balance heuristic against the direction the bounce
+ * samples itself; G = cos cos' / t^2, K = area * lights / pi); the continuing path weights the emission it meets at its
+ * next hit by the complementary x / (1 + x).  Same expected image, less noise; shadow rays are counted
+ * apart from the path segments.  The shadow rays of a depth are queued (64 bytes each, one queue entry per path of
+ * wavefront capacity, allocated by the first render that needs them) and traced by a launch of their own. */
 int pt_set_direct_lighting(pt_context* ctx, int on);
 /* shadow rays traced by pt_render calls since the last pt_clear; n_lights (may be NULL) = emissive geoms of the scene */
 int pt_shadow_rays(pt_context* ctx, uint64_t* shadow_rays, int* n_lights);

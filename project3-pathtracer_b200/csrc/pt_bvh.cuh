@@ -233,9 +233,8 @@ __device__ __forceinline__ bool can_matter(float e, const TravRay& tr, const Sca
 // the leaf `cur` (< 0): filter test (EXACT: exact test of the candidate if it can still matter)
 template <bool EXACT>
 __device__ __forceinline__ void leaf_visit(const BvhSoA& B, const GeomSoA& g, const ScanRay& r, const TravRay& tr, ScanBest& best, Hit& h,
-                                           int cur, int skip_leaf = -1) {
+                                           int cur) {
   const int leaf = ~cur & ((1 << kBvhLeafBits) - 1), cls = ~cur >> kBvhLeafBits;
-  if (leaf == skip_leaf) return;  // (the retry pass of an unconfirmed candidate leaves that candidate out)
   float lo, hi;
   PT_HIST(41);
   if (leaf_filter(cls, B.leaves + (size_t)leaf * kBvhLeafRows, r, tr.dlu, lo, hi)) {
@@ -353,8 +352,8 @@ __device__ __forceinline__ bool node_rows(const float4 a0, const float4 a1, cons
 // can still matter, result in `h`.  (The builder guarantees that the stack never needs more than kBvhStack entries.)
 template <bool EXACT, typename Stack>
 __device__ __forceinline__ bool trav_step(const BvhSoA& B, const GeomSoA& g, const ScanRay& r, const TravRay& tr, ScanBest& best, Hit& h,
-                                          int& cur, Stack& st, int skip_leaf = -1) {
-  if (cur < 0) leaf_visit<EXACT>(B, g, r, tr, best, h, cur, skip_leaf);
+                                          int& cur, Stack& st) {
+  if (cur < 0) leaf_visit<EXACT>(B, g, r, tr, best, h, cur);
   else if (node_visit<EXACT>(B, r, tr, best, h, cur, st)) return true;
   while (st.sp > 0) {
     const StackEnt ent = st.pop();
@@ -372,8 +371,7 @@ __device__ __forceinline__ bool trav_step(const BvhSoA& B, const GeomSoA& g, con
 // and the leaf's meta word before that), one L2 round trip after the other: 4 400 cycles per step
 // (profiles/r02_bvh_notes.txt).  Returns false when the lane's traversal is finished.
 template <typename Stack>
-__device__ __forceinline__ bool filter_step(const BvhSoA& B, const ScanRay& r, const TravRay& tr, ScanBest& best, int& cur, Stack& st,
-                                            int skip_leaf = -1) {
+__device__ __forceinline__ bool filter_step(const BvhSoA& B, const ScanRay& r, const TravRay& tr, ScanBest& best, int& cur, Stack& st) {
   const bool at_node = cur >= 0;
   const int leaf = ~cur & ((1 << kBvhLeafBits) - 1), cls = ~cur >> kBvhLeafBits;
   const float4* p = at_node ? B.nodes + (size_t)cur * kBvhNodeRows : B.leaves + (size_t)leaf * kBvhLeafRows;
@@ -396,7 +394,7 @@ __device__ __forceinline__ bool filter_step(const BvhSoA& B, const ScanRay& r, c
   } else {
     float lo, hi;
     PT_HIST(41);
-    if (leaf != skip_leaf && leaf_filter_rows(cls, q0, q1, q2, q3, q4, r, tr.dlu, lo, hi)) {  // (skip_leaf: the retry pass)
+    if (leaf_filter_rows(cls, q0, q1, q2, q3, q4, r, tr.dlu, lo, hi)) {
       scan_take3(best, lo, leaf);
       best.hi = fminf(best.hi, hi);  // (NaN is ignored)
     }
@@ -410,21 +408,19 @@ __device__ __forceinline__ bool filter_step(const BvhSoA& B, const ScanRay& r, c
   return false;
 }
 
-// a whole traversal by one lane (parity entry points, the deferred passes)
+// a whole traversal by one lane (parity entry points, the exact traversal of deferred paths)
 template <bool EXACT>
-__device__ __forceinline__ void bvh_traverse(const BvhSoA& B, const GeomSoA& g, const ScanRay& r, ScanBest& best, Hit& h,
-                                             int skip_leaf = -1) {
+__device__ __forceinline__ void bvh_traverse(const BvhSoA& B, const GeomSoA& g, const ScanRay& r, ScanBest& best, Hit& h) {
   if (B.n_leaves <= 0) return;
-  TravRay tr = make_trav_ray(B, r);
-  if (skip_leaf >= 0) tr.dlu = INFINITY;  // the retry pass's resolution (run_deferred) is stated without sure hits
+  const TravRay tr = make_trav_ray(B, r);
   StackEnt ov[kBvhStack];
   TravStack<0> st;
   st.sm = nullptr; st.ov = ov;
   int cur = bvh_root(B);
   if (EXACT) {
-    while (trav_step<true>(B, g, r, tr, best, h, cur, st, skip_leaf)) {}
+    while (trav_step<true>(B, g, r, tr, best, h, cur, st)) {}
   } else {
-    while (filter_step(B, r, tr, best, cur, st, skip_leaf)) {}
+    while (filter_step(B, r, tr, best, cur, st)) {}
   }
 }
 

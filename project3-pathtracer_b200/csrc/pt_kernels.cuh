@@ -651,16 +651,16 @@ __global__ void __launch_bounds__(kQThreads, PT_Q_MIN_BLOCKS) k_bounce_q(const _
 //   a POOL of up to kPool consecutive paths is taken from the wavefront's counter (fewer towards the end of the
 //   wavefront, so that the warps finish together);
 //   phase 1  filter traversal of the pool: every lane walks one ray at a time and, when it is done, takes the next ray
-//            of the pool -- generated (depth 0) or read from the wavefront's buffers right there; lanes are refilled
-//            once kRefillMin of them are idle, so the refill code runs rarely.  The result (k1, lo2) of a ray goes to
-//            shared memory: 8 bytes per ray is all a pool costs, so it can be long -- a pool ends with a tail in which
-//            the last long traversals run alone, and that tail is paid once per pool (pools of 128 rays held in
-//            shared memory: 13.7 of 32 lanes busy; profiles/r02_bvh_notes.txt);
-//   phase 2  unit by unit, all 32 lanes together: the rays once more (generated / read, coalesced this time), exact test
-//            of each path's candidate k1, shading, compaction -- as in k_bounce.  A path whose candidate is not confirmed
-//            (~3 % of the paths) is NOT re-traversed on the spot -- that would occupy the warp with one or two live
-//            lanes for a whole traversal -- but DEFERRED: its index goes to a per-warp list, and whenever 32 have
-//            gathered they are run as a unit of their own through the retry pass (run_deferred).
+//            of the pool, read from the wavefront's buffers right there (depth 0: k_raygen_wf wrote them); lanes are
+//            refilled once kRefillMin of them are idle, so the refill code runs rarely.  The result of a ray -- two
+//            candidate leaves and two bounds, 16 bytes -- goes to HBM: a pool costs no shared memory, so it can be long.
+//            A pool ends with a tail in which the last long traversals run alone, and that tail is paid once per pool
+//            (pools of 128 rays held in shared memory: 43 % of a warp's steps fell into tails; profiles/r02_bvh_notes.txt);
+//   phase 2  unit by unit, all 32 lanes together: the rays once more (coalesced this time), exact test of each path's
+//            candidate k1 and, where that does not settle the path, of k2 (bvh_resolve2), shading, compaction -- as in
+//            k_bounce.  A path that two candidates do not settle (~0.1 %) is NOT traversed exactly on the spot -- that
+//            would occupy the warp with one or two live lanes for a whole traversal -- but DEFERRED: its index goes to a
+//            per-warp list, and whenever 32 have gathered they are run as a unit of their own (run_deferred).
 #ifndef PT_BVH_POOL_UNITS
 #define PT_BVH_POOL_UNITS 32
 #endif
@@ -716,7 +716,7 @@ __device__ __forceinline__ void load_path(const BounceParams& P, uint32_t idx, f
   d = mk(b.x, b.y, b.z); sample = __float_as_uint(b.w);
 }
 
-// shading + compaction of one unit of k_bounce_bvh: ONE copy of the code for the pool's units and the retry pass's units
+// shading + compaction of one unit of k_bounce_bvh: ONE copy of the code for the pool's units and the deferred units
 // (the kernel's instruction footprint is what its warps wait for at depth 0: profiles/r02_bvh_notes.txt)
 #ifndef PT_BVH_TABLE
 #define PT_BVH_TABLE 0  // normals, tangent frames and the material row from the per-geom table, as in the few-geom kernels

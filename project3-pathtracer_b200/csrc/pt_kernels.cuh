@@ -1,6 +1,7 @@
 // pt_kernels.cuh -- the wavefront kernels (sm_100a).
 //
-//   k_bounce<FIRST,LAST,NEE>  (k_bounce_bvh for scenes with many geoms) one path segment for every live path of the wavefront, fused:
+//   k_bounce<FIRST,LAST,NEE>  one path segment for every live path of the wavefront, fused (few geoms: depth 0, and every depth
+//                           of scenes that keep nearly all their paths alive):
 //                           [FIRST: raygen + depth of field]  (raycastFromCameraKernel, src/raytraceKernel.cu:40-45)
 //                           closest hit over SoA geometry staged in shared memory (src/intersections.h:74-117)
 //                           BSDF sampling with Philox (calculateBSDF, src/interactions.h:99-104), absorption inside glass
@@ -11,6 +12,12 @@
 //                           buffer.
 //                         Persistent CTAs; warps take units from a ticket counter and never wait for each other; the
 //                         live count never visits the host.
+//   k_bounce_q<LAST,NEE>    depths >= 1 of few-geom scenes: the same segment with its second half (exact test of the filter's
+//                         candidate, shading, compaction) re-batched by winner type in per-warp shared-memory queues
+//   k_raygen_wf + k_bounce_bvh<LAST,NEE>   scenes with many geoms: primary rays into the wavefront's buffers, then one kernel
+//                         for every depth -- pooled traversal of the hierarchy (pt_bvh.cuh) with lane refill, exact
+//                         tests and shading unit by unit
+//   k_shadow_lin / k_shadow_bvh   direct light sampling: the shadow rays a depth queued, traced by a launch of their own
 //   k_raygen_list / k_intersect_list   the same device functions on caller-supplied lists (parity entry points)
 //   k_compact_u32                      the stable compaction primitive on its own: ballot -> block scan -> decoupled look-back
 //   k_points_on_geom / k_sphere_dirs / k_transmission (pt_sampling.cuh)   sampling and absorption parity entry points

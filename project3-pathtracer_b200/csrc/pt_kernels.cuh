@@ -977,11 +977,20 @@ __global__ void __launch_bounds__(kBounceThreads, PT_MIN_BLOCKS) k_shadow_lin(co
     const uint32_t unit0 = __shfl_sync(0xffffffffu, t, 0) * kTicketUnits;
     if (unit0 >= n_units) break;
     const uint32_t unit_end = min(unit0 + kTicketUnits, n_units);
+    // (the ticket's flags are requested together: one wait for HBM per ticket instead of one per unit)
+    uint32_t has_bits = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kTicketUnits; k++) {
+      const uint32_t idx = (unit0 + k) * kUnit + lane;
+      const int gl = idx < n ? __float_as_int(__ldcs(&P.sq_x[idx].z)) : -1;
+      has_bits |= (gl >= 0 ? 1u : 0u) << k;
+    }
+#pragma unroll 1
     for (uint32_t u = unit0; u < unit_end; u++) {
       // the entries of the queue that hold a ray (a path that continued without one left its entry empty) are gathered
       // until 32 are there: the trace below always runs with a full warp
       const uint32_t idx = u * kUnit + lane;
-      const bool has = idx < n && __float_as_int(__ldcs(&P.sq_x[idx].z)) >= 0;
+      const bool has = (has_bits >> (u - unit0)) & 1u;
       const uint32_t m = __ballot_sync(0xffffffffu, has);
       PT_CHECK(nq + __popc(m) <= (uint32_t)kShadowQ);
       if (has) q[nq + __popc(m & ((1u << lane) - 1u))] = idx;
